@@ -1,0 +1,251 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE ONLY - generate tests/golden/*.npz from the UNMODIFIED reference.
+
+Runs in the dev container only (needs /root/reference).  Imports the reference through
+``oracle/refshim.py`` and records, at full float64 precision, the outputs of its public
+API on seeded inputs.  The committed .npz files pin the oracle (``oracle/ccf_oracle.py``)
+and, through it and directly, the CUDA path.
+
+    python oracle/make_golden.py            # rewrites every tests/golden/*.npz
+
+Inputs are the reference's own HDF5 files and YAML configs, read where they lie.
+"""
+import copy
+import os
+import sys
+
+import numpy as np
+import scipy
+import yaml
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+import refshim  # noqa: E402
+
+REF = "/root/reference"
+OUT = os.path.join(ROOT, "tests", "golden")
+SEED = 20251018  # same stream as bench.py / SURVEY 8(d)
+PARAM_COLS = ("fsigma8", "beta", "sigma_v", "aperp", "apar")
+
+
+def synthetic_batch(n, seed=SEED):
+    """Prior-box parameter rows, columns PARAM_COLS."""
+    rng = np.random.default_rng(seed)
+    P = np.empty((n, 5))
+    P[:, 0] = rng.uniform(0.05, 1.5, n)
+    P[:, 1] = rng.uniform(0.2, 0.6, n)
+    P[:, 2] = rng.uniform(100.0, 500.0, n)
+    P[:, 3] = rng.uniform(0.9, 1.1, n)
+    P[:, 4] = rng.uniform(0.9, 1.1, n)
+    return P
+
+
+def row_to_params(row):
+    return {k: float(v) for k, v in zip(PARAM_COLS, row)}
+
+
+def meta():
+    return dict(scipy_version=scipy.__version__, numpy_version=np.__version__,
+                reference="seshnadathur/victor 0.1.4 (unmodified, via oracle/refshim.py)")
+
+
+def boss_blocks(config="config/boss_config.yaml"):
+    with open(os.path.join(REF, config)) as fh:
+        info = yaml.full_load(fh)
+    if "likelihood" in info:  # cobaya-style file
+        blk = info["likelihood"]["CCFLikelihood"]
+        model, data = blk["model"], blk["data"]
+    else:
+        model, data = info["model"], info["data"]
+    model["dir"] = data["dir"] = REF
+    return model, data
+
+
+def edge_rows(beta_grid):
+    """Hand-picked rows: grid nodes, outside-grid beta, prior corners (SURVEY 4 tier 2)."""
+    rows = [
+        [0.47, 0.37, 380.0, 1.0, 1.0],
+        [0.47, float(beta_grid[5]), 380.0, 1.0, 1.0],      # exactly on a grid node
+        [0.47, float(beta_grid[0]), 380.0, 1.0, 1.0],      # first node
+        [0.47, float(beta_grid[-1]), 380.0, 1.0, 1.0],     # last node
+        [0.47, 0.12, 380.0, 1.0, 1.0],                     # below the grid (PCHIP extrapolates)
+        [0.47, 0.70, 380.0, 1.0, 1.0],                     # above the grid
+        [0.47, float(beta_grid[7]) + 1e-9, 380.0, 1.0, 1.0],
+        [0.47, float(beta_grid[7]) - 1e-9, 380.0, 1.0, 1.0],
+        [0.05, 0.2, 100.0, 0.8, 1.2],
+        [1.5, 0.6, 500.0, 1.2, 0.8],
+        [1.5, 0.2, 100.0, 1.2, 1.2],
+        [0.05, 0.6, 500.0, 0.8, 0.8],
+        [0.47, 0.37, 60.0, 1.0, 1.0],                      # narrow pdf: under-resolved integral
+        [0.47, 0.37, 800.0, 1.0, 1.0],                     # wide pdf: r -> 0 crossings
+        [0.0, 0.37, 380.0, 1.0, 1.0],                      # no coherent outflow
+        [0.47, 0.37, 380.0, 1.02, 0.97],
+    ]
+    return np.array(rows)
+
+
+def run_points(ccf, P, **kw):
+    n = len(P)
+    p = len(ccf.s) * len(ccf.poles_s)
+    theory = np.empty((n, p))
+    chi2 = np.empty(n)
+    lnl = np.empty(n)
+    for i, row in enumerate(P):
+        params = row_to_params(row)
+        theory[i] = ccf.theory_multipole_vector(ccf.s, params, ccf.poles_s, **kw)
+        lnl[i], chi2[i] = ccf.log_likelihood(params, **kw)
+    return theory, chi2, lnl
+
+
+def golden_boss(victor):
+    model, data = boss_blocks()
+    ccf = victor.CCFFit(copy.deepcopy(model), copy.deepcopy(data))
+
+    # (1) notebook cell 22 anchors: epsilon-style parameters and the option variants
+    p0 = {"fsigma8": 0.47, "beta": 0.37, "sigma_v": 380, "epsilon": 1.0}
+    variants = [("streaming", {}), ("dispersion", {"rsd_model": "dispersion"}),
+                ("kaiser", {"rsd_model": "kaiser"}), ("anisotropic", {"assume_isotropic": False}),
+                ("likelihood_interp", {"beta_interpolation": "likelihood"})]
+    anchors = {}
+    for name, kw in variants:
+        lnl, c2 = ccf.log_likelihood(dict(p0), **kw)
+        anchors[f"{name}_lnl"], anchors[f"{name}_chi2"] = lnl, c2
+        if "beta_interpolation" not in kw:
+            anchors[f"{name}_theory"] = ccf.theory_multipole_vector(ccf.s, dict(p0), ccf.poles_s, **kw)
+    cov = ccf.get_interpolated_covariance(0.37)
+    anchors["slogdet_cov"] = np.linalg.slogdet(cov)[1]
+    anchors["data_vector"] = ccf.multipole_datavector(0.37)
+    np.savez(os.path.join(OUT, "boss_notebook_anchors.npz"), **anchors, **meta())
+
+    # (2) host-table level quantities
+    r31 = np.append([0.01], ccf.r)
+    tables = dict(iaH=ccf.iaH, r=ccf.r, s=ccf.s, beta=ccf.beta, sv_rmu=ccf.sv_rmu,
+                  r_for_sv=ccf.r_for_sv, mu_for_sv=ccf.mu_for_sv,
+                  delta_r31=ccf.delta(r31), Delta_r31=ccf.integrated_delta(r31),
+                  icov_first=ccf.icov[0], icov_last=ccf.icov[-1],
+                  xi_r_beta037=ccf.get_interpolated_real_multipoles(0.37))
+    np.savez(os.path.join(OUT, "boss_tables.npz"), **tables, **meta())
+
+    # (3) seeded batch rows (the first rows of the bench batch) + edge rows, streaming
+    P = np.vstack([synthetic_batch(65536)[:64], edge_rows(ccf.beta)])
+    theory, chi2, lnl = run_points(ccf, P)
+    np.savez(os.path.join(OUT, "boss_streaming_points.npz"), params=P, theory=theory, chi2=chi2,
+             lnl=lnl, param_cols=np.array(PARAM_COLS), **meta())
+
+    # (4) epsilon / alpha parameterisation and theory_xi on the model grid
+    eps_rows = np.array([[0.47, 0.37, 380.0, 1.0, 1.0], [0.6, 0.45, 300.0, 0.95, 1.01],
+                         [0.3, 0.25, 450.0, 1.08, 0.98]])  # fsigma8, beta, sigma_v, epsilon, alpha
+    eth, ec2, elnl, exi = [], [], [], []
+    mu = np.linspace(0, 1, 100)
+    for row in eps_rows:
+        pr = dict(fsigma8=row[0], beta=row[1], sigma_v=row[2], epsilon=row[3], alpha=row[4])
+        eth.append(ccf.theory_multipole_vector(ccf.s, dict(pr), ccf.poles_s))
+        a, b = ccf.log_likelihood(dict(pr))
+        elnl.append(a)
+        ec2.append(b)
+        exi.append(ccf.theory_xi(*np.meshgrid(ccf.s, mu), dict(pr)))
+    np.savez(os.path.join(OUT, "boss_epsilon_points.npz"), params=eps_rows, theory=np.array(eth),
+             chi2=np.array(ec2), lnl=np.array(elnl), xi_smu=np.array(exi), mu=mu, **meta())
+
+    # (5) next-row variants on a few seeded rows
+    Pv = np.vstack([P[:6], edge_rows(ccf.beta)[[0, 4, 5, 8, 9]]])
+    out = dict(params=Pv)
+    for name, kw in variants[1:4]:
+        th, c2, ll = run_points(ccf, Pv, **kw)
+        out[f"{name}_theory"], out[f"{name}_chi2"], out[f"{name}_lnl"] = th, c2, ll
+    c2l, lll = [], []
+    for row in Pv:
+        if not (ccf.beta_ccf[0] < row[1] <= ccf.beta_ccf[-1]):
+            c2l.append(np.nan)
+            lll.append(np.nan)
+            continue
+        a, b = ccf.log_likelihood(row_to_params(row), beta_interpolation="likelihood")
+        lll.append(a)
+        c2l.append(b)
+    out["likelihood_interp_chi2"], out["likelihood_interp_lnl"] = np.array(c2l), np.array(lll)
+    np.savez(os.path.join(OUT, "boss_variant_points.npz"), **out, **meta())
+
+    # (6) likelihood forms and the fixed-covariance path
+    forms = {}
+    for form in ("gaussian", "hartlap", "percival", "sellentin"):
+        like = {"form": form, "nmocks": 1000, "nparams": 4}
+        vals = [ccf.log_likelihood(row_to_params(r), likelihood=like) for r in P[:4]]
+        forms[f"{form}_lnl"] = np.array([v[0] for v in vals])
+        forms[f"{form}_chi2"] = np.array([v[1] for v in vals])
+    dfix = copy.deepcopy(data)
+    dfix["covariance_matrix"] = {
+        "data_file": "data/BOSS_DR12_CMASS_data/CMASS_zobovVoids_reconRs10_0.43z0.7_medianRvcut_fixed_D_covariance.hdf5",
+        "cov_key": "covmat", "fixed_beta": True}
+    cfix = victor.CCFFit(copy.deepcopy(model), dfix)
+    vals = [cfix.log_likelihood(row_to_params(r)) for r in P[:4]]
+    forms["fixedcov_lnl"] = np.array([v[0] for v in vals])
+    forms["fixedcov_chi2"] = np.array([v[1] for v in vals])
+    forms["params"] = P[:4]
+    np.savez(os.path.join(OUT, "boss_forms.npz"), **forms, **meta())
+
+    # (7) cobaya-config likelihood block (velocity_independent_of_AP defaults True, astar)
+    cm, cd = boss_blocks("config/boss_cobaya_config.yaml")
+    cc = victor.CCFFit(cm, cd)
+    rows = np.array([[0.47, 0.37, 380.0, 1.0, 1.0], [0.55, 0.41, 350.0, 1.03, 1.0],
+                     [0.40, 0.33, 420.0, 0.97, 1.02]])  # fsigma8, beta, sigma_v, epsilon, astar
+    th, c2, ll = [], [], []
+    for row in rows:
+        pr = dict(fsigma8=row[0], beta=row[1], sigma_v=row[2], epsilon=row[3], alpha=1, astar=row[4],
+                  b=1.9, Av=0, M=1, Q=1)
+        th.append(cc.theory_multipole_vector(cc.s, dict(pr), cc.poles_s))
+        a, b = cc.log_likelihood(dict(pr))
+        ll.append(a)
+        c2.append(b)
+    np.savez(os.path.join(OUT, "boss_cobaya_block.npz"), params=rows, theory=np.array(th),
+             chi2=np.array(c2), lnl=np.array(ll), **meta())
+
+    # (8) measured real-space model + MD covariance ("from_data" coordinates), anisotropic
+    mm = copy.deepcopy(model)
+    mm["input_model_data_file"] = ("data/BOSS_DR12_CMASS_data/"
+                                   "CMASS_zobovVoids_reconRs10_0.43z0.7_medianRvcut_measured_model.hdf5")
+    mm["realspace_ccf"]["from_data"] = True
+    dm = copy.deepcopy(data)
+    dm["covariance_matrix"]["data_file"] = (
+        "data/BOSS_DR12_CMASS_data/"
+        "CMASS_zobovVoids_reconRs10_0.43z0.7_medianRvcut_variable_isotropic_MD_covariance.hdf5")
+    cmd = victor.CCFFit(mm, dm)
+    Pm = P[:4].copy()
+    Pm[:, 1] = np.clip(Pm[:, 1], 0.25, 0.55)
+    th, c2, ll = run_points(cmd, Pm)
+    np.savez(os.path.join(OUT, "boss_measured_model.npz"), params=Pm, theory=th, chi2=c2, lnl=ll,
+             beta_covmat=cmd.beta_covmat, **meta())
+
+
+def golden_example(victor):
+    with open(os.path.join(REF, "config/example_model_input.yaml")) as fh:
+        model = yaml.full_load(fh)["model"]
+    model["dir"] = REF
+    ccf = victor.CCFModel(model)
+    s = np.linspace(0.01, 3, 100)
+    rows = np.array([[0.47, 7.0, 1.0], [0.3, 4.0, 0.97], [0.7, 10.0, 1.04]])  # fsigma8, sigma_v, epsilon
+    out = dict(params=rows, s=s, iaH=ccf.iaH, r=ccf.r, sv_rmu=ccf.sv_rmu, r_for_sv=ccf.r_for_sv)
+    for name, kw in (("streaming", {}), ("dispersion", {"rsd_model": "dispersion"}),
+                     ("kaiser", {"rsd_model": "kaiser"})):
+        th = []
+        for row in rows:
+            pr = dict(fsigma8=row[0], sigma_v=row[1], epsilon=row[2])
+            th.append(ccf.theory_multipole_vector(s, pr, [0, 2, 4], **kw))
+        out[f"{name}_theory"] = np.array(th)
+    # model-grid evaluation as well (s = r grid, poles 0,2)
+    th = []
+    for row in rows:
+        pr = dict(fsigma8=row[0], sigma_v=row[1], epsilon=row[2])
+        th.append(ccf.theory_multipole_vector(ccf.r, pr, [0, 2]))
+    out["streaming_theory_rgrid"] = np.array(th)
+    np.savez(os.path.join(OUT, "example_points.npz"), **out, **meta())
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    v = refshim.install(REF)
+    golden_boss(v)
+    golden_example(v)
+    for fn in sorted(os.listdir(OUT)):
+        print(fn, os.path.getsize(os.path.join(OUT, fn)))
