@@ -1,0 +1,155 @@
+/*
+ * victor_b200.h - C ABI of the B200-native likelihood hot path of seshnadathur/victor.
+ *
+ * The reference is pure Python; it has no FFI of its own.  The entry points below are what a
+ * binding for this path replaces, one call per public reference method:
+ *
+ *   vb200_create      <- CCFModel.__init__ / CCFFit.__init__ state hand-over
+ *                        (victor/ccf_model.py:33-97, victor/ccf_fit.py:15-42): the host-built
+ *                        spline / template / covariance tables are deep-copied to one GPU.
+ *   vb200_theory      <- CCFModel.theory_xi            (victor/ccf_model.py:538-789)
+ *                        CCFModel.theory_multipoles     (victor/ccf_model.py:791-827,
+ *                                                        victor/utils.py:9-58)
+ *                        CCFModel.theory_multipole_vector (victor/ccf_model.py:829-860)
+ *                        on caller-supplied s / mu grids, for n parameter rows at once.
+ *   vb200_likelihood  <- CCFFit.chi_squared / CCFFit.log_likelihood
+ *                        (victor/ccf_fit.py:325-354, 356-483) and, through them,
+ *                        CCFLikelihood.calculate (victor/likelihoods/CCFLikelihood.py:32-42),
+ *                        on the data's own s grid, for n parameter rows at once.
+ *
+ * Conventions
+ *   - All floating point is IEEE float64.  Arrays are C-contiguous, row-major.
+ *   - Every function returns 0 on success or a negative VB200_E* code; the message is
+ *     available from vb200_last_error() (thread-local).  Nothing throws across the ABI.
+ *   - `params`, and every output pointer, may be a HOST pointer or a DEVICE pointer (memory of
+ *     the context's GPU); the library detects which.  Host buffers are staged through device
+ *     scratch with the copies inside the call, and the call returns after the results are in
+ *     the host buffers.  With device pointers only, the call is asynchronous on `stream`
+ *     (a cudaStream_t, or NULL for the legacy default stream) and the caller synchronises.
+ *   - A context belongs to one GPU and is not re-entrant; distinct contexts are independent.
+ *   - Per-row numerical failure (NaN anywhere in the row) gives lnlike = -inf, chi2 = +inf,
+ *     as the reference does (victor/ccf_fit.py:477-481).
+ */
+#ifndef VICTOR_B200_H
+#define VICTOR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VB200_NPAR 8 /* columns of a parameter row, in this order: */
+enum { VB200_P_FSIGMA8 = 0, VB200_P_BETA, VB200_P_SIGMA_V, VB200_P_APERP, VB200_P_APAR,
+       VB200_P_ASTAR, VB200_P_M, VB200_P_Q };
+
+enum { VB200_OK = 0, VB200_EINVAL = -1, VB200_ECUDA = -2, VB200_ENOMEM = -3, VB200_EUNSUPPORTED = -4 };
+
+enum { VB200_RSD_STREAMING = 0, VB200_RSD_DISPERSION = 1, VB200_RSD_KAISER = 2 };
+enum { VB200_LIKE_LINEAR = 0, VB200_LIKE_LOG = 1 };
+
+#define VB200_MAX_POLES 3
+
+/* Model half (CCFModel).  Radial tables live on one common cell set in the template
+ * coordinate u = r / f: ncell cells, cell c covering [upper[c-1], upper[c]), cell 0 open to
+ * the left, the last cell open to the right; `origin[c]` is the local-coordinate origin of
+ * cell c; every cubic is c0 + c1 t + c2 t^2 + c3 t^3 with t = u - origin[cell].  A uniform
+ * bucket grid (spacing 1 / inv_h, first bucket at u = 0) gives the first candidate cell;
+ * at most `maxscan` upward steps follow. */
+typedef struct vb200_model_tables {
+    double iaH;               /* (1 + z_eff) / (100 E(z_eff)), ccf_model.py:45 */
+    double template_sigma8;   /* ccf_model.py:187 */
+    double beta_fixed;        /* beta used when the real-space input has no beta dependence (:585) */
+    double inv_h;
+    int32_t vel_indep_AP;     /* model['velocity_independent_of_AP'] (:606) */
+    int32_t rsd_model;        /* VB200_RSD_* */
+    int32_t n_ell;            /* real-space multipoles in xi(r, mu_r): 1 = assume_isotropic */
+    int32_t ells[VB200_MAX_POLES];
+    int32_t beta_dependent;   /* real-space input depends on reconstruction beta */
+    int32_t ncell, nbucket, maxscan;
+    int32_t nbeta;            /* length of beta_grid (>= 2) */
+    int32_t nx;               /* velocity nodes */
+    int32_t nresc;            /* nodes of the AP rescaling trapezoid (:609-610) */
+    const double *origin;     /* [ncell] */
+    const double *upper;      /* [ncell], last = +inf */
+    const int32_t *bucket_base; /* [nbucket] */
+    const double *beta_grid;  /* [nbeta] */
+    const double *xi_tab;     /* [n_ell][nbeta-1][4 powers of (beta-beta_k)][ncell][4] */
+    const double *v0;         /* [ncell][4]  spline of r * Delta(r)               (:449, 635) */
+    const double *d0;         /* [ncell][4]  spline of 3 (delta - 2 Delta / 3)    (:450, 636) */
+    const double *sv;         /* [ncell][4]  normalised sigma_v(r) template       (:654) */
+    const double *x;          /* [nx] linspace(-6, 6) (:570) */
+    const double *wx;         /* [nx] Simpson weights / sqrt(2 pi) (:690, :656) */
+    const double *mu_resc;    /* [nresc] */
+    const double *w_resc;     /* [nresc] trapezoid weights */
+} vb200_model_tables;
+
+/* Likelihood half (CCFFit); pass NULL to vb200_create for a model-only context. */
+typedef struct vb200_fit_tables {
+    int32_t ns;               /* length of the data s grid */
+    int32_t npoles;           /* multipoles in the data vector; p = npoles * ns */
+    int32_t nmu;              /* mu nodes of the projection (100) */
+    int32_t data_beta_dependent;
+    int32_t nbeta_ccf;        /* >= 2 */
+    int32_t cov_fixed;
+    int32_t nbeta_cov;        /* >= 1 */
+    int32_t like_kind;        /* VB200_LIKE_* */
+    int32_t use_logdet;
+    double like_a;            /* LINEAR: lnL = -a chi2 / 2 + norm;  LOG: lnL = -a log(1 + chi2 / nm1) / 2 + norm */
+    double like_nm1;
+    const double *s;          /* [ns] */
+    const double *mu;         /* [nmu] */
+    const double *wmu;        /* [npoles][nmu] projection weights */
+    const double *beta_ccf;   /* [nbeta_ccf] */
+    const double *data_tab;   /* [nbeta_ccf-1][4][p] PCHIP power table of the data vector */
+    const double *beta_cov;   /* [nbeta_cov] */
+    const double *icov;       /* [nbeta_cov][p][p] */
+    const double *logdet;     /* [nbeta_cov] log det of each covariance */
+    const double *lam;        /* [nbeta_cov][p] generalised eigenvalues of (cov[last], cov[i]) */
+} vb200_fit_tables;
+
+typedef struct vb200_ctx vb200_ctx;
+
+const char *vb200_version(void);
+/* 0 when the caller's view of the two table structs has the library's sizes (binding self-check). */
+int vb200_abi_check(int64_t sizeof_model_tables, int64_t sizeof_fit_tables);
+const char *vb200_last_error(void);
+int vb200_device_count(void);
+
+int vb200_create(const vb200_model_tables *model, const vb200_fit_tables *fit, int device, vb200_ctx **out);
+void vb200_destroy(vb200_ctx *ctx);
+
+/* Kernel variant switches (integers): "fast_math" (1 = hand-rolled rsqrt / rcp / exp, default;
+ * 0 = CUDA libm), "nsplit" (blocks per parameter row; 0 = automatic), "threads" (block size). */
+int vb200_set_option(vb200_ctx *ctx, const char *key, int64_t value);
+
+/* xi(s, mu) and / or its projections for n parameter rows.
+ *   params [n][VB200_NPAR]; s [ns], mu [nmu], wmu [L][nmu] are HOST arrays (copied per call);
+ *   xi_out [n][nmu][ns] or NULL; mult_out [n][L][ns] or NULL (requires wmu). */
+int vb200_theory(vb200_ctx *ctx, const double *params, int64_t n,
+                 const double *s, int32_t ns, const double *mu, int32_t nmu,
+                 const double *wmu, int32_t L,
+                 double *xi_out, double *mult_out, void *stream);
+
+/* Theory vector, chi-square and log-likelihood for n parameter rows on the fit's own grids.
+ *   theory [n][p] or NULL; chi2 [n] or NULL; lnlike [n] or NULL. */
+int vb200_likelihood(vb200_ctx *ctx, const double *params, int64_t n,
+                     double *theory, double *chi2, double *lnlike, void *stream);
+
+int vb200_synchronize(vb200_ctx *ctx);
+
+/* Kernel launches issued by this context so far (for bench.py's gpu_launches). */
+int64_t vb200_launch_count(const vb200_ctx *ctx);
+
+/* Device self-test of the hand-rolled math: out[0..n) = 2^(-x) * 1 via the fast exp path,
+ * out[n..2n) = fast 1/sqrt(x), out[2n..3n) = fast 1/x, for n HOST inputs x > 0. */
+int vb200_math_selftest(int device, const double *x, int64_t n, double *out);
+
+/* FP64 FMA issue-rate probe (8 independent DFMA chains per thread, whole GPU): the measured
+ * roofline denominator for this FP64-CUDA-core-bound path.  tflops counts 2 flop per FMA. */
+int vb200_fp64_peak(int device, int iters, double *tflops, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VICTOR_B200_H */

@@ -1,0 +1,163 @@
+"""TEST INFRASTRUCTURE ONLY - numpy walk-through of the table-driven algorithm the kernels use.
+
+Consumes the packed tables the product builds on the host (``victor_b200.tables``) and
+evaluates them with plain numpy, batched over parameter rows.  It is the bridge between the
+per-point scipy oracle (``oracle/ccf_oracle.py``, 0.13-0.25 s per point) and the CUDA kernels:
+it checks the host tables and the restructured algebra on the CPU at sizes the scipy oracle
+cannot reach, and it is the CPU reference for configurations the reference has no knob for
+(dense mu / velocity grids).  Never imported by the product.
+
+Algebra (reference lines in victor/ccf_model.py):
+    u-units: everything radial is divided by the template rescaling factor f (:606-613)
+    S_perp = s sqrt(1-mu^2) aperp / f,  S_par = s mu apar / f                    (:642-643)
+    R_par = S_par - x_m sigma_v iaH apar / f ;  u = sqrt(S_perp^2 + R_par^2)      (:648-651)
+    mu_r = R_par / u                                                              (:652)
+    z = (x_m - (A_v / sigma_v) V0(u) mu_r) / SV(u),  A_v = -(fs8/s8_t) / (3 iaH apar)
+    xi(s, mu) = sum_m wx_m (1 + xi_r(u)) exp(-z^2/2) / SV(u) - 1                  (:654-656, 690)
+    xi_l(s) = sum_k W_l[k] xi(s, mu_k)                                            (:824-825)
+"""
+import numpy as np
+
+from victor_b200 import tables as T
+
+
+def _cells(mt, u):
+    """Cell index and local coordinate for every u (bucket lookup + bounded scan)."""
+    b = np.floor(u * mt.inv_h)
+    b = np.clip(np.nan_to_num(b, nan=0.0), 0, len(mt.bucket_base) - 1).astype(np.int64)
+    cell = mt.bucket_base[b].astype(np.int64)
+    for _ in range(mt.maxscan):
+        cell = cell + (u >= mt.upper[cell])
+    return cell, u - mt.origin[cell]
+
+
+def _horner(c, cell, t):
+    k = c[cell]
+    return ((k[..., 3] * t + k[..., 2]) * t + k[..., 1]) * t + k[..., 0]
+
+
+def _beta_interval(grid, beta):
+    k = np.searchsorted(grid, beta, side="right") - 1
+    k = np.clip(k, 0, len(grid) - 2)
+    return k, beta - grid[k]
+
+
+def point_scalars(mt, rows):
+    fs8, beta, sig, aperp, apar, astar = (rows[:, i] for i in range(6))
+    eps = aperp / apar
+    iaHt = mt.iaH * apar
+    if mt.vel_indep_AP:
+        f = astar.copy()
+    else:
+        y = apar[:, None] * np.sqrt(1 + (1 - mt.mu_resc[None, :] ** 2) * (eps[:, None] ** 2 - 1))
+        f = (y * mt.w_resc[None, :]).sum(axis=1)
+    Av = -(fs8 / mt.template_sigma8) / (3 * iaHt)
+    return dict(eps=eps, iaHt=iaHt, f=f, Av=Av)
+
+
+def xi_cells(mt, beta):
+    """Per-row xi_l cell coefficients [n][n_ell][ncell][4] from the beta power table."""
+    n = len(beta)
+    if mt.beta_dependent:
+        k, t = _beta_interval(mt.beta_grid, beta)
+    else:
+        k, t = np.zeros(n, dtype=np.int64), np.zeros(n)
+    tab = mt.xi_tab[:, k]                       # [n_ell][n][4][ncell][4]
+    tt = t[None, :, None, None]
+    c = ((tab[:, :, 3] * tt + tab[:, :, 2]) * tt + tab[:, :, 1]) * tt + tab[:, :, 0]
+    return np.moveaxis(c, 0, 1)                 # [n][n_ell][ncell][4]
+
+
+def theory_xi(mt, rows, s, mu, chunk=32):
+    """xi(s, mu) for each row: [n][nmu][ns].  Streaming model, isotropic template dispersion."""
+    if mt.rsd_model != T.RSD_STREAMING:
+        raise NotImplementedError("table_emul: streaming model only")
+    rows = np.asarray(rows, float)
+    n = len(rows)
+    out = np.empty((n, len(mu), len(s)))
+    sq = np.sqrt(1 - mu ** 2)
+    for a in range(0, n, chunk):
+        R = rows[a:a + chunk]
+        sc = point_scalars(mt, R)
+        sig = R[:, 2]
+        beta = R[:, 1] if mt.beta_dependent else np.full(len(R), mt.beta_fixed)
+        xc = xi_cells(mt, beta)                                    # [c][n_ell][ncell][4]
+        Sperp = s[None, None, :] * sq[None, :, None] * (R[:, 3] / sc["f"])[:, None, None]
+        Spar = s[None, None, :] * mu[None, :, None] * (R[:, 4] / sc["f"])[:, None, None]
+        cm = mt.x[None, :] * (sig * sc["iaHt"] / sc["f"])[:, None]   # [c][nx]
+        Rpar = Spar[..., None] - cm[:, None, None, :]
+        u2 = Sperp[..., None] ** 2 + Rpar ** 2
+        with np.errstate(invalid="ignore", divide="ignore"):
+            u = np.sqrt(u2)
+            mur = Rpar / u
+        cell, t = _cells(mt, u)
+        svv = _horner(mt.sv, cell, t)
+        v0 = _horner(mt.v0, cell, t)
+        B = (sc["Av"] / sig)[:, None, None, None]
+        z = (mt.x[None, None, None, :] - B * v0 * mur) / svv
+        idx = np.arange(len(R))[:, None, None, None]
+        k0 = xc[idx, 0, cell]                                       # [...,4]
+        xi0 = ((k0[..., 3] * t + k0[..., 2]) * t + k0[..., 1]) * t + k0[..., 0]
+        tot = xi0
+        for li in range(1, mt.n_ell):
+            kl = xc[idx, li, cell]
+            xil = ((kl[..., 3] * t + kl[..., 2]) * t + kl[..., 1]) * t + kl[..., 0]
+            ell = int(mt.ells[li])
+            pl = 0.5 * (3 * mur ** 2 - 1) if ell == 2 else (35 * mur ** 4 - 30 * mur ** 2 + 3) / 8
+            tot = tot + xil * pl
+        integrand = (1 + tot) * np.exp(-0.5 * z * z) / svv
+        out[a:a + chunk] = (integrand * mt.wx[None, None, None, :]).sum(axis=-1) - 1
+    return out
+
+
+def theory_multipoles(mt, rows, s, mu, W, chunk=32):
+    """[n][L][ns] multipoles and [n][nmu][ns] xi."""
+    xi = theory_xi(mt, rows, s, mu, chunk)
+    return np.einsum("lk,nkj->nlj", W, xi), xi
+
+
+def chi2_lnl(ft, beta, theory):
+    """chi2[n], lnL[n] from stacked theory vectors [n][p].  victor/ccf_fit.py:166-260, 325-483."""
+    n = len(beta)
+    if ft.data_beta_dependent:
+        k, t = _beta_interval(ft.beta_ccf, beta)
+    else:
+        k, t = np.zeros(n, dtype=np.int64), np.zeros(n)
+    tab = ft.data_tab[k]                                            # [n][4][p]
+    tt = t[:, None]
+    d = ((tab[:, 3] * tt + tab[:, 2]) * tt + tab[:, 1]) * tt + tab[:, 0]
+    resid = theory - d
+    chi2 = np.empty(n)
+    lnl = np.empty(n)
+    g = ft.beta_cov
+    for i in range(n):
+        if ft.cov_fixed:
+            lo, hi, w = 0, 0, 0.0
+        elif beta[i] < g.min():
+            lo, hi, w = 0, 0, 0.0
+        elif beta[i] > g.max():
+            lo, hi, w = len(g) - 1, len(g) - 1, 0.0
+        elif beta[i] in g:
+            lo = hi = int(np.where(g == beta[i])[0][0])
+            w = 0.0
+        elif np.isnan(beta[i]):
+            chi2[i], lnl[i] = np.inf, -np.inf
+            continue
+        else:
+            lo = int(np.where(g < beta[i])[0][-1])
+            hi = len(g) - 1                                         # the reference's bracket quirk
+            w = (beta[i] - g[lo]) / (g[hi] - g[lo])
+        qlo = resid[i] @ ft.icov[lo] @ resid[i]
+        qhi = resid[i] @ ft.icov[hi] @ resid[i] if hi != lo else qlo
+        chi2[i] = (1 - w) * qlo + w * qhi
+        norm = 0.0
+        if ft.use_logdet:
+            ld = ft.logdet[lo] + (np.log1p(w * (ft.lam[lo] - 1)).sum() if hi != lo else 0.0)
+            norm = -0.5 * ld
+        if ft.like_kind == T.LIKE_LOG:
+            lnl[i] = -ft.like_a * np.log(1 + chi2[i] / ft.like_nm1) / 2 + norm
+        else:
+            lnl[i] = -0.5 * chi2[i] * ft.like_a + norm
+        if np.isnan(lnl[i]):
+            lnl[i], chi2[i] = -np.inf, np.inf
+    return chi2, lnl

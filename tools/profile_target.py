@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""Short, deterministic launch sequence for ncu: a few 65,536-row likelihood passes, nothing else.
+
+    python tools/profile_target.py [--batch 65536] [--passes 3] [--fast 1] [--threads 256]
+"""
+import argparse
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+from bench import boss_blocks, synthetic_batch, P  # noqa: E402
+from victor_b200 import CCFFit  # noqa: E402
+from victor_b200.model import params_to_rows  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--passes", type=int, default=3)
+    ap.add_argument("--fast", type=int, default=1)
+    ap.add_argument("--threads", type=int, default=256)
+    ap.add_argument("--nsplit", type=int, default=0)
+    args = ap.parse_args()
+    model, data = boss_blocks()
+    fit = CCFFit(model, data, device=0)
+    eng, _ = fit._fit_engine({})
+    eng.set_option("fast_math", args.fast)
+    eng.set_option("threads", args.threads)
+    eng.set_option("nsplit", args.nsplit)
+    n = args.batch
+    dev = torch.device("cuda", 0)
+    d_params = torch.from_numpy(params_to_rows(synthetic_batch(n))).to(dev)
+    d_theory = torch.empty((n, P), dtype=torch.float64, device=dev)
+    d_chi2 = torch.empty(n, dtype=torch.float64, device=dev)
+    d_lnl = torch.empty(n, dtype=torch.float64, device=dev)
+    times = []
+    for _ in range(args.passes):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        eng.likelihood_ptr(d_params.data_ptr(), n, d_theory.data_ptr(), d_chi2.data_ptr(), d_lnl.data_ptr())
+        b.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+    print(f"batch={n} fast={args.fast} threads={args.threads} nsplit={args.nsplit} "
+          f"ms={['%.3f' % t for t in times]} evals/s={n / (min(times) * 1e-3):.4g} "
+          f"chi2[0]={float(d_chi2[0]):.10f}")
+    fit.close()
+
+
+if __name__ == "__main__":
+    main()

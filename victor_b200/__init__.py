@@ -1,0 +1,10 @@
+"""victor-b200: B200-native drop-in for the likelihood hot path of seshnadathur/victor.
+
+Same names as ``victor/__init__.py:3-9`` for the classes on the path.
+"""
+from .model import CCFModel
+from .fit import CCFFit
+from .utils import InputError
+from ._version import __version__
+
+__all__ = ["CCFModel", "CCFFit", "InputError", "__version__"]

@@ -1,0 +1,521 @@
+// C-ABI host side of libvictor_b200.so: context (device copies of the host-built tables),
+// staging of host buffers, kernel launches.  See include/victor_b200.h for the contract.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/victor_b200.h"
+#include "kernels.cuh"
+
+using namespace vb200;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return fail(VB200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));    \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// growable device scratch buffer
+struct Scratch {
+    double *ptr = nullptr;
+    size_t cap = 0;  // in doubles
+    int ensure(size_t n) {
+        if (n <= cap) return VB200_OK;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        size_t want = std::max(n, (size_t)1024);
+        cudaError_t e = cudaMalloc(&ptr, want * sizeof(double));
+        if (e != cudaSuccess) {
+            ptr = nullptr;
+            return fail(VB200_ENOMEM, std::string("cudaMalloc scratch: ") + cudaGetErrorString(e));
+        }
+        cap = want;
+        return VB200_OK;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+};
+
+bool is_device_ptr(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace
+
+struct vb200_ctx {
+    int device = 0;
+    int sm_count = 148;
+    bool has_fit = false;
+    ModelDev md{};
+    FitDev fd{};
+    // fit grids (device)
+    int fit_ns = 0, fit_nmu = 0, fit_L = 0;
+    double *fit_s = nullptr, *fit_mu = nullptr, *fit_sqmu = nullptr, *fit_wmu = nullptr;
+    std::vector<void *> owned;
+    Scratch sc_params, sc_theory, sc_chi2, sc_lnl, sc_xi, sc_mult, sc_grid;
+    // options
+    int opt_fast = 1, opt_nsplit = 0, opt_threads = 256;
+    long long launches = 0;
+    size_t k1_smem_limit = 0;
+};
+
+namespace {
+
+template <class T>
+int upload(vb200_ctx *c, const T *host, size_t count, const T **dev) {
+    if (count == 0 || host == nullptr) return fail(VB200_EINVAL, "null or empty table passed to vb200_create");
+    void *p = nullptr;
+    CK(cudaMalloc(&p, count * sizeof(T)));
+    c->owned.push_back(p);
+    CK(cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    *dev = static_cast<const T *>(p);
+    return VB200_OK;
+}
+
+int check_model(const vb200_model_tables *m) {
+    if (!m) return fail(VB200_EINVAL, "model tables are NULL");
+    if (m->ncell < 2 || m->nbucket < 1 || m->nx < 3 || m->nbeta < 2 || m->nresc < 2)
+        return fail(VB200_EINVAL, "model tables: bad sizes");
+    if (m->n_ell < 1 || m->n_ell > VB200_MAX_POLES) return fail(VB200_EINVAL, "model tables: bad n_ell");
+    if (m->rsd_model != VB200_RSD_STREAMING)
+        return fail(VB200_EUNSUPPORTED, "only rsd_model 'streaming' has a kernel in this build");
+    if (m->n_ell != 1)
+        return fail(VB200_EUNSUPPORTED, "anisotropic real-space input (assume_isotropic: False) has no kernel "
+                                        "in this build");
+    if (!(m->inv_h > 0.0) || !(m->iaH > 0.0) || !(m->template_sigma8 > 0.0))
+        return fail(VB200_EINVAL, "model tables: bad scalars");
+    return VB200_OK;
+}
+
+int launch_k1(vb200_ctx *c, const double *d_params, long long n, const double *d_s, int ns,
+              const double *d_mu, const double *d_sqmu, const double *d_wmu, int nmu, int L,
+              double *d_xi, double *d_mult, cudaStream_t st) {
+    if (n <= 0) return VB200_OK;
+    int nsplit = c->opt_nsplit;
+    if (nsplit <= 0) {
+        // one block per row once the rows alone fill the GPU a few times over, else split the
+        // s range so that a single row (MCMC step) still spreads over the SMs
+        const long long target = (long long)c->sm_count * 6;
+        nsplit = (n >= target) ? 1 : (int)std::min<long long>(ns, (target + n - 1) / n);
+    }
+    nsplit = std::max(1, std::min(nsplit, ns));
+    int jper = (ns + nsplit - 1) / nsplit;
+    nsplit = (ns + jper - 1) / jper;
+    const int npairs = jper * nmu;
+    int threads = std::min(c->opt_threads, ((npairs + 31) / 32) * 32);
+    threads = std::max(32, std::min(threads, 256));
+    const size_t smem = k1_smem_bytes(c->md.ncell, c->md.nx, jper, nmu, c->md.nbucket);
+    if (smem > c->k1_smem_limit)
+        return fail(VB200_EUNSUPPORTED, "grids too large for one block's shared memory (reduce len(s) * len(mu))");
+    const long long blocks = n * nsplit;
+    if (blocks > 2147483647LL) return fail(VB200_EINVAL, "too many blocks in one launch");
+
+    K1Args a{};
+    a.m = c->md;
+    a.params = d_params;
+    a.n = n;
+    a.s = d_s;
+    a.mu = d_mu;
+    a.sqmu = d_sqmu;
+    a.wmu = d_wmu;
+    a.ns = ns;
+    a.nmu = nmu;
+    a.L = L;
+    a.jper = jper;
+    a.nsplit = nsplit;
+    a.xi_out = d_xi;
+    a.mult_out = d_mult;
+    if (c->opt_fast)
+        k_multipoles<true><<<(unsigned)blocks, threads, smem, st>>>(a);
+    else
+        k_multipoles<false><<<(unsigned)blocks, threads, smem, st>>>(a);
+    CK(cudaGetLastError());
+    c->launches++;
+    return VB200_OK;
+}
+
+int launch_k2(vb200_ctx *c, const double *d_params, const double *d_theory, long long n, double *d_chi2,
+              double *d_lnl, cudaStream_t st) {
+    if (n <= 0) return VB200_OK;
+    K2Args a{};
+    a.f = c->fd;
+    a.params = d_params;
+    a.theory = d_theory;
+    a.n = n;
+    a.chi2 = d_chi2;
+    a.lnl = d_lnl;
+    const long long blocks = (n + kK2Warps - 1) / kK2Warps;
+    const size_t smem = (size_t)kK2Warps * c->fd.p * sizeof(double);
+    k_chi2<<<(unsigned)blocks, kK2Warps * 32, smem, st>>>(a);
+    CK(cudaGetLastError());
+    c->launches++;
+    return VB200_OK;
+}
+
+void fill_exp_table(double *t) {
+    for (int j = 0; j < kExpTab; ++j) t[j] = std::exp2((double)j / kExpTab);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *vb200_version(void) { return "victor_b200 0.1.0 (sm_100a)"; }
+
+const char *vb200_last_error(void) { return g_err.c_str(); }
+
+int vb200_abi_check(int64_t sizeof_model_tables, int64_t sizeof_fit_tables) {
+    if (sizeof_model_tables != (int64_t)sizeof(vb200_model_tables) ||
+        sizeof_fit_tables != (int64_t)sizeof(vb200_fit_tables))
+        return fail(VB200_EINVAL, "table struct size mismatch between binding and library");
+    return VB200_OK;
+}
+
+int vb200_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        g_err = std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void vb200_destroy(vb200_ctx *c) {
+    if (!c) return;
+    DeviceGuard g(c->device);
+    for (void *p : c->owned) cudaFree(p);
+    c->sc_params.release();
+    c->sc_theory.release();
+    c->sc_chi2.release();
+    c->sc_lnl.release();
+    c->sc_xi.release();
+    c->sc_mult.release();
+    c->sc_grid.release();
+    delete c;
+}
+
+int vb200_create(const vb200_model_tables *m, const vb200_fit_tables *f, int device, vb200_ctx **out) {
+    if (!out) return fail(VB200_EINVAL, "out is NULL");
+    *out = nullptr;
+    int rc = check_model(m);
+    if (rc) return rc;
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(VB200_EINVAL, "no such CUDA device");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(VB200_ECUDA, "cudaSetDevice failed");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(VB200_EUNSUPPORTED, "this library is built for sm_100a (B200) only");
+
+    vb200_ctx *c = new vb200_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    auto bail = [&](int code) {
+        vb200_destroy(c);
+        return code;
+    };
+
+    ModelDev &d = c->md;
+    d.iaH = m->iaH;
+    d.s8t = m->template_sigma8;
+    d.beta_fixed = m->beta_fixed;
+    d.inv_h = m->inv_h;
+    d.vel_indep_AP = m->vel_indep_AP;
+    d.rsd_model = m->rsd_model;
+    d.n_ell = m->n_ell;
+    d.beta_dependent = m->beta_dependent;
+    d.ncell = m->ncell;
+    d.nbucket = m->nbucket;
+    d.maxscan = m->maxscan;
+    d.nbeta = m->nbeta;
+    d.nx = m->nx;
+    d.nresc = m->nresc;
+    const size_t nc4 = (size_t)m->ncell * 4;
+    if ((rc = upload(c, m->origin, (size_t)m->ncell, &d.origin))) return bail(rc);
+    if ((rc = upload(c, m->upper, (size_t)m->ncell, &d.upper))) return bail(rc);
+    if ((rc = upload(c, m->bucket_base, (size_t)m->nbucket, &d.bucket_base))) return bail(rc);
+    if ((rc = upload(c, m->beta_grid, (size_t)m->nbeta, &d.beta_grid))) return bail(rc);
+    if ((rc = upload(c, m->xi_tab, (size_t)m->n_ell * (m->nbeta - 1) * 4 * nc4, &d.xi_tab))) return bail(rc);
+    if ((rc = upload(c, m->v0, nc4, &d.v0))) return bail(rc);
+    if ((rc = upload(c, m->d0, nc4, &d.d0))) return bail(rc);
+    if ((rc = upload(c, m->sv, nc4, &d.sv))) return bail(rc);
+    if ((rc = upload(c, m->x, (size_t)m->nx, &d.x))) return bail(rc);
+    if ((rc = upload(c, m->wx, (size_t)m->nx, &d.wx))) return bail(rc);
+    if ((rc = upload(c, m->mu_resc, (size_t)m->nresc, &d.mu_resc))) return bail(rc);
+    if ((rc = upload(c, m->w_resc, (size_t)m->nresc, &d.w_resc))) return bail(rc);
+    double etab[kExpTab];
+    fill_exp_table(etab);
+    if ((rc = upload(c, etab, (size_t)kExpTab, &d.exp_tab))) return bail(rc);
+
+    if (f) {
+        if (f->ns < 1 || f->npoles < 1 || f->npoles > VB200_MAX_POLES || f->nmu < 2 || f->nbeta_ccf < 2 ||
+            f->nbeta_cov < 1)
+            return bail(fail(VB200_EINVAL, "fit tables: bad sizes"));
+        const int p = f->ns * f->npoles;
+        if (p > 32 * kK2MaxChunks) return bail(fail(VB200_EUNSUPPORTED, "data vector longer than 256"));
+        FitDev &fd = c->fd;
+        fd.p = p;
+        fd.data_beta_dependent = f->data_beta_dependent;
+        fd.nbeta_ccf = f->nbeta_ccf;
+        fd.cov_fixed = f->cov_fixed;
+        fd.nbeta_cov = f->nbeta_cov;
+        fd.like_kind = f->like_kind;
+        fd.use_logdet = f->use_logdet;
+        fd.like_a = f->like_a;
+        fd.like_nm1 = f->like_nm1;
+        if ((rc = upload(c, f->beta_ccf, (size_t)f->nbeta_ccf, &fd.beta_ccf))) return bail(rc);
+        if ((rc = upload(c, f->data_tab, (size_t)(f->nbeta_ccf - 1) * 4 * p, &fd.data_tab))) return bail(rc);
+        if ((rc = upload(c, f->beta_cov, (size_t)f->nbeta_cov, &fd.beta_cov))) return bail(rc);
+        if ((rc = upload(c, f->icov, (size_t)f->nbeta_cov * p * p, &fd.icov))) return bail(rc);
+        if ((rc = upload(c, f->logdet, (size_t)f->nbeta_cov, &fd.logdet))) return bail(rc);
+        if ((rc = upload(c, f->lam, (size_t)f->nbeta_cov * p, &fd.lam))) return bail(rc);
+        c->fit_ns = f->ns;
+        c->fit_nmu = f->nmu;
+        c->fit_L = f->npoles;
+        std::vector<double> sq((size_t)f->nmu);
+        for (int k = 0; k < f->nmu; ++k) sq[k] = std::sqrt(1.0 - f->mu[k] * f->mu[k]);
+        const double *tmp = nullptr;
+        if ((rc = upload(c, f->s, (size_t)f->ns, &tmp))) return bail(rc);
+        c->fit_s = const_cast<double *>(tmp);
+        if ((rc = upload(c, f->mu, (size_t)f->nmu, &tmp))) return bail(rc);
+        c->fit_mu = const_cast<double *>(tmp);
+        if ((rc = upload(c, sq.data(), (size_t)f->nmu, &tmp))) return bail(rc);
+        c->fit_sqmu = const_cast<double *>(tmp);
+        if ((rc = upload(c, f->wmu, (size_t)f->npoles * f->nmu, &tmp))) return bail(rc);
+        c->fit_wmu = const_cast<double *>(tmp);
+        c->has_fit = true;
+    }
+
+    // allow the large dynamic shared memory carve-out (dense mu grids stage up to ~200 KB)
+    c->k1_smem_limit = std::min<size_t>((size_t)prop.sharedMemPerBlockOptin, (size_t)200 * 1024);
+    cudaError_t e1 = cudaFuncSetAttribute(k_multipoles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)c->k1_smem_limit);
+    cudaError_t e2 = cudaFuncSetAttribute(k_multipoles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)c->k1_smem_limit);
+    if (e1 != cudaSuccess || e2 != cudaSuccess)
+        return bail(fail(VB200_ECUDA, std::string("cudaFuncSetAttribute: ") +
+                                          cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)));
+    *out = c;
+    return VB200_OK;
+}
+
+int vb200_set_option(vb200_ctx *c, const char *key, int64_t value) {
+    if (!c || !key) return fail(VB200_EINVAL, "null argument");
+    if (!strcmp(key, "fast_math")) c->opt_fast = value ? 1 : 0;
+    else if (!strcmp(key, "nsplit")) c->opt_nsplit = (int)value;
+    else if (!strcmp(key, "threads")) {
+        if (value < 32 || value > 256 || value % 32) return fail(VB200_EINVAL, "threads must be 32..256, multiple of 32");
+        c->opt_threads = (int)value;
+    } else
+        return fail(VB200_EINVAL, std::string("unknown option ") + key);
+    return VB200_OK;
+}
+
+int vb200_synchronize(vb200_ctx *c) {
+    if (!c) return fail(VB200_EINVAL, "ctx is NULL");
+    DeviceGuard g(c->device);
+    CK(cudaDeviceSynchronize());
+    return VB200_OK;
+}
+
+int64_t vb200_launch_count(const vb200_ctx *c) { return c ? c->launches : 0; }
+
+int vb200_theory(vb200_ctx *c, const double *params, int64_t n, const double *s, int32_t ns, const double *mu,
+                 int32_t nmu, const double *wmu, int32_t L, double *xi_out, double *mult_out, void *stream) {
+    if (!c) return fail(VB200_EINVAL, "ctx is NULL");
+    if (n < 0 || !params || !s || !mu || ns < 1 || nmu < 1) return fail(VB200_EINVAL, "bad arguments");
+    if (mult_out && (!wmu || L < 1 || L > VB200_MAX_POLES)) return fail(VB200_EINVAL, "mult_out needs wmu and 1 <= L <= 3");
+    if (!xi_out && !mult_out) return fail(VB200_EINVAL, "no output requested");
+    if (n == 0) return VB200_OK;
+    DeviceGuard g(c->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    bool host_io = false;
+    int rc;
+
+    // grids: host arrays, staged per call (s | mu | sqrt(1-mu^2) | wmu)
+    const int Lw = mult_out ? L : 0;
+    const size_t ng = (size_t)ns + 2 * (size_t)nmu + (size_t)Lw * nmu;
+    if ((rc = c->sc_grid.ensure(ng))) return rc;
+    {
+        std::vector<double> h(ng);
+        std::copy(s, s + ns, h.begin());
+        std::copy(mu, mu + nmu, h.begin() + ns);
+        for (int k = 0; k < nmu; ++k) h[(size_t)ns + nmu + k] = std::sqrt(1.0 - mu[k] * mu[k]);
+        if (Lw) std::copy(wmu, wmu + (size_t)Lw * nmu, h.begin() + ns + 2 * (size_t)nmu);
+        // the copy is stream-ordered; the pageable source is consumed before the call returns
+        CK(cudaMemcpyAsync(c->sc_grid.ptr, h.data(), ng * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    const double *d_s = c->sc_grid.ptr, *d_mu = d_s + ns, *d_sq = d_mu + nmu;
+    const double *d_w = Lw ? d_sq + nmu : nullptr;
+
+    const double *d_params = params;
+    if (!is_device_ptr(params)) {
+        host_io = true;
+        if ((rc = c->sc_params.ensure((size_t)n * VB200_NPAR))) return rc;
+        CK(cudaMemcpyAsync(c->sc_params.ptr, params, (size_t)n * VB200_NPAR * sizeof(double),
+                           cudaMemcpyHostToDevice, st));
+        d_params = c->sc_params.ptr;
+    }
+    double *d_xi = xi_out, *d_mult = mult_out;
+    const size_t nxi = (size_t)n * nmu * ns, nmult = (size_t)n * Lw * ns;
+    if (xi_out && !is_device_ptr(xi_out)) {
+        host_io = true;
+        if ((rc = c->sc_xi.ensure(nxi))) return rc;
+        d_xi = c->sc_xi.ptr;
+    }
+    if (mult_out && !is_device_ptr(mult_out)) {
+        host_io = true;
+        if ((rc = c->sc_mult.ensure(nmult))) return rc;
+        d_mult = c->sc_mult.ptr;
+    }
+    if ((rc = launch_k1(c, d_params, n, d_s, ns, d_mu, d_sq, d_w, nmu, Lw, d_xi, d_mult, st))) return rc;
+    if (xi_out && d_xi != xi_out)
+        CK(cudaMemcpyAsync(xi_out, d_xi, nxi * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (mult_out && d_mult != mult_out)
+        CK(cudaMemcpyAsync(mult_out, d_mult, nmult * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (host_io) CK(cudaStreamSynchronize(st));
+    return VB200_OK;
+}
+
+int vb200_likelihood(vb200_ctx *c, const double *params, int64_t n, double *theory, double *chi2, double *lnlike,
+                     void *stream) {
+    if (!c) return fail(VB200_EINVAL, "ctx is NULL");
+    if (!c->has_fit) return fail(VB200_EINVAL, "context was created without fit tables");
+    if (n < 0 || !params) return fail(VB200_EINVAL, "bad arguments");
+    if (!theory && !chi2 && !lnlike) return fail(VB200_EINVAL, "no output requested");
+    if (n == 0) return VB200_OK;
+    DeviceGuard g(c->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int p = c->fd.p;
+    bool host_io = false;
+    int rc;
+
+    const double *d_params = params;
+    if (!is_device_ptr(params)) {
+        host_io = true;
+        if ((rc = c->sc_params.ensure((size_t)n * VB200_NPAR))) return rc;
+        CK(cudaMemcpyAsync(c->sc_params.ptr, params, (size_t)n * VB200_NPAR * sizeof(double),
+                           cudaMemcpyHostToDevice, st));
+        d_params = c->sc_params.ptr;
+    }
+    double *d_theory = theory;
+    if (!theory || !is_device_ptr(theory)) {
+        if ((rc = c->sc_theory.ensure((size_t)n * p))) return rc;
+        d_theory = c->sc_theory.ptr;
+        if (theory) host_io = true;
+    }
+    double *d_chi2 = chi2, *d_lnl = lnlike;
+    if (chi2 && !is_device_ptr(chi2)) {
+        host_io = true;
+        if ((rc = c->sc_chi2.ensure((size_t)n))) return rc;
+        d_chi2 = c->sc_chi2.ptr;
+    }
+    if (lnlike && !is_device_ptr(lnlike)) {
+        host_io = true;
+        if ((rc = c->sc_lnl.ensure((size_t)n))) return rc;
+        d_lnl = c->sc_lnl.ptr;
+    }
+    if ((rc = launch_k1(c, d_params, n, c->fit_s, c->fit_ns, c->fit_mu, c->fit_sqmu, c->fit_wmu, c->fit_nmu,
+                        c->fit_L, nullptr, d_theory, st)))
+        return rc;
+    if (chi2 || lnlike)
+        if ((rc = launch_k2(c, d_params, d_theory, n, d_chi2, d_lnl, st))) return rc;
+    if (theory && d_theory != theory)
+        CK(cudaMemcpyAsync(theory, d_theory, (size_t)n * p * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (chi2 && d_chi2 != chi2) CK(cudaMemcpyAsync(chi2, d_chi2, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (lnlike && d_lnl != lnlike)
+        CK(cudaMemcpyAsync(lnlike, d_lnl, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (host_io) CK(cudaStreamSynchronize(st));
+    return VB200_OK;
+}
+
+int vb200_math_selftest(int device, const double *x, int64_t n, double *out) {
+    if (!x || !out || n <= 0) return fail(VB200_EINVAL, "bad arguments");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(VB200_ECUDA, "cudaSetDevice failed");
+    double *dx = nullptr, *dout = nullptr, *dtab = nullptr;
+    double etab[kExpTab];
+    fill_exp_table(etab);
+    CK(cudaMalloc(&dx, n * sizeof(double)));
+    CK(cudaMalloc(&dout, 3 * n * sizeof(double)));
+    CK(cudaMalloc(&dtab, sizeof(etab)));
+    CK(cudaMemcpy(dx, x, n * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dtab, etab, sizeof(etab), cudaMemcpyHostToDevice));
+    k_math_selftest<<<(unsigned)((n + 255) / 256), 256>>>(dx, n, dtab, dout);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, dout, 3 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(dx);
+    cudaFree(dout);
+    cudaFree(dtab);
+    return VB200_OK;
+}
+
+int vb200_fp64_peak(int device, int iters, double *tflops, double *ms) {
+    if (!tflops || iters < 1) return fail(VB200_EINVAL, "bad arguments");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(VB200_ECUDA, "cudaSetDevice failed");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    double *d = nullptr;
+    CK(cudaMalloc(&d, sizeof(double)));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    k_fp64_peak<<<blocks, threads>>>(d, iters / 4 + 1, 0.999999, 1e-9);  // warm-up
+    CK(cudaEventRecord(e0));
+    k_fp64_peak<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, e0, e1));
+    const double fma_count = (double)blocks * threads * (double)iters * 64.0;
+    *tflops = 2.0 * fma_count / (t * 1e-3) / 1e12;
+    if (ms) *ms = t;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    return VB200_OK;
+}
+
+}  // extern "C"

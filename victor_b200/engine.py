@@ -1,0 +1,117 @@
+"""One GPU context: host tables uploaded once, then batched evaluations through the C ABI.
+
+This is the only place the Python classes touch the device.  Inputs and outputs of the
+convenience methods are numpy arrays on the host (the library stages them; copies are part of
+the call); ``likelihood_ptr`` / ``theory`` with device pointers give the asynchronous,
+device-resident path used by bench.py and by callers that keep their batches in torch tensors.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from . import tables as _tables
+
+
+def default_device():
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return torch.cuda.current_device()
+    except ImportError:
+        pass
+    return 0
+
+
+class Engine:
+    def __init__(self, model_tables, fit=None, device=None):
+        """``fit``: None or dict(ft=FitTables, s=..., mu=..., wmu=...)."""
+        self.lib = _lib.load()
+        if self.lib.vb200_device_count() < 1:
+            raise RuntimeError("victor_b200 needs a CUDA device (B200, sm_100a); none is visible and there is "
+                               f"no CPU fallback: {_lib.last_error()}")
+        self.device = default_device() if device is None else int(device)
+        mc, keep_m = _lib.pack_model(model_tables)
+        fc = None
+        self.p = None
+        if fit is not None:
+            fc, keep_f = _lib.pack_fit(fit["ft"], fit["s"], fit["mu"], fit["wmu"])
+            self.p = int(fit["ft"].p)
+        handle = ctypes.c_void_p()
+        rc = self.lib.vb200_create(ctypes.byref(mc), ctypes.byref(fc) if fc is not None else None,
+                                   self.device, ctypes.byref(handle))
+        if rc != 0:
+            msg = _lib.last_error()
+            if rc == -4:
+                raise NotImplementedError(msg)
+            raise RuntimeError(f"vb200_create failed ({rc}): {msg}")
+        self.handle = handle
+        self.model_tables = model_tables
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = _lib.last_error()
+            if rc == -4:
+                raise NotImplementedError(msg)
+            if rc == -1:
+                raise ValueError(msg)
+            raise RuntimeError(f"victor_b200 call failed ({rc}): {msg}")
+
+    def set_option(self, key, value):
+        self._check(self.lib.vb200_set_option(self.handle, key.encode(), int(value)))
+
+    def launch_count(self):
+        return int(self.lib.vb200_launch_count(self.handle))
+
+    def synchronize(self):
+        self._check(self.lib.vb200_synchronize(self.handle))
+
+    # ---- host-array convenience paths -------------------------------------------------
+    def theory(self, rows, s, mu, wmu):
+        """(xi[n][nmu][ns] or None, multipoles[n][L][ns] or None); xi only when wmu is None."""
+        rows = np.ascontiguousarray(rows, dtype=np.float64)
+        s = np.ascontiguousarray(s, dtype=np.float64)
+        mu = np.ascontiguousarray(mu, dtype=np.float64)
+        n = rows.shape[0]
+        xi = mult = None
+        if wmu is None:
+            xi = np.empty((n, len(mu), len(s)))
+            L, wp = 0, None
+        else:
+            wmu = np.ascontiguousarray(wmu, dtype=np.float64)
+            L = wmu.shape[0]
+            mult = np.empty((n, L, len(s)))
+            wp = wmu.ctypes.data
+        self._check(self.lib.vb200_theory(
+            self.handle, rows.ctypes.data, n, s.ctypes.data, len(s), mu.ctypes.data, len(mu), wp, L,
+            xi.ctypes.data if xi is not None else None,
+            mult.ctypes.data if mult is not None else None, None))
+        return xi, mult
+
+    def likelihood(self, rows, want_theory=False):
+        """(theory[n][p] or None, chi2[n], lnl[n]) as host arrays."""
+        rows = np.ascontiguousarray(rows, dtype=np.float64)
+        n = rows.shape[0]
+        theory = np.empty((n, self.p)) if want_theory else None
+        chi2 = np.empty(n)
+        lnl = np.empty(n)
+        self._check(self.lib.vb200_likelihood(
+            self.handle, rows.ctypes.data, n, theory.ctypes.data if want_theory else None,
+            chi2.ctypes.data, lnl.ctypes.data, None))
+        return theory, chi2, lnl
+
+    # ---- raw-pointer path (host or device pointers, caller-owned buffers) ---------------
+    def likelihood_ptr(self, params_ptr, n, theory_ptr, chi2_ptr, lnl_ptr, stream=None):
+        self._check(self.lib.vb200_likelihood(self.handle, params_ptr, int(n), theory_ptr, chi2_ptr, lnl_ptr,
+                                              stream))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.vb200_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

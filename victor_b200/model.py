@@ -1,0 +1,351 @@
+"""Drop-in ``CCFModel``: victor's model class served by the B200 CUDA path.
+
+Mirrors the public surface of ``victor.CCFModel`` (victor/ccf_model.py:24-1041) for the
+likelihood hot path: same constructor dict, same attribute names (``r, beta, poles_r, iaH,
+r_for_sv, mu_for_sv, sv_rmu, template_sigma8, model`` ...), same method names and return
+types.  Construction (file loading, template preparation) runs on the host with the same
+scipy routines as the reference; every evaluation runs on the GPU through the C-ABI library
+(``victor_b200/csrc``) -- there is no CPU evaluation path.
+
+New, batched entry points: ``theory_multipole_vector_batch`` / ``theory_multipoles_batch`` /
+``theory_xi_batch`` take a parameter table (dict of arrays or float64[n, k]) and evaluate all
+rows in one launch; the reference-style single-point methods call them with n = 1.
+"""
+import os
+
+import numpy as np
+from scipy.integrate import quad
+from scipy.interpolate import InterpolatedUnivariateSpline, RectBivariateSpline
+from scipy.special import legendre
+
+from . import tables as _tables
+from .utils import InputError, load_input_file, trapezoid
+
+
+def _ext3_spline(x, y):
+    return InterpolatedUnivariateSpline(x, y, ext=3)
+
+
+def hubble_ratio(cosmology, z):
+    """E(z) for LambdaCDM with Om, Ok, OL = 1 - Om - Ok and no radiation.
+
+    victor/cosmology.py:26-45 builds ``astropy.cosmology.LambdaCDM(H0, Om0, Ode0)`` (whose
+    default Tcmb0 = 0 means no radiation term) and returns H(z)/H0.
+    """
+    cosmology = cosmology or {}
+    om = cosmology.get("Omega_m", 0.31)
+    ok = cosmology.get("Omega_K", 0)
+    ol = 1 - om - ok
+    curv = 1.0 - om - ol
+    zp1 = 1.0 + z
+    return float(np.sqrt(om * zp1 ** 3 + curv * zp1 ** 2 + ol))
+
+
+def params_to_rows(params, n_hint=None):
+    """Normalise a parameter specification to float64[n, NPAR] (tables.PARAM_ORDER).
+
+    Accepts a dict of scalars/arrays with victor's parameter names, or an array [n, k] whose
+    first columns follow PARAM_ORDER (k >= 3; missing columns take victor's defaults).  The
+    (epsilon, alpha) parameterisation is converted exactly as the reference does
+    (ccf_model.py:589-596): apar = alpha * epsilon^(-2/3), aperp = epsilon * apar.
+    """
+    defaults = {"fsigma8": np.nan, "beta": np.nan, "sigma_v": 380.0, "aperp": 1.0, "apar": 1.0,
+                "astar": 1.0, "M": 1.0, "Q": 1.0}
+    if isinstance(params, dict):
+        cols = {}
+        lens = [np.size(v) for k, v in params.items()
+                if k in defaults or k in ("epsilon", "alpha")]
+        n = max(lens) if lens else 1
+        if n_hint:
+            n = max(n, n_hint)
+
+        def col(name, default):
+            v = params.get(name, default)
+            return np.broadcast_to(np.asarray(v, dtype=np.float64), (n,)).copy()
+
+        if "epsilon" in params:
+            eps = col("epsilon", 1.0)
+            cols["apar"] = col("alpha", 1.0) * eps ** (-2 / 3)
+            cols["aperp"] = eps * cols["apar"]
+        rows = np.empty((n, _tables.NPAR))
+        for i, name in enumerate(_tables.PARAM_ORDER):
+            rows[:, i] = cols[name] if name in cols else col(name, defaults[name])
+        return rows
+    arr = np.atleast_2d(np.asarray(params, dtype=np.float64))
+    if arr.shape[1] == _tables.NPAR:
+        return np.ascontiguousarray(arr)
+    if arr.shape[1] < 3 or arr.shape[1] > _tables.NPAR:
+        raise InputError(f"parameter table must have between 3 and {_tables.NPAR} columns "
+                         f"{_tables.PARAM_ORDER}")
+    rows = np.empty((arr.shape[0], _tables.NPAR))
+    for i, name in enumerate(_tables.PARAM_ORDER):
+        rows[:, i] = arr[:, i] if i < arr.shape[1] else defaults[name]
+    return rows
+
+
+class CCFModel:
+    """Redshift-space void-galaxy / density-split CCF model (drop-in for victor.CCFModel)."""
+
+    extensions = {"npy": [".npy"], "npz": [".npz"],
+                  "hdf5": [".hdf", ".h4", ".hdf4", ".he2", ".h5", ".hdf5", ".he5", ".h5py"]}
+
+    def __init__(self, model, device=None):
+        # reference: ccf_model.py:33-97
+        self.z_eff = model["z_eff"]
+        self.iaH = (1 + self.z_eff) / (100 * hubble_ratio(model.get("cosmology"), self.z_eff))
+
+        input_fn = os.path.join(model.get("dir", ""), model["input_model_data_file"])
+        if not os.path.isfile(input_fn):
+            raise InputError(f"File {input_fn} containing input model data not found")
+        input_data = load_input_file(input_fn)
+
+        self._load_realspace_ccf(model["realspace_ccf"], input_data)
+        self.matter_model = model["matter_ccf"].get("model", "linear_bias")
+        self.realspace_ccf_from_data = model["realspace_ccf"].get("from_data", False)
+        if self.matter_model == "linear_bias" and not self.realspace_ccf_from_data:
+            self.template_sigma8 = model["matter_ccf"].get("template_sigma8", None)
+            if not self.template_sigma8:
+                raise InputError("When using linear bias for the matter ccf and the real-space ccf is from "
+                                 "a template, template_sigma8 must be provided")
+        if self.matter_model == "template":
+            self._set_matter_ccf_template(model["matter_ccf"], input_data)
+        self._set_velocity_pdf(model["velocity_pdf"], input_data)
+
+        self.model = {
+            "rsd_model": model.get("rsd_model", "streaming"),
+            "kaiser_approximation": model.get("kaiser_approximation", False),
+            "kaiser_coord_shift": model.get("kaiser_coord_shift", True),
+            "assume_isotropic": model["realspace_ccf"].get("assume_isotropic", True),
+            "realspace_ccf_from_data": self.realspace_ccf_from_data,
+            "matter_model": self.matter_model,
+            "excursion_set_options": model["matter_ccf"].get("excursion_set_options", {}),
+            "bias": model["matter_ccf"].get("bias", 1.9),
+            "mean_model": model["velocity_pdf"]["mean"].get("model", "linear"),
+            "pdf_form": model["velocity_pdf"].get("form", "gaussian"),
+            "empirical_corr": model["velocity_pdf"]["mean"].get("empirical_corr", False),
+            "velocity_independent_of_AP":
+                model["velocity_pdf"].get("rescale_templates_independent_of_AP", True),
+        }
+        self._device = device
+        self._engines = {}
+
+    # ------------------------------------------------------------------ loaders (host, once)
+    def _load_realspace_ccf(self, realspace_ccf, input_data):
+        # reference: ccf_model.py:99-181
+        fmt = realspace_ccf.get("format", "multipoles")
+        self.fixed_real_input = not realspace_ccf.get("reconstruction", False)
+        ccf_keys = np.atleast_1d(realspace_ccf["ccf_keys"])
+        if not self.fixed_real_input:
+            beta_key = realspace_ccf.get("beta_key", None)
+            if beta_key is None:
+                raise InputError("Reconstruction specified for realspace ccf but no beta key provided")
+            if beta_key not in input_data:
+                raise InputError(f"Key {beta_key} not found in input model data file")
+            self.beta = input_data[beta_key]
+            if not np.all(np.diff(self.beta) > 0):
+                raise InputError("Realspace beta grid must be strictly monotonically increasing")
+        if (fmt == "multipoles" and len(ccf_keys) < 2) or (fmt == "rmu" and len(ccf_keys) != 3):
+            raise InputError(f"Wrong number of ccf keys provided for ccf format {fmt}")
+        for key in ccf_keys:
+            if key not in input_data:
+                raise InputError(f"Key {key} not found in input model data file")
+        isim = realspace_ccf.get("simulation_number", None)
+        if isim is not None and not isinstance(isim, int):
+            raise InputError("If provided, simulation_number must be an integer")
+        if fmt != "multipoles":
+            raise NotImplementedError("real-space ccf input in 'rmu' format has no B200 path; convert it to "
+                                      "multipoles first")
+        self.r = input_data[ccf_keys[0]]
+        npole = len(ccf_keys) - 1
+        self.poles_r = np.atleast_1d([0, 2, 4][:npole])
+        self.real_multipoles = {}
+        expected = self.r.shape if self.fixed_real_input else (len(self.beta), len(self.r))
+        for i, ell in enumerate(self.poles_r):
+            arr = input_data[ccf_keys[i + 1]]
+            arr = arr if isim is None else arr[isim]
+            if arr.shape != expected:
+                raise InputError(f"Shape of real ccf multipole {ell} is {arr.shape}, expected {expected}")
+            self.real_multipoles[f"{ell}"] = arr
+
+    def _set_matter_ccf_template(self, matter_ccf, input_data):
+        # reference: ccf_model.py:183-220
+        self.template_sigma8 = matter_ccf.get("template_sigma8", None)
+        if not self.template_sigma8:
+            raise InputError("When using template model for the matter ccf, template_sigma8 must be provided")
+        template_keys = np.atleast_1d(matter_ccf.get("template_keys"))
+        if len(template_keys) != 2:
+            raise InputError("Wrong number of matter ccf template keys provided: expected 2 "
+                             "(radial distance and monopole)")
+        for key in template_keys:
+            if key not in input_data:
+                raise InputError(f"Key {key} not found in input model data file")
+        r_for_delta = input_data[template_keys[0]]
+        delta = input_data[template_keys[1]]
+        if len(r_for_delta) != len(delta):
+            raise InputError(f"Shape of matter ccf template is {len(delta)}, expected {len(r_for_delta)}")
+        grid = np.linspace(r_for_delta.min(), r_for_delta.max())
+        if matter_ccf.get("integrated", False):
+            self.integrated_delta = _ext3_spline(r_for_delta, delta)
+            slope = np.gradient(self.integrated_delta(grid), grid)
+            self.delta = _ext3_spline(grid, self.integrated_delta(grid) + grid * slope / 3)
+        else:
+            self.delta = _ext3_spline(r_for_delta, delta)
+            enclosed = np.zeros_like(grid)
+            for i, rr in enumerate(grid):
+                enclosed[i] = quad(lambda x: 3 * self.delta(x) * x ** 2 / rr ** 3, 0, rr, full_output=1)[0]
+            self.integrated_delta = _ext3_spline(grid, enclosed)
+
+    def _set_velocity_pdf(self, velocity_pdf, input_data):
+        # reference: ccf_model.py:222-297
+        mean_model = velocity_pdf["mean"].get("model", "linear")
+        self.has_velocity_template = False
+        if mean_model == "template":
+            raise NotImplementedError("velocity mean model 'template' (a testing option of the reference) "
+                                      "has no B200 path")
+        if mean_model == "nonlinear" and self.matter_model != "excursion_set":
+            raise InputError("Cannot have nonlinear mean velocity model unless using excursion_set matter model")
+        dispersion = velocity_pdf.get("dispersion", {})
+        disp_model = dispersion.get("model", "constant")
+        if disp_model == "template":
+            template_keys = np.atleast_1d(dispersion.get("template_keys"))
+            if len(template_keys) < 2 or len(template_keys) > 3:
+                raise InputError(f"{len(template_keys)} velocity dispersion template keys provided, require 2 or 3")
+            for key in template_keys:
+                if key not in input_data:
+                    raise InputError(f"Key {key} not found in input model data file")
+            self.r_for_sv = input_data[template_keys[0]]
+            sv = input_data[template_keys[-1]]
+            self.sv_isotropic = len(template_keys) == 2
+            if self.sv_isotropic:
+                self.mu_for_sv = np.linspace(0, 1)
+                sv = (np.ones((len(self.mu_for_sv), len(self.r_for_sv))) * sv).T
+            else:
+                self.mu_for_sv = input_data[template_keys[1]]
+            if sv.shape != (len(self.r_for_sv), len(self.mu_for_sv)):
+                raise InputError(f"Dispersion template shape {sv.shape} does not match expected "
+                                 f"({len(self.r_for_sv)}, {len(self.mu_for_sv)})")
+            if dispersion.get("filter", True):
+                from scipy.signal import savgol_filter
+                window = dispersion.get("filter_window", 3)
+                polyorder = dispersion.get("filter_order", 1)
+                sv = np.array([savgol_filter(sv[:, i], window, polyorder) for i in range(sv.shape[1])]).T
+        elif disp_model == "constant":
+            # the reference leaves `sv` unbound on this branch and raises UnboundLocalError
+            # (ccf_model.py:284-292); report it as an input problem instead
+            raise InputError("dispersion model 'constant' is not usable (the reference fails on it too); "
+                             "provide a dispersion template")
+        else:
+            raise InputError(f"Bad choice '{disp_model}' for dispersion model, options are 'constant' or 'template'")
+        if sv.shape[0] == len(self.r_for_sv):
+            sv = sv.T
+        # normalise by the monopole at the largest r: bilinear interp2d + 200-point trapezoid
+        # over mu in [0, 1] (ccf_model.py:295-297, utils.py:45-56)
+        lin = RectBivariateSpline(self.r_for_sv, self.mu_for_sv, sv.T, kx=1, ky=1, s=0)
+        mu = np.linspace(0.0, 1.0, 200)
+        row = lin(self.r_for_sv[-1], mu)[0]
+        monopole_last = 1 * trapezoid(row * legendre(0)(mu), mu)
+        self.sv_rmu = sv / monopole_last
+
+    # ------------------------------------------------------------------ option handling
+    def _merged_options(self, kwargs):
+        opts = dict(self.model)
+        opts.update(kwargs)
+        return opts
+
+    def _engine(self, opts, need_fit=False):
+        """Context on the GPU for this option set (tables are built and uploaded once per set)."""
+        from .engine import Engine
+        key = (opts["rsd_model"], bool(opts["assume_isotropic"]), bool(opts["velocity_independent_of_AP"]),
+               opts["matter_model"], opts["mean_model"], bool(opts["empirical_corr"]),
+               bool(opts["realspace_ccf_from_data"]), self._fit_key(opts) if need_fit else None)
+        eng = self._engines.get(key)
+        if eng is None:
+            mt = _tables.build_model_tables(self, opts)
+            fit = self._fit_tables(opts) if need_fit else None
+            eng = Engine(mt, fit, device=self._device)
+            self._engines[key] = eng
+        return eng
+
+    def _fit_key(self, opts):
+        return None
+
+    def _fit_tables(self, opts):
+        return None
+
+    # ------------------------------------------------------------------ evaluation (GPU)
+    def get_interpolated_real_multipoles(self, beta=None):
+        """Host helper with the reference's semantics (ccf_model.py:299-326); not on the GPU path."""
+        from scipy.interpolate import PchipInterpolator
+        stack = np.array([self.real_multipoles[f"{ell}"] for ell in self.poles_r])
+        if self.fixed_real_input:
+            return np.atleast_2d(stack)
+        if beta is None:
+            raise InputError("Need to supply a valid value of beta for interpolation")
+        return np.atleast_2d(PchipInterpolator(self.beta, stack, axis=1)(beta))
+
+    def theory_xi_batch(self, s, mu, params, **kwargs):
+        """xi(s, mu) for every parameter row: float64[n, len(mu), len(s)]."""
+        opts = self._merged_options(kwargs)
+        s = np.atleast_1d(np.asarray(s, dtype=np.float64))
+        mu = np.atleast_1d(np.asarray(mu, dtype=np.float64))
+        return self._engine(opts).theory(params_to_rows(params), s, mu, None)[0]
+
+    def theory_xi(self, s, mu, params, **kwargs):
+        """Model xi(s, mu) (reference: ccf_model.py:538-789).
+
+        1-D ``s`` and ``mu`` give an array of shape (len(mu), len(s)); 2-D meshgrid inputs are
+        reduced to their sorted unique values first, as the reference does (:577).
+        """
+        s = np.atleast_1d(s)
+        mu = np.atleast_1d(mu)
+        if np.ndim(s) == 2 and np.ndim(mu) == 2:
+            if s.shape != mu.shape:
+                raise InputError("theory_xi: If arguments s and mu are 2D arrays they must have same shape")
+            s, mu = np.unique(s), np.unique(mu)
+        elif not (np.ndim(s) == 1 and np.ndim(mu) == 1):
+            raise InputError("theory_xi: arguments s and mu have incompatible dimensions")
+        self._check_point(params, kwargs)
+        return self.theory_xi_batch(s, mu, params, **kwargs)[0]
+
+    def theory_multipoles_batch(self, s, params, poles=(0, 2), **kwargs):
+        """Legendre multipoles for every parameter row: float64[n, len(poles), len(s)]."""
+        opts = self._merged_options(kwargs)
+        poles = np.atleast_1d(poles)
+        s = np.atleast_1d(np.asarray(s, dtype=np.float64))
+        if len(s) < 4:
+            raise InputError("theory_multipoles needs at least 4 values of s (bicubic interpolation in the "
+                             "reference, ccf_model.py:824)")
+        if np.any(np.diff(s) <= 0):
+            raise InputError("theory_multipoles: s must be strictly increasing")
+        mu, W = _tables.mu_projection_weights(poles)
+        return self._engine(opts).theory(params_to_rows(params), s, mu, W)[1]
+
+    def theory_multipoles(self, s, params, poles=[0, 2], **kwargs):
+        """Dict of model multipoles at ``s`` (reference: ccf_model.py:791-827)."""
+        self._check_point(params, kwargs)
+        poles = np.atleast_1d(poles)
+        out = self.theory_multipoles_batch(s, params, poles, **kwargs)[0]
+        return {f"{ell}": out[i] for i, ell in enumerate(poles)}
+
+    def theory_multipole_vector_batch(self, s, params, poles=(0, 2), **kwargs):
+        """Stacked theory vectors, float64[n, len(poles) * len(s)]."""
+        out = self.theory_multipoles_batch(s, params, poles, **kwargs)
+        return out.reshape(out.shape[0], -1)
+
+    def theory_multipole_vector(self, s, params, poles=[0, 2], **kwargs):
+        """Theory vector stacking all requested multipoles (reference: ccf_model.py:829-860)."""
+        self._check_point(params, kwargs)
+        return self.theory_multipole_vector_batch(s, params, poles, **kwargs)[0]
+
+    def _check_point(self, params, kwargs):
+        """Reference behaviour for missing parameters: KeyError on params['beta'] / ['fsigma8']."""
+        opts = self._merged_options(kwargs)
+        if isinstance(params, dict):
+            if not (self.fixed_real_input and opts["matter_model"] != "linear_bias"):
+                params["beta"]
+            params["fsigma8"]
+
+    def close(self):
+        for eng in self._engines.values():
+            eng.close()
+        self._engines = {}

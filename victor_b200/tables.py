@@ -1,0 +1,376 @@
+"""Host-side table builder: everything the CUDA kernels read, built once with scipy.
+
+The reference re-fits FITPACK / PCHIP splines inside every likelihood call
+(victor/ccf_model.py:299-326, 615-636, 654; victor/ccf_fit.py:193).  All of those fits are
+linear in their data and their abscissae only get rescaled by one per-point factor, so here
+they are done ONCE on the host, with the same scipy routines, and flattened into
+piecewise-polynomial coefficient tables the device evaluates directly:
+
+* every radial spline (xi_l(u; beta), V0(u), D0(u), sigma_v template SV(u)) is re-expressed
+  on ONE set of cells -- the union of all their knots in the template coordinate u = r/f --
+  so the kernel does a single cell search and a single local coordinate per quadrature point;
+  outside a spline's own knot range its cell polynomial is the constant boundary value, which
+  is exactly FITPACK's ``ext=3`` / ``bispeu`` clamping;
+* the beta dependence of xi^r and of the data vector (PCHIP over the reconstruction grid,
+  extrapolating outside it) becomes, per beta interval, a cubic in (beta - beta_k) whose four
+  coefficient sets are themselves spline fits (fit of the PCHIP coefficient vectors);
+* the mu-projection (bicubic interp2d -> 200-point trapezoid with Legendre weights,
+  ccf_model.py:824-825, utils.py:45-56) and the Simpson rule in velocity (ccf_model.py:690)
+  become fixed weight vectors;
+* the log-determinant of the (linearly blended) covariance uses the generalised eigenvalues
+  of (cov[hi], cov[lo]):  logdet((1-t) C_lo + t C_hi) = logdet C_lo + sum log1p(t (lam - 1)).
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+from scipy.integrate import simpson
+from scipy.interpolate import InterpolatedUnivariateSpline, PchipInterpolator, PPoly
+from scipy.special import legendre
+
+from .utils import InputError, trapezoid
+
+RSD_STREAMING, RSD_DISPERSION, RSD_KAISER = 0, 1, 2
+LIKE_LINEAR, LIKE_LOG = 0, 1          # lnL = -a/2 chi2 + norm   |   lnL = -m/2 log(1 + chi2/(nm-1)) + norm
+MAX_POLES = 3
+NPAR = 8                               # fsigma8, beta, sigma_v, aperp, apar, astar, M, Q
+PARAM_ORDER = ("fsigma8", "beta", "sigma_v", "aperp", "apar", "astar", "M", "Q")
+
+
+# --------------------------------------------------------------------------------------------
+# quadrature weight vectors
+# --------------------------------------------------------------------------------------------
+def velocity_nodes(nx=50):
+    """x nodes and weights of the velocity integral.
+
+    ``x = linspace(-6, 6)`` (ccf_model.py:570) and ``simps(..., x=v_par)`` (:690) with
+    v_par = x sigma_v.  Returns (x, w) with  integral f dv  =  sigma_v * sum_m w[m] f_m, the
+    weights being whatever scipy's composite Simpson rule assigns on this grid (for an even
+    number of points that includes its asymmetric end correction).
+    """
+    x = np.linspace(-6, 6, nx)
+    w = simpson(np.eye(nx), x=x, axis=1)
+    return x, w
+
+
+def mu_nodes(poles, nmu=100):
+    """mu grid of theory_multipoles (ccf_model.py:816-822): [0,1] for even poles, else [-1,1]."""
+    poles = np.atleast_1d(poles)
+    even = not np.any(poles % 2)
+    return (np.linspace(0, 1, nmu) if even else np.linspace(-1, 1, nmu)), even
+
+
+def mu_projection_weights(poles, nmu=100, npts=200):
+    """Weights W[l, k] with  xi_l(s_j) = sum_k W[l, k] xi(s_j, mu_k).
+
+    The reference builds ``interp2d(s, mu, xi, kind='cubic')`` and integrates it over 200 mu
+    values at each s_j with the trapezoid rule against (2l+1) L_l (ccf_model.py:824-825,
+    utils.py:45-56).  At a data abscissa s_j the tensor-product interpolant reduces to the
+    1-D not-a-knot cubic spline in mu through the row xi(s_j, :), so the whole operation is a
+    fixed linear functional of that row, independent of the s grid.
+    """
+    poles = np.atleast_1d(poles)
+    mu, even = mu_nodes(poles, nmu)
+    fine = np.linspace(0.0, 1.0, npts) if even else np.linspace(-1, 1, npts)
+    basis = np.empty((nmu, npts))
+    eye = np.eye(nmu)
+    for k in range(nmu):
+        basis[k] = InterpolatedUnivariateSpline(mu, eye[k], k=3)(fine)
+    tw = np.empty(npts)
+    d = np.diff(fine)
+    tw[0], tw[-1] = d[0] / 2, d[-1] / 2
+    tw[1:-1] = (d[:-1] + d[1:]) / 2
+    W = np.empty((len(poles), nmu))
+    for i, ell in enumerate(poles):
+        pref = (2 * ell + 1) if even else (2 * ell + 1) / 2
+        W[i] = pref * basis @ (tw * legendre(ell)(fine))
+    return mu, W
+
+
+# --------------------------------------------------------------------------------------------
+# splines -> per-cell cubic coefficients on a common cell set
+# --------------------------------------------------------------------------------------------
+def _shift_cubic(c_desc, delta):
+    """Re-expand p(d) = c3 d^3 + c2 d^2 + c1 d + c0 about d = delta; ascending output."""
+    c3, c2, c1, c0 = (np.longdouble(v) for v in c_desc)
+    dl = np.longdouble(delta)
+    n0 = ((c3 * dl + c2) * dl + c1) * dl + c0
+    n1 = (3 * c3 * dl + 2 * c2) * dl + c1
+    n2 = 3 * c3 * dl + c2
+    return np.array([n0, n1, n2, c3], dtype=np.float64)
+
+
+def spline_cells(x, y, knots):
+    """Cubic coefficients (ascending, local coordinate t = u - cell_origin) of the ext=3 spline
+    ``InterpolatedUnivariateSpline(x, y, ext=3)`` on every cell of ``knots``.
+
+    Cells: 0 = (-inf, knots[0]), i = [knots[i-1], knots[i]), last = [knots[-1], inf).
+    Cell origins: knots[0] for cell 0, knots[i-1] otherwise.  ``x`` must be a subset of
+    ``knots`` so that no cell straddles a knot of this spline.
+    """
+    x = np.asarray(x, float)
+    spl = InterpolatedUnivariateSpline(x, y, k=3)
+    pp = PPoly.from_spline(spl._eval_args)
+    brk, coef = pp.x, pp.c                      # coef[:, i] on [brk[i], brk[i+1]]
+    ncell = len(knots) + 1
+    out = np.zeros((ncell, 4))
+    lo_val, hi_val = float(spl(x[0])), float(spl(x[-1]))
+    for c in range(ncell):
+        a = knots[0] if c == 0 else knots[c - 1]
+        if c == 0 or a < x[0]:
+            # whole cell below the spline's range?  (cell [a, b) with b <= x[0])
+            b = knots[0] if c == 0 else (knots[c] if c < len(knots) else np.inf)
+            if b <= x[0]:
+                out[c, 0] = lo_val
+                continue
+            raise InputError("spline_cells: cell straddles the first knot of a spline")
+        if a >= x[-1]:
+            out[c, 0] = hi_val
+            continue
+        b = knots[c] if c < len(knots) else np.inf
+        mid = 0.5 * (a + min(b, x[-1]))
+        i = int(np.searchsorted(brk, mid, side="right") - 1)
+        i = min(max(i, 0), coef.shape[1] - 1)
+        while brk[i + 1] <= brk[i]:             # skip zero-length end intervals
+            i += 1
+        out[c] = _shift_cubic(coef[:, i], a - brk[i])
+    return out
+
+
+def union_knots(*grids):
+    ks = np.unique(np.concatenate([np.asarray(g, float) for g in grids]))
+    return ks
+
+
+def bucket_map(knots, max_buckets=4096):
+    """Uniform bucket grid over [0, knots[-1]] -> first candidate cell, plus scan length.
+
+    bucket b covers [b*h, (b+1)*h); base[b] = cell containing b*h; the kernel then advances
+    while u >= upper_knot(cell), at most ``maxscan`` times (number of knots strictly inside a
+    bucket).  The last bucket extends to +inf.
+    """
+    knots = np.asarray(knots, float)
+    span = knots[-1]
+    gaps = np.diff(knots)
+    h = gaps.min()
+    nb = int(np.ceil(span / h)) + 1
+    if nb > max_buckets:
+        nb = max_buckets
+        h = span / (nb - 1)
+    # snap h to an exactly representable reciprocal when the knots sit on a lattice
+    inv_h = 1.0 / h
+    if abs(inv_h - round(inv_h)) < 1e-12:
+        inv_h = float(round(inv_h))
+        h = 1.0 / inv_h
+    nb = int(np.floor(span * inv_h)) + 2
+    starts = np.arange(nb) * h
+    base = np.searchsorted(knots, starts, side="right").astype(np.int32)   # cell index of start
+    ends = starts + h
+    ends[-1] = np.inf
+    top = np.searchsorted(knots, ends, side="left")  # knots < end  -> highest cell reachable
+    maxscan = int(np.max(top - base))
+    return inv_h, base, maxscan
+
+
+# --------------------------------------------------------------------------------------------
+# the packed tables
+# --------------------------------------------------------------------------------------------
+@dataclass
+class ModelTables:
+    """Parameter-independent tables of the model half (CCFModel)."""
+    iaH: float
+    template_sigma8: float
+    vel_indep_AP: bool
+    rsd_model: int
+    n_ell: int                      # real-space multipoles entering xi(r, mu_r): 1 if isotropic
+    ells: np.ndarray                # their orders
+    beta_dependent: bool
+    beta_fixed: float               # beta used when the input has no beta dependence
+    knots: np.ndarray               # union knots [nk]; ncell = nk + 1
+    origin: np.ndarray              # cell origins [ncell]
+    upper: np.ndarray               # upper knot of each cell [ncell] (+inf for the last)
+    inv_h: float
+    bucket_base: np.ndarray         # int32 [nb]
+    maxscan: int
+    beta_grid: np.ndarray           # [nbeta] (>= 2) real-space reconstruction grid
+    xi_tab: np.ndarray              # [n_ell][nbint][4 (power of t, ascending)][ncell][4]
+    v0: np.ndarray                  # [ncell][4]
+    d0: np.ndarray                  # [ncell][4]
+    sv: np.ndarray                  # [ncell][4]   (isotropic sigma_v template)
+    x: np.ndarray                   # [nx]
+    wx: np.ndarray                  # [nx]  Simpson weights / sqrt(2 pi)
+    mu_resc: np.ndarray             # [50] nodes of the AP rescaling trapezoid
+    w_resc: np.ndarray              # [50] its weights
+    extras: dict = field(default_factory=dict)
+
+    @property
+    def ncell(self):
+        return len(self.knots) + 1
+
+
+@dataclass
+class FitTables:
+    """Tables of the likelihood half (CCFFit)."""
+    p: int
+    data_beta_dependent: bool
+    beta_ccf: np.ndarray            # [nbd] (>= 2)
+    data_tab: np.ndarray            # [nbint_d][4][p]
+    cov_fixed: bool
+    beta_cov: np.ndarray            # [nbc]
+    icov: np.ndarray                # [nbc][p][p]
+    logdet: np.ndarray              # [nbc]
+    lam: np.ndarray                 # [nbc][p]  generalised eigenvalues of (cov[last], cov[i])
+    like_kind: int
+    like_a: float                   # LINEAR: a;  LOG: m
+    like_nm1: float                 # LOG: nmocks - 1
+    use_logdet: bool
+
+
+def pchip_power_table(grid, values):
+    """PCHIP over ``grid`` of ``values`` [ngrid][...] -> (coef[nint][4 ascending][...]).
+
+    scipy's ``PchipInterpolator.c`` has shape (4 descending, nint, ...); with
+    ``extrapolate=True`` (default; ccf_model.py:326, ccf_fit.py:193) the end polynomials are
+    used outside the grid, so the interval index is simply clamped.
+    """
+    pc = PchipInterpolator(grid, values, axis=0)
+    c = np.asarray(pc.c)                      # (4, nint, ...)
+    return np.ascontiguousarray(np.moveaxis(c[::-1], 0, 1))  # (nint, 4 ascending, ...)
+
+
+def build_model_tables(state, options, nx=50):
+    """``state``: a loaded victor_b200.model.CCFModel; ``options``: its merged model dict."""
+    if options["matter_model"] != "template":
+        raise NotImplementedError(
+            f"matter_model '{options['matter_model']}' has no B200 path yet (only 'template')")
+    if options["mean_model"] != "linear" or options["empirical_corr"]:
+        raise NotImplementedError("only the 'linear' mean-velocity model without empirical correction "
+                                  "has a B200 path")
+    if options["realspace_ccf_from_data"]:
+        raise NotImplementedError("realspace_ccf from_data coordinates have no B200 path yet")
+    rsd = {"streaming": RSD_STREAMING, "dispersion": RSD_DISPERSION, "kaiser": RSD_KAISER}.get(
+        options["rsd_model"])
+    if rsd is None:
+        if options["rsd_model"] == "euclid_special":
+            raise NotImplementedError("rsd_model 'euclid_special' has no B200 path")
+        raise InputError(f"theory_xi: Unrecognised choice of model {options['rsd_model']}")
+    if not state.sv_isotropic:
+        raise NotImplementedError("anisotropic sigma_v(r, mu) templates have no B200 path yet")
+
+    r = np.asarray(state.r, float)
+    r31 = np.append([0.01], r)
+    knots = union_knots(r31, state.r_for_sv)
+    ncell = len(knots) + 1
+    origin = np.concatenate([[knots[0]], knots])
+    upper = np.concatenate([knots, [np.inf]])
+    inv_h, base, maxscan = bucket_map(knots)
+
+    # velocity templates (ccf_model.py:421-423, 449-450, 635-636): data at r31, knots r31
+    D31 = state.integrated_delta(r31)
+    d31 = state.delta(r31)
+    # velocity_terms() re-splines the profiles at their own abscissae before use (:422-423);
+    # an interpolating spline evaluated at its knots returns the data, so V0/D0 data are:
+    v0 = spline_cells(r31, r31 * D31, knots)
+    d0 = spline_cells(r31, 3.0 * (d31 - 2.0 * D31 / 3.0), knots)
+
+    # sigma_v template: all mu rows identical -> 1-D cubic spline in u (FITPACK tensor spline of a
+    # function constant in mu is that 1-D spline)
+    sv = spline_cells(state.r_for_sv, state.sv_rmu[0], knots)
+
+    # real-space multipoles
+    iso = bool(options["assume_isotropic"])
+    ells = np.array([0]) if iso else np.asarray(state.poles_r)
+    n_ell = len(ells)
+    beta_dep = not state.fixed_real_input
+    if beta_dep:
+        beta_grid = np.asarray(state.beta, float)
+        nbint = len(beta_grid) - 1
+        xi_tab = np.zeros((n_ell, nbint, 4, ncell, 4))
+        for i, ell in enumerate(ells):
+            pw = pchip_power_table(beta_grid, state.real_multipoles[f"{ell}"])  # (nbint, 4, nr)
+            for k in range(nbint):
+                for q in range(4):
+                    xi_tab[i, k, q] = spline_cells(r, pw[k, q], knots)
+    else:
+        beta_grid = np.array([0.0, 1.0])
+        xi_tab = np.zeros((n_ell, 1, 4, ncell, 4))
+        for i, ell in enumerate(ells):
+            xi_tab[i, 0, 0] = spline_cells(r, state.real_multipoles[f"{ell}"], knots)
+
+    x, w = velocity_nodes(nx)
+    mu_resc = np.linspace(1e-10, 1)
+    d = np.diff(mu_resc)
+    w_resc = np.zeros_like(mu_resc)
+    w_resc[:-1] += d / 2
+    w_resc[1:] += d / 2
+
+    return ModelTables(
+        iaH=float(state.iaH), template_sigma8=float(state.template_sigma8),
+        vel_indep_AP=bool(options["velocity_independent_of_AP"]), rsd_model=rsd,
+        n_ell=n_ell, ells=ells.astype(np.int32), beta_dependent=beta_dep, beta_fixed=0.40,
+        knots=knots, origin=origin, upper=upper, inv_h=inv_h,
+        bucket_base=base.astype(np.int32), maxscan=maxscan, beta_grid=beta_grid,
+        xi_tab=np.ascontiguousarray(xi_tab), v0=v0, d0=d0, sv=sv,
+        x=x, wx=w / np.sqrt(2 * np.pi), mu_resc=mu_resc, w_resc=w_resc)
+
+
+def likelihood_constants(like, p):
+    """(kind, a, nm1) of the likelihood form.  ccf_fit.py:455-473."""
+    form = str(like["form"]).lower()
+    nm = like.get("nmocks", 1)
+    if form == "sellentin":
+        return LIKE_LOG, float(nm), float(nm - 1)
+    if form == "hartlap":
+        return LIKE_LINEAR, float((nm - p - 2) / (nm - 1)), 0.0
+    if form == "percival":
+        npar = like["nparams"]  # KeyError if absent, like the reference
+        B = (nm - p - 2) / ((nm - p - 1) * (nm - p - 4))
+        m = npar + 2 + (nm - 1 + B * (p - npar)) / (1 + B * (p - npar))
+        return LIKE_LOG, float(m), float(nm - 1)
+    if form == "gaussian":
+        return LIKE_LINEAR, 1.0, 0.0
+    raise InputError("Unrecognised likelihood form")
+
+
+def build_fit_tables(fit, like):
+    """``fit``: a loaded victor_b200.fit.CCFFit; ``like``: the likelihood option dict."""
+    from scipy.linalg import eigh
+    p = len(fit.s) * len(fit.poles_s)
+    stack = np.array([fit.redshift_multipoles[f"{ell}"] for ell in fit.poles_s])
+    if fit.fixed_data:
+        beta_ccf = np.array([0.0, 1.0])
+        data_tab = np.zeros((1, 4, p))
+        data_tab[0, 0] = stack.reshape(p)
+    else:
+        beta_ccf = np.asarray(fit.beta_ccf, float)
+        vals = np.moveaxis(stack, 1, 0).reshape(len(beta_ccf), p)   # [nbeta][l*ns + j]
+        data_tab = pchip_power_table(beta_ccf, vals)
+    if fit.fixed_covmat:
+        cov = np.asarray(fit.covmat, float)[None]
+        icov = np.asarray(fit.icov, float)[None]
+        beta_cov = np.array([0.0])
+    else:
+        cov = np.asarray(fit.covmat, float)
+        icov = np.asarray(fit.icov, float)
+        beta_cov = np.asarray(fit.beta_covmat, float)
+    nbc = len(cov)
+    logdet = np.zeros(nbc)
+    lam = np.ones((nbc, p))
+    use_logdet = not fit.fixed_covmat
+    if use_logdet:
+        for i in range(nbc):
+            sign, ld = np.linalg.slogdet(cov[i])
+            try:
+                np.linalg.cholesky(cov[i])
+            except np.linalg.LinAlgError:
+                sign = 0
+            if sign != 1:
+                raise InputError(f"covariance matrix {i} is not positive definite; the reference would "
+                                 "return (-inf, inf) or an unnormalised likelihood for it")
+            logdet[i] = ld
+        for i in range(nbc - 1):
+            lam[i] = eigh(cov[-1], cov[i], eigvals_only=True)
+    kind, a, nm1 = likelihood_constants(like, p)
+    return FitTables(p=p, data_beta_dependent=not fit.fixed_data, beta_ccf=beta_ccf,
+                     data_tab=np.ascontiguousarray(data_tab), cov_fixed=bool(fit.fixed_covmat),
+                     beta_cov=beta_cov, icov=np.ascontiguousarray(icov), logdet=logdet, lam=lam,
+                     like_kind=kind, like_a=a, like_nm1=nm1, use_logdet=use_logdet)
