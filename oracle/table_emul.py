@@ -25,9 +25,11 @@ def _cells(mt, u):
     """Cell index and local coordinate for every u (bucket lookup + bounded scan)."""
     b = np.floor(u * mt.inv_h)
     b = np.clip(np.nan_to_num(b, nan=0.0), 0, len(mt.bucket_base) - 1).astype(np.int64)
-    cell = mt.bucket_base[b].astype(np.int64)
+    entry = mt.bucket_base[b].astype(np.int64)
+    flagged = entry < 0
+    cell = entry & 0x7FFFFFFF
     for _ in range(mt.maxscan):
-        cell = cell + (u >= mt.upper[cell])
+        cell = cell + (flagged & (u >= mt.upper[cell]))
     return cell, u - mt.origin[cell]
 
 

@@ -92,6 +92,7 @@ struct vb200_ctx {
     int opt_fast = 1, opt_nsplit = 0, opt_threads = 256;
     long long launches = 0;
     size_t k1_smem_limit = 0;
+    double xw[2 * kMaxNx] = {0};  // host copy of x_m | w_m for the kernel-parameter table
 };
 
 namespace {
@@ -112,6 +113,8 @@ int check_model(const vb200_model_tables *m) {
     if (m->ncell < 2 || m->nbucket < 1 || m->nx < 3 || m->nbeta < 2 || m->nresc < 2)
         return fail(VB200_EINVAL, "model tables: bad sizes");
     if (m->n_ell < 1 || m->n_ell > VB200_MAX_POLES) return fail(VB200_EINVAL, "model tables: bad n_ell");
+    if (m->nx > kMaxNx) return fail(VB200_EUNSUPPORTED, "more than 128 velocity nodes");
+    if (m->ncell > 32767) return fail(VB200_EUNSUPPORTED, "too many spline cells");
     if (m->rsd_model != VB200_RSD_STREAMING)
         return fail(VB200_EUNSUPPORTED, "only rsd_model 'streaming' has a kernel in this build");
     if (m->n_ell != 1)
@@ -139,7 +142,7 @@ int launch_k1(vb200_ctx *c, const double *d_params, long long n, const double *d
     const int npairs = jper * nmu;
     int threads = std::min(c->opt_threads, ((npairs + 31) / 32) * 32);
     threads = std::max(32, std::min(threads, 256));
-    const size_t smem = k1_smem_bytes(c->md.ncell, c->md.nx, jper, nmu, c->md.nbucket);
+    const size_t smem = k1_smem_bytes(c->md.ncell, jper, nmu, c->md.nbucket);
     if (smem > c->k1_smem_limit)
         return fail(VB200_EUNSUPPORTED, "grids too large for one block's shared memory (reduce len(s) * len(mu))");
     const long long blocks = n * nsplit;
@@ -160,6 +163,7 @@ int launch_k1(vb200_ctx *c, const double *d_params, long long n, const double *d
     a.nsplit = nsplit;
     a.xi_out = d_xi;
     a.mult_out = d_mult;
+    memcpy(a.xw, c->xw, sizeof(a.xw));
     if (c->opt_fast)
         k_multipoles<true><<<(unsigned)blocks, threads, smem, st>>>(a);
     else
@@ -285,6 +289,10 @@ int vb200_create(const vb200_model_tables *m, const vb200_fit_tables *f, int dev
     double etab[kExpTab];
     fill_exp_table(etab);
     if ((rc = upload(c, etab, (size_t)kExpTab, &d.exp_tab))) return bail(rc);
+    for (int i = 0; i < m->nx; ++i) {
+        c->xw[i] = m->x[i];
+        c->xw[kMaxNx + i] = m->wx[i];
+    }
 
     if (f) {
         if (f->ns < 1 || f->npoles < 1 || f->npoles > VB200_MAX_POLES || f->nmu < 2 || f->nbeta_ccf < 2 ||

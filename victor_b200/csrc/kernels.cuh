@@ -24,6 +24,7 @@ namespace vb200 {
 constexpr int kMaxPoles = 3;
 constexpr int kCoefPerCell = 12;  // xi (+1), B*V0, SV  -- 4 each
 constexpr int kExpTab = 32;
+constexpr int kMaxNx = 128;       // velocity nodes that fit in the kernel-parameter table
 
 struct ModelDev {
     double iaH, s8t, beta_fixed, inv_h;
@@ -44,6 +45,7 @@ struct K1Args {
     int jper, nsplit;
     double *xi_out;    // [n][nmu][ns] or null
     double *mult_out;  // [n][L][ns]  or null
+    double xw[2 * kMaxNx];  // x_m then Simpson weight / sqrt(2 pi): read through the constant bank
 };
 
 struct FitDev {
@@ -73,39 +75,6 @@ __device__ __forceinline__ double fast_rsqrt(double a) {
     double p = fma(0.375, e, 0.5);
     double pe = p * e;
     return fma(y, pe, y);
-}
-
-__device__ __forceinline__ double fast_rcp(double a) {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-    double e = fma(-a, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-a, y, 1.0);
-    return fma(y, e, y);
-}
-
-// 2^(-c * z2) with c = log2(e) / 2, i.e. exp(-z2 / 2); z2 >= 0.  Table-assisted:
-// -c z2 = (32 n + j + r) / 32, |r| <= 1/2;  result = 2^n * 2^(j/32) * exp(r ln2 / 32).
-__device__ __forceinline__ double fast_gauss(double z2, const double *tab) {
-    const double kMagic = 6755399441055744.0;        // 1.5 * 2^52
-    const double kScale = -23.083120654223414;        // -16 * log2(e)
-    double tn = fma(z2, kScale, kMagic);
-    int ni = __double2loint(tn);
-    double nf = tn - kMagic;
-    double r = fma(z2, kScale, -nf);
-    // exp(r * ln2/32), Taylor to degree 6: |r ln2/32| <= 0.0109 -> remainder 4e-18
-    double p = 1.4345655584131932e-13;
-    p = fma(p, r, 3.9737099845494154e-11);
-    p = fma(p, r, 9.172562701824643e-09);
-    p = fma(p, r, 1.6938509724371819e-06);
-    p = fma(p, r, 2.3459619820224677e-04);
-    p = fma(p, r, 2.166084939249829e-02);
-    p = fma(p, r, 1.0);
-    int j = ni & (kExpTab - 1);
-    int n = max(ni >> 5, -1000);
-    double t = tab[j];
-    t = __hiloint2double(__double2hiint(t) + (n << 20), __double2loint(t));
-    return p * t;
 }
 
 template <bool kFast>
@@ -141,12 +110,69 @@ __device__ __forceinline__ int beta_interval(const double *grid, int n, double b
 // ---------------------------------------------------------------------------------------
 // K1
 // ---------------------------------------------------------------------------------------
-// dynamic shared memory layout (doubles unless noted), see k1_smem_bytes():
-//   coef[ncell*12] | origin[ncell] | upper[ncell] | cm[nx] | xs[nx] | wxs[nx] | etab[32] |
-//   stage[jper*nmu] | scal[8] | int bucket_base[nbucket]
-__host__ __device__ inline size_t k1_smem_bytes(int ncell, int nx, int jper, int nmu, int nbucket) {
-    size_t d = (size_t)ncell * (kCoefPerCell + 2) + 3 * (size_t)nx + kExpTab + (size_t)jper * nmu + 8;
+// Shared memory (dynamic), see k1_smem_bytes():
+//   rec[ncell][14]  per-row cell records: xi+1 (4) | B*V0 (4) | SV (4) | origin | pad   (16 B aligned;
+//                   stride 112 B = 28 banks, so 8 consecutive cells tile the 32 banks exactly)
+//   etab[32]        2^(j/32)
+//   stage[jper*nmu] xi(s_j, mu_k) of this block
+//   scal[8]         per-row scalars
+//   upper[ncell]    upper knot of each cell (slow path of the cell search only)
+//   int bbase[nbucket]  bucket -> first cell; bit 31 set when a knot lies strictly inside the bucket
+constexpr int kRec = 14;
+constexpr int kBucketFlag = (int)0x80000000;
+
+__host__ __device__ inline size_t k1_smem_bytes(int ncell, int jper, int nmu, int nbucket) {
+    size_t d = (size_t)ncell * (kRec + 1) + kExpTab + (size_t)jper * nmu + 8;
     return d * sizeof(double) + (size_t)nbucket * sizeof(int);
+}
+
+__device__ __forceinline__ double2 lds_f64x2(unsigned addr) {
+    double2 v;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int lds_s32(unsigned addr) {
+    int v;
+    asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// exp(r ln2/32) Taylor coefficients (degree 6) -- kept in constant memory so that the FP64 pipe
+// reads them as c[bank][offset] operands instead of re-materialising them with integer moves
+__constant__ double kExpPoly[6] = {2.166084939249829e-02, 2.3459619820224677e-04, 1.6938509724371819e-06,
+                                   9.172562701824643e-09, 3.9737099845494154e-11, 1.4345655584131932e-13};
+
+// exp(-z2/2) from the shared-memory table at 32-bit shared address `etab_s`
+__device__ __forceinline__ double gauss_tab(double z2, unsigned etab_s) {
+    const double kMagic = 6755399441055744.0;   // 1.5 * 2^52
+    const double kScale = -23.083120654223414;   // -16 log2(e)
+    const double tn = fma(z2, kScale, kMagic);
+    const int ni = __double2loint(tn);
+    const double nf = tn - kMagic;
+    const double r = fma(z2, kScale, -nf);
+    double p = fma(kExpPoly[5], r, kExpPoly[4]);
+    p = fma(p, r, kExpPoly[3]);
+    p = fma(p, r, kExpPoly[2]);
+    p = fma(p, r, kExpPoly[1]);
+    p = fma(p, r, kExpPoly[0]);
+    p = fma(p, r, 1.0);
+    const int n = max(ni >> 5, -1000);
+    double t = lds_f64(etab_s + ((ni & (kExpTab - 1)) << 3));
+    t = __hiloint2double(__double2hiint(t) + (n << 20), __double2loint(t));
+    return p * t;
+}
+
+// 1/a: MUFU seed (rel. error e ~ 2^-20) then y (1 + e + e^2): cubic convergence
+__device__ __forceinline__ double rcp_cubic(double a) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double e = fma(-a, y, 1.0);
+    return fma(y, fma(e, e, e), y);
 }
 
 template <bool kFast>
@@ -154,16 +180,12 @@ __global__ void __launch_bounds__(256) k_multipoles(const __grid_constant__ K1Ar
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const ModelDev &m = a.m;
     const int ncell = m.ncell, nx = m.nx;
-    double *coef = reinterpret_cast<double *>(smem_raw);
-    double *origin = coef + (size_t)ncell * kCoefPerCell;
-    double *upper = origin + ncell;
-    double *cm = upper + ncell;
-    double *xs = cm + nx;
-    double *wxs = xs + nx;
-    double *etab = wxs + nx;
+    double *rec = reinterpret_cast<double *>(smem_raw);
+    double *etab = rec + (size_t)ncell * kRec;
     double *stage = etab + kExpTab;
     double *scal = stage + (size_t)a.jper * a.nmu;
-    int *bbase = reinterpret_cast<int *>(scal + 8);
+    double *upper = scal + 8;
+    int *bbase = reinterpret_cast<int *>(upper + ncell);
 
     const int tid = threadIdx.x, nthr = blockDim.x;
     const long long row = blockIdx.x / a.nsplit;
@@ -196,28 +218,18 @@ __global__ void __launch_bounds__(256) k_multipoles(const __grid_constant__ K1Ar
             scal[0] = f;
             scal[1] = aperp / f;
             scal[2] = apar / f;
-            scal[3] = sigv * iaHt / f;   // velocity node spacing in u-units per unit x
-            scal[4] = Av / sigv;         // B: mean velocity in units of sigma_v per unit V0 mu_r
+            scal[3] = sigv * iaHt / f;   // displacement in u-units per unit x
+            scal[4] = Av / sigv;         // B: mean velocity / sigma_v per unit V0 mu_r
         }
     }
-    // ---- copy the parameter-independent pieces ----
-    for (int i = tid; i < ncell; i += nthr) {
-        origin[i] = m.origin[i];
-        upper[i] = m.upper[i];
-    }
+    for (int i = tid; i < ncell; i += nthr) upper[i] = m.upper[i];
     for (int i = tid; i < m.nbucket; i += nthr) bbase[i] = m.bucket_base[i];
     if (tid < kExpTab) etab[tid] = m.exp_tab[tid];
     __syncthreads();
-    const double B = scal[4];
-    for (int i = tid; i < nx; i += nthr) {
-        double x = m.x[i];
-        cm[i] = x * scal[3];
-        xs[i] = x;
-        wxs[i] = m.wx[i];
-    }
-    // ---- this row's cell table: xi^r(u; beta) from the beta power table (+1 folded into c0),
-    //      B * V0(u), SV(u) ----
+    // ---- this row's cell records: xi^r(u; beta) from the beta power table (+1 folded into c0),
+    //      B * V0(u), SV(u), origin ----
     {
+        const double B = scal[4];
         int kb = 0;
         double tb = 0.0;
         if (m.beta_dependent) {
@@ -230,20 +242,27 @@ __global__ void __launch_bounds__(256) k_multipoles(const __grid_constant__ K1Ar
             const int cell = i >> 2, c = i & 3;
             double v = fma(fma(fma(tab[3 * per + i], tb, tab[2 * per + i]), tb, tab[per + i]), tb, tab[i]);
             if (c == 0) v += 1.0;
-            coef[cell * kCoefPerCell + c] = v;
-            coef[cell * kCoefPerCell + 4 + c] = B * m.v0[i];
-            coef[cell * kCoefPerCell + 8 + c] = m.sv[i];
+            double *r = rec + cell * kRec;
+            r[c] = v;
+            r[4 + c] = B * m.v0[i];
+            r[8 + c] = m.sv[i];
+            if (c == 0) {
+                r[12] = m.origin[cell];
+                r[13] = 0.0;
+            }
         }
     }
     __syncthreads();
 
-    // ---- quadrature: thread <-> (s_j, mu_k), loop over velocity nodes ----
-    const double sperp_f = scal[1], spar_f = scal[2];
+    // ---- quadrature: thread <-> (s_j, mu_k), loop over the velocity nodes in registers ----
+    const double sperp_f = scal[1], spar_f = scal[2], kappa = scal[3];
     const int nmu = a.nmu;
     const int npairs = jn * nmu;
     const int nbm1 = m.nbucket - 1;
-    const int maxscan = m.maxscan;
     const double inv_h = m.inv_h;
+    const unsigned rec_s = (unsigned)__cvta_generic_to_shared(rec);
+    const unsigned etab_s = (unsigned)__cvta_generic_to_shared(etab);
+    const unsigned bb_s = (unsigned)__cvta_generic_to_shared(bbase);
     for (int pidx = tid; pidx < npairs; pidx += nthr) {
         const int jl = pidx / nmu, k = pidx - jl * nmu;
         const double sj = a.s[j0 + jl];
@@ -253,31 +272,38 @@ __global__ void __launch_bounds__(256) k_multipoles(const __grid_constant__ K1Ar
         double acc = 0.0;
 #pragma unroll 2
         for (int mi = 0; mi < nx; ++mi) {
-            const double rp = Spar - cm[mi];
-            const double u2 = fma(rp, rp, Sperp2);
+            const double xm = a.xw[mi], wm = a.xw[kMaxNx + mi];   // uniform: constant-bank reads
+            const double rp = fma(-xm, kappa, Spar);              // ccf_model.py:648-650
+            const double u2 = fma(rp, rp, Sperp2);                // :651
             double u, mur;
-            radius<kFast>(u2, rp, u, mur);
+            radius<kFast>(u2, rp, u, mur);                        // :651-652
             // bucket = floor(u * inv_h) through a round-down FMA onto 1.5 * 2^52
             int b = __double2loint(__fma_rd(u, inv_h, 6755399441055744.0));
             b = min(max(b, 0), nbm1);
-            int cell = bbase[b];
-            for (int sc = 0; sc < maxscan; ++sc) cell += (u >= upper[cell]) ? 1 : 0;
-            const double t = u - origin[cell];
-            const double *c = coef + cell * kCoefPerCell;
-            const double xi1 = horner3(c, t);
-            const double vb = horner3(c + 4, t);
-            const double sv = horner3(c + 8, t);
+            int cell = lds_s32(bb_s + (b << 2));
+            if (cell < 0) {  // a knot lies inside this bucket: finish the search by comparison
+                cell &= ~kBucketFlag;
+                for (int sc = 0; sc < m.maxscan; ++sc) cell += (u >= upper[cell]) ? 1 : 0;
+            }
+            const unsigned ra = rec_s + cell * (kRec * 8);
+            const double2 c89 = lds_f64x2(ra + 64), cab = lds_f64x2(ra + 80);
+            const double t = u - lds_f64(ra + 96);
+            const double2 c45 = lds_f64x2(ra + 32), c67 = lds_f64x2(ra + 48);
+            const double2 c01 = lds_f64x2(ra), c23 = lds_f64x2(ra + 16);
+            const double sv = fma(fma(fma(cab.y, t, cab.x), t, c89.y), t, c89.x);   // :654-655
+            const double vb = fma(fma(fma(c67.y, t, c67.x), t, c45.y), t, c45.x);   // :635, :656
+            const double xi1 = fma(fma(fma(c23.y, t, c23.x), t, c01.y), t, c01.x);  // :621, :683
             double q, g;
             if (kFast) {
-                q = fast_rcp(sv);
-                const double z = fma(-vb, mur, xs[mi]) * q;
-                g = fast_gauss(z * z, etab);
+                q = rcp_cubic(sv);
+                const double z = fma(-vb, mur, xm) * q;                               // :656
+                g = gauss_tab(z * z, etab_s);
             } else {
                 q = 1.0 / sv;
-                const double z = (xs[mi] - vb * mur) * q;
+                const double z = (xm - vb * mur) * q;
                 g = exp(-0.5 * z * z);
             }
-            acc = fma(wxs[mi] * (xi1 * q), g, acc);
+            acc = fma(wm * (xi1 * q), g, acc);                                        // :690
         }
         stage[pidx] = acc - 1.0;  // ccf_model.py:690
     }
@@ -441,9 +467,9 @@ __global__ void k_math_selftest(const double *x, long long n, const double *etab
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double v = x[i];
-    out[i] = fast_gauss(v, tab);   // exp(-v/2)
+    out[i] = gauss_tab(v, (unsigned)__cvta_generic_to_shared(tab));   // exp(-v/2)
     out[n + i] = fast_rsqrt(v);
-    out[2 * n + i] = fast_rcp(v);
+    out[2 * n + i] = rcp_cubic(v);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -141,34 +141,51 @@ def union_knots(*grids):
     return ks
 
 
-def bucket_map(knots, max_buckets=4096):
-    """Uniform bucket grid over [0, knots[-1]] -> first candidate cell, plus scan length.
+BUCKET_FLAG = np.int32(-2 ** 31)   # bit 31 of a bucket entry: a knot lies strictly inside the bucket
 
-    bucket b covers [b*h, (b+1)*h); base[b] = cell containing b*h; the kernel then advances
-    while u >= upper_knot(cell), at most ``maxscan`` times (number of knots strictly inside a
-    bucket).  The last bucket extends to +inf.
+
+def _bucket_try(knots, inv_h):
+    span = knots[-1]
+    nb = int(np.floor(span * inv_h)) + 2
+    h = 1.0 / inv_h
+    starts = np.arange(nb) * h
+    ends = starts + h
+    ends[-1] = np.inf
+    base = np.searchsorted(knots, starts, side="right")      # knots <= start: cell holding the start
+    top = np.searchsorted(knots, ends, side="left")          # knots <  end : highest cell reachable
+    return base, top
+
+
+def bucket_map(knots, candidates=(512, 1024, 2048)):
+    """Uniform bucket grid over [0, knots[-1]] -> first candidate cell, flag and scan length.
+
+    Bucket b covers [b/inv_h, (b+1)/inv_h); the last one extends to +inf.  entry[b] = index of
+    the cell containing the bucket start, with bit 31 set when further knots lie strictly inside
+    the bucket, in which case the kernel advances while u >= upper(cell), at most ``maxscan``
+    times.  The spacing is chosen among the knot lattice (1 / smallest gap, snapped to an exact
+    reciprocal when it is one) and a few fine uniform grids, whichever flags the fewest buckets:
+    knots on a lattice (BOSS: integers) give buckets that never straddle a knot.
     """
     knots = np.asarray(knots, float)
     span = knots[-1]
-    gaps = np.diff(knots)
-    h = gaps.min()
-    nb = int(np.ceil(span / h)) + 1
-    if nb > max_buckets:
-        nb = max_buckets
-        h = span / (nb - 1)
-    # snap h to an exactly representable reciprocal when the knots sit on a lattice
-    inv_h = 1.0 / h
-    if abs(inv_h - round(inv_h)) < 1e-12:
-        inv_h = float(round(inv_h))
-        h = 1.0 / inv_h
-    nb = int(np.floor(span * inv_h)) + 2
-    starts = np.arange(nb) * h
-    base = np.searchsorted(knots, starts, side="right").astype(np.int32)   # cell index of start
-    ends = starts + h
-    ends[-1] = np.inf
-    top = np.searchsorted(knots, ends, side="left")  # knots < end  -> highest cell reachable
+    lattice = 1.0 / np.diff(knots).min()
+    if abs(lattice - round(lattice)) < 1e-9 * max(1.0, lattice):
+        lattice = float(round(lattice))
+    options = [lattice] + [(n - 2) / span for n in candidates]
+    best = None
+    for inv_h in options:
+        if span * inv_h > 8190:
+            continue
+        base, top = _bucket_try(knots, inv_h)
+        flagged = np.count_nonzero(top > base)
+        score = (flagged / len(base), len(base))
+        if best is None or score < best[0]:
+            best = (score, inv_h, base, top)
+    _, inv_h, base, top = best
+    entry = base.astype(np.int32)
+    entry[top > base] |= BUCKET_FLAG
     maxscan = int(np.max(top - base))
-    return inv_h, base, maxscan
+    return float(inv_h), entry, maxscan
 
 
 # --------------------------------------------------------------------------------------------
@@ -308,7 +325,7 @@ def build_model_tables(state, options, nx=50):
         vel_indep_AP=bool(options["velocity_independent_of_AP"]), rsd_model=rsd,
         n_ell=n_ell, ells=ells.astype(np.int32), beta_dependent=beta_dep, beta_fixed=0.40,
         knots=knots, origin=origin, upper=upper, inv_h=inv_h,
-        bucket_base=base.astype(np.int32), maxscan=maxscan, beta_grid=beta_grid,
+        bucket_base=base, maxscan=maxscan, beta_grid=beta_grid,
         xi_tab=np.ascontiguousarray(xi_tab), v0=v0, d0=d0, sv=sv,
         x=x, wx=w / np.sqrt(2 * np.pi), mu_resc=mu_resc, w_resc=w_resc)
 
