@@ -30,7 +30,7 @@ def _cells(mt, u):
     cell = entry & 0x7FFFFFFF
     for _ in range(mt.maxscan):
         cell = cell + (flagged & (u >= mt.upper[cell]))
-    return cell, u - mt.origin[cell]
+    return cell, np.where(u - mt.origin[cell] < 0, 0.0, u - mt.origin[cell])
 
 
 def _horner(c, cell, t):

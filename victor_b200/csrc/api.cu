@@ -93,6 +93,7 @@ struct vb200_ctx {
     long long launches = 0;
     size_t k1_smem_limit = 0;
     double xw[2 * kMaxNx] = {0};  // host copy of x_m | w_m for the kernel-parameter table
+    bool has_flags = false;       // some bucket entry carries the interior-knot flag
 };
 
 namespace {
@@ -164,10 +165,13 @@ int launch_k1(vb200_ctx *c, const double *d_params, long long n, const double *d
     a.xi_out = d_xi;
     a.mult_out = d_mult;
     memcpy(a.xw, c->xw, sizeof(a.xw));
-    if (c->opt_fast)
-        k_multipoles<true><<<(unsigned)blocks, threads, smem, st>>>(a);
-    else
-        k_multipoles<false><<<(unsigned)blocks, threads, smem, st>>>(a);
+    const int variant = (c->opt_fast ? 2 : 0) | (c->has_flags ? 1 : 0);
+    switch (variant) {
+        case 3: k_multipoles<true, true><<<(unsigned)blocks, threads, smem, st>>>(a); break;
+        case 2: k_multipoles<true, false><<<(unsigned)blocks, threads, smem, st>>>(a); break;
+        case 1: k_multipoles<false, true><<<(unsigned)blocks, threads, smem, st>>>(a); break;
+        default: k_multipoles<false, false><<<(unsigned)blocks, threads, smem, st>>>(a); break;
+    }
     CK(cudaGetLastError());
     c->launches++;
     return VB200_OK;
@@ -289,6 +293,7 @@ int vb200_create(const vb200_model_tables *m, const vb200_fit_tables *f, int dev
     double etab[kExpTab];
     fill_exp_table(etab);
     if ((rc = upload(c, etab, (size_t)kExpTab, &d.exp_tab))) return bail(rc);
+    for (int i = 0; i < m->nbucket; ++i) c->has_flags = c->has_flags || (m->bucket_base[i] < 0);
     for (int i = 0; i < m->nx; ++i) {
         c->xw[i] = m->x[i];
         c->xw[kMaxNx + i] = m->wx[i];
@@ -335,13 +340,14 @@ int vb200_create(const vb200_model_tables *m, const vb200_fit_tables *f, int dev
 
     // allow the large dynamic shared memory carve-out (dense mu grids stage up to ~200 KB)
     c->k1_smem_limit = std::min<size_t>((size_t)prop.sharedMemPerBlockOptin, (size_t)200 * 1024);
-    cudaError_t e1 = cudaFuncSetAttribute(k_multipoles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)c->k1_smem_limit);
-    cudaError_t e2 = cudaFuncSetAttribute(k_multipoles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)c->k1_smem_limit);
-    if (e1 != cudaSuccess || e2 != cudaSuccess)
-        return bail(fail(VB200_ECUDA, std::string("cudaFuncSetAttribute: ") +
-                                          cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)));
+    const void *variants[4] = {(const void *)k_multipoles<true, true>, (const void *)k_multipoles<true, false>,
+                               (const void *)k_multipoles<false, true>, (const void *)k_multipoles<false, false>};
+    for (const void *fn : variants) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)c->k1_smem_limit);
+        if (e != cudaSuccess)
+            return bail(fail(VB200_ECUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)));
+    }
     *out = c;
     return VB200_OK;
 }

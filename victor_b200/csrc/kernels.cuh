@@ -175,7 +175,22 @@ __device__ __forceinline__ double rcp_cubic(double a) {
     return fma(y, fma(e, e, e), y);
 }
 
-template <bool kFast>
+// keep a value in a register: the compiler cannot re-derive the result of a volatile asm, so it
+// stops re-materialising loop invariants (shared-window base, reciprocal spacing) inside the loop
+__device__ __forceinline__ unsigned pin_u32(unsigned v) {
+    unsigned r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+__device__ __forceinline__ double pin_f64(double v) {
+    double r;
+    asm volatile("mov.f64 %0, %1;" : "=d"(r) : "d"(v));
+    return r;
+}
+
+// kFast: hand-rolled rsqrt / rcp / exp (else CUDA libm).  kFlags: some bucket holds a knot in
+// its interior, so the cell search may need the comparison path (non-lattice knot sets).
+template <bool kFast, bool kFlags>
 __global__ void __launch_bounds__(256) k_multipoles(const __grid_constant__ K1Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const ModelDev &m = a.m;
@@ -258,11 +273,11 @@ __global__ void __launch_bounds__(256) k_multipoles(const __grid_constant__ K1Ar
     const double sperp_f = scal[1], spar_f = scal[2], kappa = scal[3];
     const int nmu = a.nmu;
     const int npairs = jn * nmu;
-    const int nbm1 = m.nbucket - 1;
-    const double inv_h = m.inv_h;
-    const unsigned rec_s = (unsigned)__cvta_generic_to_shared(rec);
-    const unsigned etab_s = (unsigned)__cvta_generic_to_shared(etab);
-    const unsigned bb_s = (unsigned)__cvta_generic_to_shared(bbase);
+    const unsigned nbm1 = (unsigned)(m.nbucket - 1);
+    const double inv_h = pin_f64(m.inv_h);
+    const unsigned rec_s = pin_u32((unsigned)__cvta_generic_to_shared(rec));
+    const unsigned etab_s = pin_u32((unsigned)__cvta_generic_to_shared(etab));
+    const unsigned bb_s = pin_u32((unsigned)__cvta_generic_to_shared(bbase));
     for (int pidx = tid; pidx < npairs; pidx += nthr) {
         const int jl = pidx / nmu, k = pidx - jl * nmu;
         const double sj = a.s[j0 + jl];
@@ -277,17 +292,24 @@ __global__ void __launch_bounds__(256) k_multipoles(const __grid_constant__ K1Ar
             const double u2 = fma(rp, rp, Sperp2);                // :651
             double u, mur;
             radius<kFast>(u2, rp, u, mur);                        // :651-652
-            // bucket = floor(u * inv_h) through a round-down FMA onto 1.5 * 2^52
-            int b = __double2loint(__fma_rd(u, inv_h, 6755399441055744.0));
-            b = min(max(b, 0), nbm1);
+            // bucket = floor(u * inv_h) through a round-down FMA onto 1.5 * 2^52 (u >= 0; NaN -> 0)
+            const unsigned b = min((unsigned)__double2loint(__fma_rd(u, inv_h, 6755399441055744.0)), nbm1);
             int cell = lds_s32(bb_s + (b << 2));
-            if (cell < 0) {  // a knot lies inside this bucket: finish the search by comparison
-                cell &= ~kBucketFlag;
-                for (int sc = 0; sc < m.maxscan; ++sc) cell += (u >= upper[cell]) ? 1 : 0;
+            if (kFlags) {
+                if (cell < 0) {  // a knot lies inside this bucket: finish the search by comparison
+                    cell &= ~kBucketFlag;
+                    for (int sc = 0; sc < m.maxscan; ++sc) cell += (u >= upper[cell]) ? 1 : 0;
+                }
             }
             const unsigned ra = rec_s + cell * (kRec * 8);
             const double2 c89 = lds_f64x2(ra + 64), cab = lds_f64x2(ra + 80);
-            const double t = u - lds_f64(ra + 96);
+            double t = u - lds_f64(ra + 96);
+            {   // t = max(t, 0): below the first knot every spline is its boundary value (ext=3), which
+                // is the first cell's cubic at t = 0.  Done on the sign bit with integer ops; a
+                // negative t becomes a positive denormal-sized number, i.e. 0 for the cubic.
+                const int hi = __double2hiint(t);
+                t = __hiloint2double(hi & ~(hi >> 31), __double2loint(t));
+            }
             const double2 c45 = lds_f64x2(ra + 32), c67 = lds_f64x2(ra + 48);
             const double2 c01 = lds_f64x2(ra), c23 = lds_f64x2(ra + 16);
             const double sv = fma(fma(fma(cab.y, t, cab.x), t, c89.y), t, c89.x);   // :654-655

@@ -153,7 +153,9 @@ def _bucket_try(knots, inv_h):
     ends[-1] = np.inf
     base = np.searchsorted(knots, starts, side="right")      # knots <= start: cell holding the start
     top = np.searchsorted(knots, ends, side="left")          # knots <  end : highest cell reachable
-    return base, top
+    # cell 0 (below the first knot) is never entered: the kernel clamps the local coordinate at
+    # 0, and every spline below the first knot equals the first cell's cubic at t = 0 (ext=3)
+    return np.maximum(base, 1), np.maximum(top, 1)
 
 
 def bucket_map(knots, candidates=(512, 1024, 2048)):
