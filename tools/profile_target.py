@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--fast", type=int, default=1)
     ap.add_argument("--threads", type=int, default=256)
     ap.add_argument("--nsplit", type=int, default=0)
+    ap.add_argument("--ilp", type=int, default=2)
     args = ap.parse_args()
     model, data = boss_blocks()
     fit = CCFFit(model, data, device=0)
@@ -31,6 +32,7 @@ def main():
     eng.set_option("fast_math", args.fast)
     eng.set_option("threads", args.threads)
     eng.set_option("nsplit", args.nsplit)
+    eng.set_option("ilp", args.ilp)
     n = args.batch
     dev = torch.device("cuda", 0)
     d_params = torch.from_numpy(params_to_rows(synthetic_batch(n))).to(dev)
@@ -45,7 +47,7 @@ def main():
         b.record()
         torch.cuda.synchronize()
         times.append(a.elapsed_time(b))
-    print(f"batch={n} fast={args.fast} threads={args.threads} nsplit={args.nsplit} "
+    print(f"batch={n} fast={args.fast} threads={args.threads} nsplit={args.nsplit} ilp={args.ilp} "
           f"ms={['%.3f' % t for t in times]} evals/s={n / (min(times) * 1e-3):.4g} "
           f"chi2[0]={float(d_chi2[0]):.10f}")
     fit.close()

@@ -89,7 +89,7 @@ struct vb200_ctx {
     std::vector<void *> owned;
     Scratch sc_params, sc_theory, sc_chi2, sc_lnl, sc_xi, sc_mult, sc_grid;
     // options
-    int opt_fast = 1, opt_nsplit = 0, opt_threads = 256;
+    int opt_fast = 1, opt_nsplit = 0, opt_threads = 256, opt_ilp = 4;
     long long launches = 0;
     size_t k1_smem_limit = 0;
     double xw[2 * kMaxNx] = {0};  // host copy of x_m | w_m for the kernel-parameter table
@@ -124,6 +124,19 @@ int check_model(const vb200_model_tables *m) {
     if (!(m->inv_h > 0.0) || !(m->iaH > 0.0) || !(m->template_sigma8 > 0.0))
         return fail(VB200_EINVAL, "model tables: bad scalars");
     return VB200_OK;
+}
+
+typedef void (*k1_fn)(const K1Args);
+
+k1_fn pick_k1(bool fast, bool flags, int ilp) {
+    if (!fast) return flags ? k_multipoles<false, true, 1> : k_multipoles<false, false, 1>;
+    if (flags) return ilp >= 2 ? k_multipoles<true, true, 2> : k_multipoles<true, true, 1>;
+    switch (ilp) {
+        case 1: return k_multipoles<true, false, 1>;
+        case 3: return k_multipoles<true, false, 3>;
+        case 4: return k_multipoles<true, false, 4>;
+        default: return k_multipoles<true, false, 2>;
+    }
 }
 
 int launch_k1(vb200_ctx *c, const double *d_params, long long n, const double *d_s, int ns,
@@ -165,13 +178,9 @@ int launch_k1(vb200_ctx *c, const double *d_params, long long n, const double *d
     a.xi_out = d_xi;
     a.mult_out = d_mult;
     memcpy(a.xw, c->xw, sizeof(a.xw));
-    const int variant = (c->opt_fast ? 2 : 0) | (c->has_flags ? 1 : 0);
-    switch (variant) {
-        case 3: k_multipoles<true, true><<<(unsigned)blocks, threads, smem, st>>>(a); break;
-        case 2: k_multipoles<true, false><<<(unsigned)blocks, threads, smem, st>>>(a); break;
-        case 1: k_multipoles<false, true><<<(unsigned)blocks, threads, smem, st>>>(a); break;
-        default: k_multipoles<false, false><<<(unsigned)blocks, threads, smem, st>>>(a); break;
-    }
+    auto fn = pick_k1(c->opt_fast != 0, c->has_flags, c->opt_ilp);
+    void *kargs[] = {(void *)&a};
+    CK(cudaLaunchKernel((const void *)fn, dim3((unsigned)blocks), dim3(threads), kargs, smem, st));
     CK(cudaGetLastError());
     c->launches++;
     return VB200_OK;
@@ -340,14 +349,15 @@ int vb200_create(const vb200_model_tables *m, const vb200_fit_tables *f, int dev
 
     // allow the large dynamic shared memory carve-out (dense mu grids stage up to ~200 KB)
     c->k1_smem_limit = std::min<size_t>((size_t)prop.sharedMemPerBlockOptin, (size_t)200 * 1024);
-    const void *variants[4] = {(const void *)k_multipoles<true, true>, (const void *)k_multipoles<true, false>,
-                               (const void *)k_multipoles<false, true>, (const void *)k_multipoles<false, false>};
-    for (const void *fn : variants) {
-        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)c->k1_smem_limit);
-        if (e != cudaSuccess)
-            return bail(fail(VB200_ECUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)));
-    }
+    for (int fast = 0; fast < 2; ++fast)
+        for (int flags = 0; flags < 2; ++flags)
+            for (int ilp = 1; ilp <= 4; ++ilp) {
+                cudaError_t e = cudaFuncSetAttribute((const void *)pick_k1(fast, flags, ilp),
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)c->k1_smem_limit);
+                if (e != cudaSuccess)
+                    return bail(fail(VB200_ECUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)));
+            }
     *out = c;
     return VB200_OK;
 }
@@ -356,6 +366,7 @@ int vb200_set_option(vb200_ctx *c, const char *key, int64_t value) {
     if (!c || !key) return fail(VB200_EINVAL, "null argument");
     if (!strcmp(key, "fast_math")) c->opt_fast = value ? 1 : 0;
     else if (!strcmp(key, "nsplit")) c->opt_nsplit = (int)value;
+    else if (!strcmp(key, "ilp")) c->opt_ilp = (int)std::max<int64_t>(1, std::min<int64_t>(4, value));
     else if (!strcmp(key, "threads")) {
         if (value < 32 || value > 256 || value % 32) return fail(VB200_EINVAL, "threads must be 32..256, multiple of 32");
         c->opt_threads = (int)value;

@@ -188,9 +188,68 @@ __device__ __forceinline__ double pin_f64(double v) {
     return r;
 }
 
+// U consecutive velocity nodes of one (s_j, mu_k) pair, written stage by stage so that the U
+// dependency chains are interleaved in program order (FP64 latency ~10 cycles, issue every 2).
+template <bool kFast, bool kFlags, int U>
+__device__ __forceinline__ double quad_nodes(const K1Args &a, int mi, double kappa, double Spar, double Sperp2,
+                                             double inv_h, unsigned nbm1, unsigned bb_s, unsigned rec_s,
+                                             unsigned etab_s, const double *upper, double acc) {
+    double xm[U], wm[U], u[U], mur[U], t[U], q[U], z2[U], g[U];
+    unsigned ra[U];
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+        xm[i] = a.xw[mi + i];
+        wm[i] = a.xw[kMaxNx + mi + i];
+        const double rp = fma(-xm[i], kappa, Spar);           // ccf_model.py:648-650
+        const double u2 = fma(rp, rp, Sperp2);                // :651
+        radius<kFast>(u2, rp, u[i], mur[i]);                  // :651-652
+    }
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+        const unsigned b = min((unsigned)__double2loint(__fma_rd(u[i], inv_h, 6755399441055744.0)), nbm1);
+        int cell = lds_s32(bb_s + (b << 2));
+        if (kFlags) {
+            if (cell < 0) {
+                cell &= ~kBucketFlag;
+                for (int sc = 0; sc < a.m.maxscan; ++sc) cell += (u[i] >= upper[cell]) ? 1 : 0;
+            }
+        }
+        ra[i] = rec_s + cell * (kRec * 8);
+    }
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+        double tt = u[i] - lds_f64(ra[i] + 96);
+        const int hi = __double2hiint(tt);
+        t[i] = __hiloint2double(max(hi, 0), __double2loint(tt));   // t = max(t, 0), see k_multipoles
+    }
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+        const double2 c89 = lds_f64x2(ra[i] + 64), cab = lds_f64x2(ra[i] + 80);
+        const double sv = fma(fma(fma(cab.y, t[i], cab.x), t[i], c89.y), t[i], c89.x);   // :654-655
+        q[i] = kFast ? rcp_cubic(sv) : 1.0 / sv;
+    }
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+        const double2 c45 = lds_f64x2(ra[i] + 32), c67 = lds_f64x2(ra[i] + 48);
+        const double vb = fma(fma(fma(c67.y, t[i], c67.x), t[i], c45.y), t[i], c45.x);   // :635, :656
+        const double z = fma(-vb, mur[i], xm[i]) * q[i];
+        z2[i] = z * z;
+    }
+#pragma unroll
+    for (int i = 0; i < U; ++i) g[i] = kFast ? gauss_tab(z2[i], etab_s) : exp(-0.5 * z2[i]);
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+        const double2 c01 = lds_f64x2(ra[i]), c23 = lds_f64x2(ra[i] + 16);
+        const double xi1 = fma(fma(fma(c23.y, t[i], c23.x), t[i], c01.y), t[i], c01.x);  // :621, :683
+        acc = fma(wm[i] * (xi1 * q[i]), g[i], acc);                                       // :690
+    }
+    return acc;
+}
+
 // kFast: hand-rolled rsqrt / rcp / exp (else CUDA libm).  kFlags: some bucket holds a knot in
 // its interior, so the cell search may need the comparison path (non-lattice knot sets).
-template <bool kFast, bool kFlags>
+// kU: velocity nodes processed together per loop trip (instruction-level parallelism).
+template <bool kFast, bool kFlags, int kU>
 __global__ void __launch_bounds__(256) k_multipoles(const __grid_constant__ K1Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const ModelDev &m = a.m;
@@ -285,48 +344,13 @@ __global__ void __launch_bounds__(256) k_multipoles(const __grid_constant__ K1Ar
         const double Spar = sj * a.mu[k] * spar_f;
         const double Sperp2 = Sperp * Sperp;
         double acc = 0.0;
-#pragma unroll 2
-        for (int mi = 0; mi < nx; ++mi) {
-            const double xm = a.xw[mi], wm = a.xw[kMaxNx + mi];   // uniform: constant-bank reads
-            const double rp = fma(-xm, kappa, Spar);              // ccf_model.py:648-650
-            const double u2 = fma(rp, rp, Sperp2);                // :651
-            double u, mur;
-            radius<kFast>(u2, rp, u, mur);                        // :651-652
-            // bucket = floor(u * inv_h) through a round-down FMA onto 1.5 * 2^52 (u >= 0; NaN -> 0)
-            const unsigned b = min((unsigned)__double2loint(__fma_rd(u, inv_h, 6755399441055744.0)), nbm1);
-            int cell = lds_s32(bb_s + (b << 2));
-            if (kFlags) {
-                if (cell < 0) {  // a knot lies inside this bucket: finish the search by comparison
-                    cell &= ~kBucketFlag;
-                    for (int sc = 0; sc < m.maxscan; ++sc) cell += (u >= upper[cell]) ? 1 : 0;
-                }
-            }
-            const unsigned ra = rec_s + cell * (kRec * 8);
-            const double2 c89 = lds_f64x2(ra + 64), cab = lds_f64x2(ra + 80);
-            double t = u - lds_f64(ra + 96);
-            {   // t = max(t, 0): below the first knot every spline is its boundary value (ext=3), which
-                // is the first cell's cubic at t = 0.  Done on the sign bit with integer ops; a
-                // negative t becomes a positive denormal-sized number, i.e. 0 for the cubic.
-                const int hi = __double2hiint(t);
-                t = __hiloint2double(hi & ~(hi >> 31), __double2loint(t));
-            }
-            const double2 c45 = lds_f64x2(ra + 32), c67 = lds_f64x2(ra + 48);
-            const double2 c01 = lds_f64x2(ra), c23 = lds_f64x2(ra + 16);
-            const double sv = fma(fma(fma(cab.y, t, cab.x), t, c89.y), t, c89.x);   // :654-655
-            const double vb = fma(fma(fma(c67.y, t, c67.x), t, c45.y), t, c45.x);   // :635, :656
-            const double xi1 = fma(fma(fma(c23.y, t, c23.x), t, c01.y), t, c01.x);  // :621, :683
-            double q, g;
-            if (kFast) {
-                q = rcp_cubic(sv);
-                const double z = fma(-vb, mur, xm) * q;                               // :656
-                g = gauss_tab(z * z, etab_s);
-            } else {
-                q = 1.0 / sv;
-                const double z = (xm - vb * mur) * q;
-                g = exp(-0.5 * z * z);
-            }
-            acc = fma(wm * (xi1 * q), g, acc);                                        // :690
-        }
+        int mi = 0;
+        for (; mi + kU <= nx; mi += kU)
+            acc = quad_nodes<kFast, kFlags, kU>(a, mi, kappa, Spar, Sperp2, inv_h, nbm1, bb_s, rec_s, etab_s,
+                                                upper, acc);
+        for (; mi < nx; ++mi)
+            acc = quad_nodes<kFast, kFlags, 1>(a, mi, kappa, Spar, Sperp2, inv_h, nbm1, bb_s, rec_s, etab_s,
+                                               upper, acc);
         stage[pidx] = acc - 1.0;  // ccf_model.py:690
     }
     __syncthreads();
