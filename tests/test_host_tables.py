@@ -1,0 +1,225 @@
+"""CPU: the host side of the product -- loaders, table builder, parameter handling -- checked
+against golden outputs of the unmodified reference, with the packed tables evaluated by the
+numpy walk-through in oracle/table_emul.py (the same algebra the kernels run).
+
+No kernel is launched here; what is tested is that the tables the product uploads, evaluated
+with the kernels' formulas in float64, reproduce the reference within the parity tolerances.
+"""
+import copy
+
+import numpy as np
+import pytest
+
+from oracle import table_emul as E
+
+RTOL, ATOL, C2_ATOL = 1e-9, 1e-13, 1e-6
+
+
+@pytest.fixture(scope="module")
+def fit(boss_blocks):
+    from victor_b200 import CCFFit
+    model, data = boss_blocks
+    return CCFFit(copy.deepcopy(model), copy.deepcopy(data))
+
+
+@pytest.fixture(scope="module")
+def packed(fit):
+    from victor_b200 import tables as T
+    mt = T.build_model_tables(fit, fit.model)
+    like = fit.fit_options["likelihood"]
+    ft = T.build_fit_tables(fit, like)
+    mu, W = T.mu_projection_weights(fit.poles_s)
+    return mt, ft, mu, W
+
+
+def test_loaders_match_reference_state(fit, golden):
+    t = golden("boss_tables")
+    assert abs(fit.iaH - float(t["iaH"])) < 1e-16
+    for key in ("r", "s", "beta", "sv_rmu", "r_for_sv", "mu_for_sv"):
+        np.testing.assert_allclose(getattr(fit, key), t[key], rtol=1e-14, atol=0)
+    r31 = np.append([0.01], fit.r)
+    np.testing.assert_allclose(fit.delta(r31), t["delta_r31"], rtol=1e-13)
+    np.testing.assert_allclose(fit.integrated_delta(r31), t["Delta_r31"], rtol=1e-13)
+    np.testing.assert_allclose(fit.get_interpolated_real_multipoles(0.37), t["xi_r_beta037"], rtol=1e-14)
+    np.testing.assert_allclose(fit.icov[0], t["icov_first"], rtol=1e-9, atol=1e-6)
+    a = golden("boss_notebook_anchors")
+    np.testing.assert_allclose(fit.multipole_datavector(0.37), a["data_vector"], rtol=1e-14)
+    assert abs(np.linalg.slogdet(fit.get_interpolated_covariance(0.37))[1] - float(a["slogdet_cov"])) < 1e-9
+
+
+def test_covariance_bracket_uses_last_index(fit):
+    """The reference's bracket: lower neighbour and the LAST grid index (ccf_fit.py:225-227)."""
+    g = fit.beta_covmat
+    lo, hi, t = fit._bracket(0.37)
+    assert (lo, hi) == (12, 30) and abs(t - 0.045370370370370484) < 1e-15
+    assert fit._bracket(g[0] - 0.01) == (0, 0, 0.0)
+    assert fit._bracket(g[-1] + 0.01) == (30, 30, 0.0)
+    assert fit._bracket(g[5]) == (5, 5, 0.0)
+    cov = fit.get_interpolated_covariance(0.37)
+    np.testing.assert_allclose(cov, (1 - t) * fit.covmat[12] + t * fit.covmat[30], rtol=1e-15)
+
+
+def test_weight_vectors(packed):
+    from victor_b200 import tables as T
+    mt, ft, mu, W = packed
+    assert mu.shape == (100,) and W.shape == (2, 100)
+    assert abs(W[0].sum() - 1.0) < 1e-13          # monopole of a constant is the constant
+    assert abs(W[1].sum()) < 1e-4                 # quadrature of L_2: small, not exactly zero
+    x, w = T.velocity_nodes(50)
+    assert abs(w.sum() - 12.0) < 1e-12            # integral of 1 over [-6, 6]
+    assert abs((w * x).sum()) < 0.02 and w[-1] != w[0]   # scipy's even-N end correction is one-sided
+    # the rule integrates a unit Gaussian over +-6 sigma to ~1e-7 (what the 50 nodes can resolve)
+    assert abs((w * np.exp(-0.5 * x * x)).sum() / np.sqrt(2 * np.pi) - 1) < 1e-6
+    _, W3 = T.mu_projection_weights([0, 2, 4])
+    f = 0.3 + 0.5 * (3 * mu ** 2 - 1) / 2 - 0.2 * (35 * mu ** 4 - 30 * mu ** 2 + 3) / 8
+    np.testing.assert_allclose(W3 @ f, [0.3, 0.5, -0.2], atol=2e-4)
+    mu_odd, W_odd = T.mu_projection_weights([0, 1])
+    assert mu_odd[0] == -1.0 and abs(W_odd[0].sum() - 1.0) < 1e-12
+
+
+def test_cells_reproduce_scipy_splines(fit, packed):
+    """Cell cubics + bucket search == FITPACK ext=3 splines, including the clamped ranges."""
+    from scipy.interpolate import InterpolatedUnivariateSpline, PchipInterpolator
+    mt = packed[0]
+    rng = np.random.default_rng(5)
+    u = np.concatenate([rng.uniform(0, 170, 20000), mt.knots, mt.knots - 1e-12, mt.knots + 1e-12,
+                        [0.0, 1e-300, 0.005, 0.01, 1.999999, 2.0, 118.0, 147.0, 1e4]])
+    cell, t = E._cells(mt, u)
+    assert np.all(cell >= 1) and np.all(cell <= mt.ncell - 1) and np.all(t >= 0)
+    inside = (u >= mt.knots[0])
+    assert np.all(mt.origin[cell][inside] <= u[inside]) and np.all(u < mt.upper[cell])
+    sv = InterpolatedUnivariateSpline(fit.r_for_sv, fit.sv_rmu[0], ext=3)
+    np.testing.assert_allclose(E._horner(mt.sv, cell, t), sv(u), rtol=1e-13, atol=1e-15)
+    r31 = np.append([0.01], fit.r)
+    v0 = InterpolatedUnivariateSpline(r31, r31 * fit.integrated_delta(r31), ext=3)
+    np.testing.assert_allclose(E._horner(mt.v0, cell, t), v0(u), rtol=1e-12, atol=1e-13)
+    for beta in (0.37, 0.12, 0.70, float(fit.beta[7])):
+        xi0 = PchipInterpolator(fit.beta, fit.real_multipoles["0"], axis=0)(beta)
+        want = InterpolatedUnivariateSpline(fit.r, xi0, ext=3)(u)
+        xc = E.xi_cells(mt, np.array([beta]))[0, 0]
+        np.testing.assert_allclose(E._horner(xc, cell, t), want, rtol=1e-11, atol=1e-14)
+
+
+def test_bucket_map_nonuniform_knots():
+    from victor_b200 import tables as T
+    rng = np.random.default_rng(11)
+    knots = np.unique(np.concatenate([[0.01], np.cumsum(rng.uniform(0.11, 0.13, 25)), [0.5, 1.7]]))
+    inv_h, entry, maxscan = T.bucket_map(knots)
+    assert maxscan >= 1 and np.any(entry < 0)
+
+    class M:
+        pass
+    m = M()
+    m.inv_h, m.bucket_base, m.maxscan = inv_h, entry, maxscan
+    m.upper = np.concatenate([knots, [np.inf]])
+    m.origin = np.concatenate([[knots[0]], knots])
+    u = np.concatenate([rng.uniform(0, knots[-1] * 1.3, 50000), knots, np.nextafter(knots, 0), [0.0]])
+    cell, _ = E._cells(m, u)
+    want = np.maximum(np.searchsorted(knots, u, side="right"), 1)
+    assert np.array_equal(cell, want)
+
+
+def test_tables_reproduce_reference_streaming(packed, fit, golden):
+    """All 80 golden rows (64 seeded + 16 edge rows): multipoles, chi2 and lnL from the packed
+    tables, against the unmodified reference."""
+    from victor_b200.model import params_to_rows
+    mt, ft, mu, W = packed
+    g = golden("boss_streaming_points")
+    rows = params_to_rows(g["params"])
+    mult, _ = E.theory_multipoles(mt, rows, np.asarray(fit.s, float), mu, W)
+    theory = mult.reshape(len(rows), -1)
+    np.testing.assert_allclose(theory, g["theory"], rtol=RTOL, atol=ATOL)
+    for a in (0, 30):
+        scale = np.abs(g["theory"][:, a:a + 30]).max(axis=1)
+        err = np.abs(theory[:, a:a + 30] - g["theory"][:, a:a + 30]).max(axis=1)
+        assert np.all(err <= 1e-11 * scale)         # two orders inside the 1e-9 contract
+    chi2, lnl = E.chi2_lnl(ft, rows[:, 1], theory)
+    np.testing.assert_allclose(chi2, g["chi2"], rtol=0, atol=C2_ATOL)
+    np.testing.assert_allclose(lnl, g["lnl"], rtol=0, atol=C2_ATOL)
+    assert np.abs(chi2 - g["chi2"]).max() < 1e-8    # measured headroom: ~1e-11
+
+
+def test_likelihood_forms_from_tables(packed, fit, golden):
+    from victor_b200 import tables as T
+    from victor_b200.model import params_to_rows
+    mt, _, mu, W = packed
+    g = golden("boss_forms")
+    rows = params_to_rows(g["params"])
+    mult, _ = E.theory_multipoles(mt, rows, np.asarray(fit.s, float), mu, W)
+    theory = mult.reshape(len(rows), -1)
+    for form in ("gaussian", "hartlap", "percival", "sellentin"):
+        ft = T.build_fit_tables(fit, {"form": form, "nmocks": 1000, "nparams": 4})
+        chi2, lnl = E.chi2_lnl(ft, rows[:, 1], theory)
+        np.testing.assert_allclose(chi2, g[f"{form}_chi2"], rtol=0, atol=C2_ATOL)
+        np.testing.assert_allclose(lnl, g[f"{form}_lnl"], rtol=0, atol=C2_ATOL)
+    with pytest.raises(Exception):
+        T.likelihood_constants({"form": "nonsense"}, 60)
+
+
+def test_example_config_tables(example_block, golden):
+    """Non-uniform knots, fixed real-space input, caller-supplied s grid, poles 0/2/4."""
+    from victor_b200 import CCFModel, tables as T
+    from victor_b200.model import params_to_rows
+    g = golden("example_points")
+    m = CCFModel(copy.deepcopy(example_block))
+    assert abs(m.iaH - float(g["iaH"])) < 1e-16
+    np.testing.assert_allclose(m.sv_rmu, g["sv_rmu"], rtol=1e-13)
+    mt = T.build_model_tables(m, m.model)
+    mu, W = T.mu_projection_weights([0, 2, 4])
+    P = {"fsigma8": g["params"][:, 0], "sigma_v": g["params"][:, 1], "epsilon": g["params"][:, 2]}
+    mult, _ = E.theory_multipoles(mt, params_to_rows(P), g["s"], mu, W)
+    np.testing.assert_allclose(mult.reshape(3, -1), g["streaming_theory"], rtol=RTOL, atol=ATOL)
+
+
+def test_params_to_rows_conventions():
+    from victor_b200 import InputError
+    from victor_b200.model import params_to_rows
+    rows = params_to_rows({"fsigma8": 0.47, "beta": 0.37, "sigma_v": 380, "epsilon": 0.95, "alpha": 1.01})
+    apar = 1.01 * 0.95 ** (-2 / 3)
+    assert rows.shape == (1, 8) and rows[0, 4] == apar and rows[0, 3] == 0.95 * apar   # ccf_model.py:589-592
+    rows = params_to_rows({"fsigma8": [0.1, 0.2, 0.3], "beta": 0.4, "sigma_v": 300.0, "aperp": 1.0, "apar": 1.0,
+                           "b": 1.9, "Av": 0, "chi2_unused": 7})                       # cobaya passes extras
+    assert rows.shape == (3, 8) and np.all(rows[:, 1] == 0.4) and np.all(rows[:, 5] == 1.0)
+    rows = params_to_rows(np.array([[0.47, 0.37, 380.0]]))
+    assert rows.shape == (1, 8) and rows[0, 3] == 1.0 and rows[0, 4] == 1.0
+    with pytest.raises(InputError):
+        params_to_rows(np.zeros((2, 2)))
+
+
+def test_input_errors(boss_blocks):
+    from victor_b200 import CCFFit, CCFModel, InputError
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    bad = copy.deepcopy(model)
+    bad["input_model_data_file"] = "nope.hdf5"
+    with pytest.raises(InputError):
+        CCFModel(bad)
+    bad = copy.deepcopy(model)
+    bad["realspace_ccf"]["ccf_keys"] = ["r", "missing"]
+    with pytest.raises(InputError):
+        CCFModel(bad)
+    bad = copy.deepcopy(model)
+    bad["matter_ccf"]["template_sigma8"] = None
+    with pytest.raises(InputError):
+        CCFModel(bad)
+    bad = copy.deepcopy(model)
+    bad["velocity_pdf"]["dispersion"] = {"model": "constant"}
+    with pytest.raises(InputError):
+        CCFModel(bad)
+    badd = copy.deepcopy(data)
+    badd["covariance_matrix"]["cov_key"] = "missing"
+    with pytest.raises(InputError):
+        CCFFit(copy.deepcopy(model), badd)
+    badd = copy.deepcopy(data)
+    badd["covariance_matrix"] = {"data_file": "data/boss_dr12_cmass/cmass_fixed_D_covariance.npz",
+                                 "cov_key": "covmat", "fixed_beta": False, "beta_key": "beta"}
+    with pytest.raises(InputError):      # 60x60 matrix where a beta stack is announced
+        CCFFit(copy.deepcopy(model), badd)
+
+
+def test_no_cpu_fallback_without_a_gpu(fit):
+    """On a box without a CUDA device the product must fail loudly, not compute on the CPU."""
+    from victor_b200 import _lib
+    if _lib.load().vb200_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fit.log_likelihood({"fsigma8": 0.47, "beta": 0.37, "sigma_v": 380, "epsilon": 1.0})

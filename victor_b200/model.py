@@ -65,7 +65,10 @@ def params_to_rows(params, n_hint=None):
 
         if "epsilon" in params:
             eps = col("epsilon", 1.0)
-            cols["apar"] = col("alpha", 1.0) * eps ** (-2 / 3)
+            # Python-float pow for small tables: bit-identical to the reference's scalar
+            # `epsilon**(-2/3)`; numpy's vectorised pow may differ from libm in the last bit
+            powed = np.array([float(e) ** (-2 / 3) for e in eps]) if n <= 1024 else eps ** (-2 / 3)
+            cols["apar"] = col("alpha", 1.0) * powed
             cols["aperp"] = eps * cols["apar"]
         rows = np.empty((n, _tables.NPAR))
         for i, name in enumerate(_tables.PARAM_ORDER):
