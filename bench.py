@@ -46,7 +46,7 @@ NS, NMU, NX, L, P = 30, 100, 50, 2, 60
 FLOP_PER_EVAL = 41 * NS * NMU * NX + 8 * NS * NMU + 2 * L * NS * NMU + (3 * P * P + 2 * P * P + 2 * P) \
     + (3 * P * P + P ** 3 // 3 + P) + 1500
 FLOP_K1_PER_EVAL = 41 * NS * NMU * NX + 8 * NS * NMU + 2 * L * NS * NMU + 1500
-BYTES_PER_EVAL = 40 + 8 * L * NS + 16
+BYTES_PER_EVAL = 64 + 8 * L * NS + 16   # parameter row in, theory + chi2 + lnL out
 FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12
 
 
@@ -95,7 +95,7 @@ def _oracle_eval(rows):
     return time.perf_counter() - t0, out
 
 
-def cpu_oracle_throughput(rows_per_worker=6, repeats=1):
+def cpu_oracle_throughput(rows_per_worker=160, repeats=1):
     """Oracle port on all host cores: evals / max worker time."""
     import multiprocessing as mp
     cores = os.cpu_count() or 1

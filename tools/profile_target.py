@@ -24,7 +24,7 @@ def main():
     ap.add_argument("--fast", type=int, default=1)
     ap.add_argument("--threads", type=int, default=256)
     ap.add_argument("--nsplit", type=int, default=0)
-    ap.add_argument("--ilp", type=int, default=2)
+    ap.add_argument("--ilp", type=int, default=4)
     args = ap.parse_args()
     model, data = boss_blocks()
     fit = CCFFit(model, data, device=0)
