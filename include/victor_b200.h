@@ -120,7 +120,9 @@ int vb200_create(const vb200_model_tables *model, const vb200_fit_tables *fit, i
 void vb200_destroy(vb200_ctx *ctx);
 
 /* Kernel variant switches (integers): "fast_math" (1 = hand-rolled rsqrt / rcp / exp, default;
- * 0 = CUDA libm), "nsplit" (blocks per parameter row; 0 = automatic), "threads" (block size). */
+ * 0 = CUDA libm), "nsplit" (blocks per parameter row; 0 = automatic), "threads" (block size),
+ * "ilp" (velocity nodes per loop trip: 1, 2, 4), "exp_degree" (5 or 6), "group_weights"
+ * (1 = apply the alternating Simpson weights once per class instead of once per node). */
 int vb200_set_option(vb200_ctx *ctx, const char *key, int64_t value);
 
 /* xi(s, mu) and / or its projections for n parameter rows.
@@ -141,9 +143,20 @@ int vb200_synchronize(vb200_ctx *ctx);
 /* Kernel launches issued by this context so far (for bench.py's gpu_launches). */
 int64_t vb200_launch_count(const vb200_ctx *ctx);
 
-/* Device self-test of the hand-rolled math: out[0..n) = 2^(-x) * 1 via the fast exp path,
- * out[n..2n) = fast 1/sqrt(x), out[2n..3n) = fast 1/x, for n HOST inputs x > 0. */
+/* Device self-test of the hand-rolled math for n HOST inputs x > 0; out has 4n entries:
+ * out[0..n) = exp(-x/2) (degree-6 remainder polynomial), out[n..2n) = 1/sqrt(x),
+ * out[2n..3n) = 1/x, out[3n..4n) = exp(-x/2) (degree-5 economised polynomial). */
 int vb200_math_selftest(int device, const double *x, int64_t n, double *out);
+
+/* Measurement hooks used while tuning (tools/probe_pipes.py): time of a kernel issuing only
+ * DFMA (mode 0), only one kind of FP64 conversion (1, 3, 5) or both interleaved (2, 4, 6);
+ * and the raw MUFU seeds rsqrt.approx / rcp.approx for n HOST inputs (out has 2n entries). */
+int vb200_pipe_probe(int device, int mode, int iters, double *ms);
+int vb200_seed_probe(int device, const double *x, int64_t n, double *out);
+/* DFMA issue-model probe: `chains` dependent FMA chains per thread, `mix` other instructions
+ * (kind 0 integer, 1 shared-memory load; kind 2 = DMUL-with-constant-operand chains) after every
+ * DFMA, `blocks_per_sm` blocks of 128 threads (= warps per SM sub-partition). */
+int vb200_mix_probe(int device, int chains, int mix, int kind, int blocks_per_sm, int iters, double *ms);
 
 /* FP64 FMA issue-rate probe (8 independent DFMA chains per thread, whole GPU): the measured
  * roofline denominator for this FP64-CUDA-core-bound path.  tflops counts 2 flop per FMA. */

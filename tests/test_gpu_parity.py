@@ -13,6 +13,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 RTOL, ATOL, CHI2_ATOL = 1e-9, 1e-13, 1e-6
+DEFAULT_EXP_DEGREE, DEFAULT_GROUP, DEFAULT_CACHE = 6, 0, 0   # library defaults (victor_b200/csrc/api.cu)
 
 
 def assert_theory(got, want, ns=None):
@@ -50,18 +51,19 @@ def test_fast_math_primitives():
     x = np.concatenate([rng.uniform(1e-6, 400.0, 200000), 10.0 ** rng.uniform(-8, 8, 50000),
                         np.array([0.0, 1e-300, 1.0, 2.0, 1300.0])])
     x = np.ascontiguousarray(x)
-    out = np.empty(3 * len(x))
+    out = np.empty(4 * len(x))
     rc = lib.vb200_math_selftest(0, x.ctypes.data, len(x), out.ctypes.data)
     assert rc == 0, _lib.last_error()
     n = len(x)
-    g, rs, rc_ = out[:n], out[n:2 * n], out[2 * n:]
+    g, rs, rc_, g5 = out[:n], out[n:2 * n], out[2 * n:3 * n], out[3 * n:]
     want = np.exp(-0.5 * x)
     # |z| <= 10: the range that carries the integral; a few ulp.  Beyond it the single-constant
     # range reduction loses ~1e-17 * z^2 relative, irrelevant where exp(-z^2/2) < 2e-22.
     core = x <= 100.0
-    assert np.max(np.abs(g[core] / want[core] - 1)) < 4e-15
     tail = (x > 100.0) & (want > 1e-280)
-    assert np.max(np.abs(g[tail] / want[tail] - 1)) < 2e-13
+    for got in (g, g5):
+        assert np.max(np.abs(got[core] / want[core] - 1)) < 4e-15
+        assert np.max(np.abs(got[tail] / want[tail] - 1)) < 2e-13
     pos = (x > 1e-290)
     assert np.max(np.abs(rs[pos] * np.sqrt(x[pos]) - 1)) < 1e-15
     assert np.max(np.abs(rc_[pos] * x[pos] - 1)) < 1e-15
@@ -76,6 +78,27 @@ def test_boss_streaming_golden(fit, golden, fast):
         lnl, chi2, theory = fit.log_likelihood_batch(g["params"], return_theory=True)
     finally:
         eng.set_option("fast_math", 1)
+    assert_theory(theory, g["theory"], ns=len(fit.s))
+    np.testing.assert_allclose(chi2, g["chi2"], rtol=0, atol=CHI2_ATOL)
+    np.testing.assert_allclose(lnl, g["lnl"], rtol=0, atol=CHI2_ATOL)
+
+
+@pytest.mark.parametrize("opts", [{"ilp": 1}, {"ilp": 2}, {"exp_degree": 5}, {"group_weights": 1},
+                                  {"exp_degree": 5, "group_weights": 1}, {"threads": 128},
+                                  {"cell_cache": 1}, {"cell_cache": 1, "ilp": 1}, {"cell_cache": 2, "ilp": 2}])
+def test_kernel_variants_hold_parity(fit, golden, opts):
+    """Every tuning variant of K1 must meet the same bar as the default."""
+    g = golden("boss_streaming_points")
+    eng, _ = fit._fit_engine({})
+    defaults = {"ilp": 4, "exp_degree": DEFAULT_EXP_DEGREE, "group_weights": DEFAULT_GROUP, "threads": 256,
+                "cell_cache": DEFAULT_CACHE}
+    try:
+        for k, v in opts.items():
+            eng.set_option(k, v)
+        lnl, chi2, theory = fit.log_likelihood_batch(g["params"], return_theory=True)
+    finally:
+        for k, v in defaults.items():
+            eng.set_option(k, v)
     assert_theory(theory, g["theory"], ns=len(fit.s))
     np.testing.assert_allclose(chi2, g["chi2"], rtol=0, atol=CHI2_ATOL)
     np.testing.assert_allclose(lnl, g["lnl"], rtol=0, atol=CHI2_ATOL)

@@ -89,7 +89,9 @@ struct vb200_ctx {
     std::vector<void *> owned;
     Scratch sc_params, sc_theory, sc_chi2, sc_lnl, sc_xi, sc_mult, sc_grid;
     // options
-    int opt_fast = 1, opt_nsplit = 0, opt_threads = 256, opt_ilp = 4;
+    int opt_fast = 1, opt_nsplit = 0, opt_threads = 256, opt_ilp = 4, opt_expdeg = 6, opt_group = 0, opt_cache = 0;
+    int g0 = 0, g1 = 0;           // velocity nodes [g0, g1) whose weights alternate wA, wB
+    double wA = 0.0, wB = 0.0;
     long long launches = 0;
     size_t k1_smem_limit = 0;
     double xw[2 * kMaxNx] = {0};  // host copy of x_m | w_m for the kernel-parameter table
@@ -128,15 +130,29 @@ int check_model(const vb200_model_tables *m) {
 
 typedef void (*k1_fn)(const K1Args);
 
-k1_fn pick_k1(bool fast, bool flags, int ilp) {
-    if (!fast) return flags ? k_multipoles<false, true, 1> : k_multipoles<false, false, 1>;
-    if (flags) return ilp >= 2 ? k_multipoles<true, true, 2> : k_multipoles<true, true, 1>;
-    switch (ilp) {
-        case 1: return k_multipoles<true, false, 1>;
-        case 3: return k_multipoles<true, false, 3>;
-        case 4: return k_multipoles<true, false, 4>;
-        default: return k_multipoles<true, false, 2>;
+// Kernel variants that exist in this build.  The tuned path is <fast, U = 4>; the others are
+// kept for parity tests (libm math) and for measurement (ILP, exp degree, weight grouping).
+k1_fn pick_k1(bool fast, bool flags, int ilp, int expdeg, bool group, int cache = 0) {
+    if (fast && !flags && cache == 1) {
+        if (ilp == 1) return k_multipoles<K1Cfg<true, false, 1, 5, false, true>>;
+        if (ilp == 2) return k_multipoles<K1Cfg<true, false, 2, 5, false, true>>;
+        return k_multipoles<K1Cfg<true, false, 4, 5, false, true>>;
     }
+    if (fast && !flags && cache >= 2) {  // same, compiled for 4 resident blocks (64 registers)
+        if (ilp == 1) return k_multipoles<K1Cfg<true, false, 1, 5, false, true, 4>>;
+        if (ilp == 2) return k_multipoles<K1Cfg<true, false, 2, 5, false, true, 4>>;
+        return k_multipoles<K1Cfg<true, false, 4, 5, false, true, 4>>;
+    }
+    if (!fast) return flags ? k_multipoles<K1Cfg<false, true, 1>> : k_multipoles<K1Cfg<false, false, 1>>;
+    if (flags) {
+        if (ilp < 4) return k_multipoles<K1Cfg<true, true, 1>>;
+        return expdeg == 5 ? k_multipoles<K1Cfg<true, true, 4, 5>> : k_multipoles<K1Cfg<true, true, 4, 6>>;
+    }
+    if (ilp == 1) return k_multipoles<K1Cfg<true, false, 1>>;
+    if (ilp == 2) return k_multipoles<K1Cfg<true, false, 2>>;
+    if (group)
+        return expdeg == 5 ? k_multipoles<K1Cfg<true, false, 4, 5, true>> : k_multipoles<K1Cfg<true, false, 4, 6, true>>;
+    return expdeg == 5 ? k_multipoles<K1Cfg<true, false, 4, 5>> : k_multipoles<K1Cfg<true, false, 4, 6>>;
 }
 
 int launch_k1(vb200_ctx *c, const double *d_params, long long n, const double *d_s, int ns,
@@ -178,7 +194,12 @@ int launch_k1(vb200_ctx *c, const double *d_params, long long n, const double *d
     a.xi_out = d_xi;
     a.mult_out = d_mult;
     memcpy(a.xw, c->xw, sizeof(a.xw));
-    auto fn = pick_k1(c->opt_fast != 0, c->has_flags, c->opt_ilp);
+    a.g0 = c->g0;
+    a.g1 = c->g1;
+    a.wA = c->wA;
+    a.wB = c->wB;
+    const bool group = c->opt_group && c->g1 - c->g0 >= 8;
+    auto fn = pick_k1(c->opt_fast != 0, c->has_flags, c->opt_ilp, c->opt_expdeg, group, c->opt_cache);
     void *kargs[] = {(void *)&a};
     CK(cudaLaunchKernel((const void *)fn, dim3((unsigned)blocks), dim3(threads), kargs, smem, st));
     CK(cudaGetLastError());
@@ -202,6 +223,35 @@ int launch_k2(vb200_ctx *c, const double *d_params, const double *d_theory, long
     CK(cudaGetLastError());
     c->launches++;
     return VB200_OK;
+}
+
+// Longest run [g0, g1) of velocity nodes whose weights alternate between two values (the interior
+// of a composite Simpson rule: 4/3, 2/3, 4/3, ... times h); its length is cut to a multiple of 4.
+// Weights within 4 ulp of each other count as equal and their mean is used.
+void find_weight_groups(vb200_ctx *c, const double *w, int nx) {
+    auto same = [](double a, double b) { return std::fabs(a - b) <= 1e-15 * std::fabs(a + b); };
+    int best0 = 0, best1 = 0;
+    for (int s0 = 0; s0 + 3 < nx; ++s0) {
+        int e = s0 + 2;
+        while (e < nx && same(w[e], w[e - 2])) ++e;
+        if (e - s0 > best1 - best0) {
+            best0 = s0;
+            best1 = e;
+        }
+    }
+    best1 = best0 + ((best1 - best0) / 4) * 4;
+    c->g0 = best0;
+    c->g1 = best1;
+    if (best1 > best0) {
+        double sa = 0.0, sb = 0.0;
+        for (int i = best0; i < best1; i += 2) {
+            sa += w[i];
+            sb += w[i + 1];
+        }
+        const int half = (best1 - best0) / 2;
+        c->wA = sa / half;
+        c->wB = sb / half;
+    }
 }
 
 void fill_exp_table(double *t) {
@@ -307,6 +357,7 @@ int vb200_create(const vb200_model_tables *m, const vb200_fit_tables *f, int dev
         c->xw[i] = m->x[i];
         c->xw[kMaxNx + i] = m->wx[i];
     }
+    find_weight_groups(c, m->wx, m->nx);
 
     if (f) {
         if (f->ns < 1 || f->npoles < 1 || f->npoles > VB200_MAX_POLES || f->nmu < 2 || f->nbeta_ccf < 2 ||
@@ -349,15 +400,13 @@ int vb200_create(const vb200_model_tables *m, const vb200_fit_tables *f, int dev
 
     // allow the large dynamic shared memory carve-out (dense mu grids stage up to ~200 KB)
     c->k1_smem_limit = std::min<size_t>((size_t)prop.sharedMemPerBlockOptin, (size_t)200 * 1024);
-    for (int fast = 0; fast < 2; ++fast)
-        for (int flags = 0; flags < 2; ++flags)
-            for (int ilp = 1; ilp <= 4; ++ilp) {
-                cudaError_t e = cudaFuncSetAttribute((const void *)pick_k1(fast, flags, ilp),
-                                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                     (int)c->k1_smem_limit);
-                if (e != cudaSuccess)
-                    return bail(fail(VB200_ECUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)));
-            }
+    for (int v = 0; v < 256; ++v) {
+        const int ilp = 1 << (v & 3);  // 1, 2, 4, (8 -> 4)
+        cudaError_t e = cudaFuncSetAttribute((const void *)pick_k1(v & 4, v & 8, ilp, (v & 16) ? 5 : 6, v & 32, v >> 6),
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k1_smem_limit);
+        if (e != cudaSuccess)
+            return bail(fail(VB200_ECUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)));
+    }
     *out = c;
     return VB200_OK;
 }
@@ -366,7 +415,12 @@ int vb200_set_option(vb200_ctx *c, const char *key, int64_t value) {
     if (!c || !key) return fail(VB200_EINVAL, "null argument");
     if (!strcmp(key, "fast_math")) c->opt_fast = value ? 1 : 0;
     else if (!strcmp(key, "nsplit")) c->opt_nsplit = (int)value;
-    else if (!strcmp(key, "ilp")) c->opt_ilp = (int)std::max<int64_t>(1, std::min<int64_t>(4, value));
+    else if (!strcmp(key, "ilp")) c->opt_ilp = value >= 4 ? 4 : (value >= 2 ? 2 : 1);
+    else if (!strcmp(key, "exp_degree")) {
+        if (value != 5 && value != 6) return fail(VB200_EINVAL, "exp_degree must be 5 or 6");
+        c->opt_expdeg = (int)value;
+    } else if (!strcmp(key, "group_weights")) c->opt_group = value ? 1 : 0;
+    else if (!strcmp(key, "cell_cache")) c->opt_cache = (int)std::max<int64_t>(0, std::min<int64_t>(2, value));
     else if (!strcmp(key, "threads")) {
         if (value < 32 || value > 256 || value % 32) return fail(VB200_EINVAL, "threads must be 32..256, multiple of 32");
         c->opt_threads = (int)value;
@@ -502,16 +556,106 @@ int vb200_math_selftest(int device, const double *x, int64_t n, double *out) {
     double etab[kExpTab];
     fill_exp_table(etab);
     CK(cudaMalloc(&dx, n * sizeof(double)));
-    CK(cudaMalloc(&dout, 3 * n * sizeof(double)));
+    CK(cudaMalloc(&dout, 4 * n * sizeof(double)));
     CK(cudaMalloc(&dtab, sizeof(etab)));
     CK(cudaMemcpy(dx, x, n * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dtab, etab, sizeof(etab), cudaMemcpyHostToDevice));
     k_math_selftest<<<(unsigned)((n + 255) / 256), 256>>>(dx, n, dtab, dout);
     CK(cudaGetLastError());
-    CK(cudaMemcpy(out, dout, 3 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out, dout, 4 * n * sizeof(double), cudaMemcpyDeviceToHost));
     cudaFree(dx);
     cudaFree(dout);
     cudaFree(dtab);
+    return VB200_OK;
+}
+
+int vb200_pipe_probe(int device, int mode, int iters, double *ms) {
+    if (!ms || iters < 1 || mode < 0 || mode > 6) return fail(VB200_EINVAL, "bad arguments");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(VB200_ECUDA, "cudaSetDevice failed");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    double *d = nullptr;
+    CK(cudaMalloc(&d, sizeof(double)));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    auto run = [&](int it) {
+        switch (mode) {
+            case 0: k_pipe_probe<0><<<blocks, threads>>>(d, it, 0.999999, 1e-9); break;
+            case 1: k_pipe_probe<1><<<blocks, threads>>>(d, it, 0.999999, 1e-9); break;
+            case 2: k_pipe_probe<2><<<blocks, threads>>>(d, it, 0.999999, 1e-9); break;
+            case 3: k_pipe_probe<3><<<blocks, threads>>>(d, it, 0.999999, 1e-9); break;
+            case 4: k_pipe_probe<4><<<blocks, threads>>>(d, it, 0.999999, 1e-9); break;
+            case 5: k_pipe_probe<5><<<blocks, threads>>>(d, it, 0.999999, 1e-9); break;
+            default: k_pipe_probe<6><<<blocks, threads>>>(d, it, 0.999999, 1e-9); break;
+        }
+    };
+    run(iters / 4 + 1);
+    CK(cudaEventRecord(e0));
+    run(iters);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaGetLastError());
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, e0, e1));
+    *ms = t;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    return VB200_OK;
+}
+
+int vb200_mix_probe(int device, int chains, int mix, int kind, int blocks_per_sm, int iters, double *ms) {
+    if (!ms || iters < 1 || blocks_per_sm < 1) return fail(VB200_EINVAL, "bad arguments");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(VB200_ECUDA, "cudaSetDevice failed");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    double *d = nullptr;
+    CK(cudaMalloc(&d, sizeof(double)));
+    const int blocks = prop.multiProcessorCount * blocks_per_sm;
+    typedef void (*fn_t)(double *, int, double, double, int);
+    fn_t fn = nullptr;
+#define VB_MIX(C, M, K) if (chains == C && mix == M && kind == K) fn = k_mix_probe<C, M, K>;
+    VB_MIX(1, 0, 0) VB_MIX(2, 0, 0) VB_MIX(4, 0, 0) VB_MIX(8, 0, 0)
+    VB_MIX(4, 1, 0) VB_MIX(4, 2, 0) VB_MIX(8, 1, 0) VB_MIX(2, 1, 0)
+    VB_MIX(4, 1, 1) VB_MIX(8, 1, 1) VB_MIX(2, 1, 1)
+    VB_MIX(4, 0, 2) VB_MIX(8, 0, 2)
+#undef VB_MIX
+    if (!fn) return fail(VB200_EINVAL, "no such probe variant");
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    fn<<<blocks, 128>>>(d, iters / 4 + 1, 0.999999, 1e-9, 3);
+    CK(cudaEventRecord(e0));
+    fn<<<blocks, 128>>>(d, iters, 0.999999, 1e-9, 3);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaGetLastError());
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, e0, e1));
+    *ms = t;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    return VB200_OK;
+}
+
+int vb200_seed_probe(int device, const double *x, int64_t n, double *out) {
+    if (!x || !out || n <= 0) return fail(VB200_EINVAL, "bad arguments");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(VB200_ECUDA, "cudaSetDevice failed");
+    double *dx = nullptr, *dout = nullptr;
+    CK(cudaMalloc(&dx, n * sizeof(double)));
+    CK(cudaMalloc(&dout, 2 * n * sizeof(double)));
+    CK(cudaMemcpy(dx, x, n * sizeof(double), cudaMemcpyHostToDevice));
+    k_seed_probe<<<(unsigned)((n + 255) / 256), 256>>>(dx, n, dout);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, dout, 2 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(dx);
+    cudaFree(dout);
     return VB200_OK;
 }
 

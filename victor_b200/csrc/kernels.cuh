@@ -45,6 +45,8 @@ struct K1Args {
     int jper, nsplit;
     double *xi_out;    // [n][nmu][ns] or null
     double *mult_out;  // [n][L][ns]  or null
+    int g0, g1;        // velocity nodes [g0, g1) carry alternating weights wA, wB (kGroup variants)
+    double wA, wB;
     double xw[2 * kMaxNx];  // x_m then Simpson weight / sqrt(2 pi): read through the constant bank
 };
 
@@ -146,8 +148,13 @@ __device__ __forceinline__ int lds_s32(unsigned addr) {
 // reads them as c[bank][offset] operands instead of re-materialising them with integer moves
 __constant__ double kExpPoly[6] = {2.166084939249829e-02, 2.3459619820224677e-04, 1.6938509724371819e-06,
                                    9.172562701824643e-09, 3.9737099845494154e-11, 1.4345655584131932e-13};
+// degree-5 economised (Chebyshev-node) fit of the same function on |r| <= 1/2: max relative error
+// 1.4e-16, one FMA less than the Taylor form (coefficients from a 60-digit mpmath solve)
+__constant__ double kExpPoly5[5] = {2.166084939249829e-02, 2.345961981994449e-04, 1.6938509724285119e-06,
+                                    9.172607532092245e-09, 3.9737238568525983e-11};
 
 // exp(-z2/2) from the shared-memory table at 32-bit shared address `etab_s`
+template <int kDeg = 6>
 __device__ __forceinline__ double gauss_tab(double z2, unsigned etab_s) {
     const double kMagic = 6755399441055744.0;   // 1.5 * 2^52
     const double kScale = -23.083120654223414;   // -16 log2(e)
@@ -155,11 +162,19 @@ __device__ __forceinline__ double gauss_tab(double z2, unsigned etab_s) {
     const int ni = __double2loint(tn);
     const double nf = tn - kMagic;
     const double r = fma(z2, kScale, -nf);
-    double p = fma(kExpPoly[5], r, kExpPoly[4]);
-    p = fma(p, r, kExpPoly[3]);
-    p = fma(p, r, kExpPoly[2]);
-    p = fma(p, r, kExpPoly[1]);
-    p = fma(p, r, kExpPoly[0]);
+    double p;
+    if (kDeg == 6) {
+        p = fma(kExpPoly[5], r, kExpPoly[4]);
+        p = fma(p, r, kExpPoly[3]);
+        p = fma(p, r, kExpPoly[2]);
+        p = fma(p, r, kExpPoly[1]);
+        p = fma(p, r, kExpPoly[0]);
+    } else {
+        p = fma(kExpPoly5[4], r, kExpPoly5[3]);
+        p = fma(p, r, kExpPoly5[2]);
+        p = fma(p, r, kExpPoly5[1]);
+        p = fma(p, r, kExpPoly5[0]);
+    }
     p = fma(p, r, 1.0);
     const int n = max(ni >> 5, -1000);
     double t = lds_f64(etab_s + ((ni & (kExpTab - 1)) << 3));
@@ -188,69 +203,172 @@ __device__ __forceinline__ double pin_f64(double v) {
     return r;
 }
 
+// Compile-time variant of K1.
+//   kFast  : hand-rolled rsqrt / rcp / exp (else CUDA libm).
+//   kFlags : some bucket holds a knot in its interior, so the cell search may need the
+//            comparison path (non-lattice knot sets).
+//   kU     : velocity nodes processed together per loop trip (instruction-level parallelism).
+//   kExp   : degree of the exp remainder polynomial (6 = Taylor, 5 = economised).
+//   kGroup : the velocity weights inside [g0, g1) alternate between two values (composite
+//            Simpson interior); accumulate the two classes unweighted and apply the weights once.
+//   kCache : every thread keeps the record of the cell it used last in registers and reloads it
+//            (predicated loads) only when its cell changes: consecutive velocity nodes of one
+//            (s, mu) pair mostly stay in one cell, so most lanes skip most shared-memory reads.
+template <bool kFast_, bool kFlags_, int kU_, int kExp_ = 6, bool kGroup_ = false, bool kCache_ = false,
+          int kMinBlocks_ = 1>
+struct K1Cfg {
+    static constexpr bool kFast = kFast_, kFlags = kFlags_, kGroup = kGroup_, kCache = kCache_;
+    static constexpr int kU = kU_, kExp = kExp_, kMinBlocks = kMinBlocks_;
+};
+
+// per-thread loop invariants of the quadrature
+struct QuadCtx {
+    double kappa, Spar, Sperp2, inv_h;
+    unsigned nbm1, bb_s, rec_s, etab_s;
+    const double *upper;
+    int maxscan;
+};
+
 // U consecutive velocity nodes of one (s_j, mu_k) pair, written stage by stage so that the U
 // dependency chains are interleaved in program order (FP64 latency ~10 cycles, issue every 2).
-template <bool kFast, bool kFlags, int U>
-__device__ __forceinline__ double quad_nodes(const K1Args &a, int mi, double kappa, double Spar, double Sperp2,
-                                             double inv_h, unsigned nbm1, unsigned bb_s, unsigned rec_s,
-                                             unsigned etab_s, const double *upper, double acc) {
-    double xm[U], wm[U], u[U], mur[U], t[U], q[U], z2[U], g[U];
+// kW = false: the nodes' weights are applied later (grouped accumulation into accA / accB).
+template <class C, int U, bool kW>
+__device__ __forceinline__ void quad_nodes(const K1Args &a, const QuadCtx &q, int mi, double &accA, double &accB) {
+    double xm[U], u[U], mur[U], t[U], rq[U], z2[U], g[U];
     unsigned ra[U];
 #pragma unroll
     for (int i = 0; i < U; ++i) {
         xm[i] = a.xw[mi + i];
-        wm[i] = a.xw[kMaxNx + mi + i];
-        const double rp = fma(-xm[i], kappa, Spar);           // ccf_model.py:648-650
-        const double u2 = fma(rp, rp, Sperp2);                // :651
-        radius<kFast>(u2, rp, u[i], mur[i]);                  // :651-652
+        const double rp = fma(-xm[i], q.kappa, q.Spar);       // ccf_model.py:648-650
+        const double u2 = fma(rp, rp, q.Sperp2);              // :651
+        radius<C::kFast>(u2, rp, u[i], mur[i]);               // :651-652
     }
 #pragma unroll
     for (int i = 0; i < U; ++i) {
-        const unsigned b = min((unsigned)__double2loint(__fma_rd(u[i], inv_h, 6755399441055744.0)), nbm1);
-        int cell = lds_s32(bb_s + (b << 2));
-        if (kFlags) {
-            if (cell < 0) {
+        // bucket = floor(u * inv_h) through a round-down FMA onto 1.5 * 2^52 (u >= 0; NaN -> 0)
+        const unsigned b = min((unsigned)__double2loint(__fma_rd(u[i], q.inv_h, 6755399441055744.0)), q.nbm1);
+        int cell = lds_s32(q.bb_s + (b << 2));
+        if (C::kFlags) {
+            if (cell < 0) {  // a knot lies inside this bucket: finish the search by comparison
                 cell &= ~kBucketFlag;
-                for (int sc = 0; sc < a.m.maxscan; ++sc) cell += (u[i] >= upper[cell]) ? 1 : 0;
+                for (int sc = 0; sc < q.maxscan; ++sc) cell += (u[i] >= q.upper[cell]) ? 1 : 0;
             }
         }
-        ra[i] = rec_s + cell * (kRec * 8);
+        ra[i] = q.rec_s + cell * (kRec * 8);
     }
 #pragma unroll
     for (int i = 0; i < U; ++i) {
+        // t = max(t, 0): below the first knot every spline is its boundary value (ext=3), which is
+        // the first cell's cubic at t = 0.  Done on the high word with an integer max: a negative
+        // t becomes a positive denormal-sized number, i.e. 0 for the cubic.
         double tt = u[i] - lds_f64(ra[i] + 96);
         const int hi = __double2hiint(tt);
-        t[i] = __hiloint2double(max(hi, 0), __double2loint(tt));   // t = max(t, 0), see k_multipoles
+        t[i] = __hiloint2double(max(hi, 0), __double2loint(tt));
     }
 #pragma unroll
     for (int i = 0; i < U; ++i) {
         const double2 c89 = lds_f64x2(ra[i] + 64), cab = lds_f64x2(ra[i] + 80);
         const double sv = fma(fma(fma(cab.y, t[i], cab.x), t[i], c89.y), t[i], c89.x);   // :654-655
-        q[i] = kFast ? rcp_cubic(sv) : 1.0 / sv;
+        rq[i] = C::kFast ? rcp_cubic(sv) : 1.0 / sv;
     }
 #pragma unroll
     for (int i = 0; i < U; ++i) {
         const double2 c45 = lds_f64x2(ra[i] + 32), c67 = lds_f64x2(ra[i] + 48);
         const double vb = fma(fma(fma(c67.y, t[i], c67.x), t[i], c45.y), t[i], c45.x);   // :635, :656
-        const double z = fma(-vb, mur[i], xm[i]) * q[i];
+        const double z = fma(-vb, mur[i], xm[i]) * rq[i];
         z2[i] = z * z;
     }
 #pragma unroll
-    for (int i = 0; i < U; ++i) g[i] = kFast ? gauss_tab(z2[i], etab_s) : exp(-0.5 * z2[i]);
+    for (int i = 0; i < U; ++i) g[i] = C::kFast ? gauss_tab<C::kExp>(z2[i], q.etab_s) : exp(-0.5 * z2[i]);
 #pragma unroll
     for (int i = 0; i < U; ++i) {
         const double2 c01 = lds_f64x2(ra[i]), c23 = lds_f64x2(ra[i] + 16);
         const double xi1 = fma(fma(fma(c23.y, t[i], c23.x), t[i], c01.y), t[i], c01.x);  // :621, :683
-        acc = fma(wm[i] * (xi1 * q[i]), g[i], acc);                                       // :690
+        if (kW) {
+            accA = fma(a.xw[kMaxNx + mi + i] * (xi1 * rq[i]), g[i], accA);               // :690
+        } else if (i & 1) {
+            accB = fma(xi1 * rq[i], g[i], accB);
+        } else {
+            accA = fma(xi1 * rq[i], g[i], accA);
+        }
     }
-    return acc;
 }
 
-// kFast: hand-rolled rsqrt / rcp / exp (else CUDA libm).  kFlags: some bucket holds a knot in
-// its interior, so the cell search may need the comparison path (non-lattice knot sets).
-// kU: velocity nodes processed together per loop trip (instruction-level parallelism).
-template <bool kFast, bool kFlags, int kU>
-__global__ void __launch_bounds__(256) k_multipoles(const __grid_constant__ K1Args a) {
+// register-resident copy of one cell record
+struct CellCache {
+    unsigned addr;
+    double c[12], org;
+};
+
+__device__ __forceinline__ void cell_cache_update(CellCache &cc, unsigned ra) {
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        " setp.ne.u32 p, %13, %14;\n"
+        " @p ld.shared.v2.f64 {%0, %1}, [%14];\n"
+        " @p ld.shared.v2.f64 {%2, %3}, [%14+16];\n"
+        " @p ld.shared.v2.f64 {%4, %5}, [%14+32];\n"
+        " @p ld.shared.v2.f64 {%6, %7}, [%14+48];\n"
+        " @p ld.shared.v2.f64 {%8, %9}, [%14+64];\n"
+        " @p ld.shared.v2.f64 {%10, %11}, [%14+80];\n"
+        " @p ld.shared.f64 %12, [%14+96];\n"
+        " @p mov.u32 %13, %14;\n"
+        "}"
+        : "+d"(cc.c[0]), "+d"(cc.c[1]), "+d"(cc.c[2]), "+d"(cc.c[3]), "+d"(cc.c[4]), "+d"(cc.c[5]),
+          "+d"(cc.c[6]), "+d"(cc.c[7]), "+d"(cc.c[8]), "+d"(cc.c[9]), "+d"(cc.c[10]), "+d"(cc.c[11]),
+          "+d"(cc.org), "+r"(cc.addr)
+        : "r"(ra));
+}
+
+// kCache variant of quad_nodes: the radius / cell-search stage and the exp stage run U nodes
+// abreast, the polynomial stage goes node by node through the cached record.
+template <class C, int U>
+__device__ __forceinline__ void quad_nodes_cached(const K1Args &a, const QuadCtx &q, int mi, double &acc,
+                                                  CellCache &cc) {
+    double xm[U], u[U], mur[U], z2[U], xq[U], g[U];
+    unsigned ra[U];
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+        xm[i] = a.xw[mi + i];
+        const double rp = fma(-xm[i], q.kappa, q.Spar);
+        const double u2 = fma(rp, rp, q.Sperp2);
+        radius<C::kFast>(u2, rp, u[i], mur[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+        const unsigned b = min((unsigned)__double2loint(__fma_rd(u[i], q.inv_h, 6755399441055744.0)), q.nbm1);
+        int cell = lds_s32(q.bb_s + (b << 2));
+        if (C::kFlags) {
+            if (cell < 0) {
+                cell &= ~kBucketFlag;
+                for (int sc = 0; sc < q.maxscan; ++sc) cell += (u[i] >= q.upper[cell]) ? 1 : 0;
+            }
+        }
+        ra[i] = q.rec_s + cell * (kRec * 8);
+    }
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+        cell_cache_update(cc, ra[i]);
+        double tt = u[i] - cc.org;
+        const int hi = __double2hiint(tt);
+        const double t = __hiloint2double(max(hi, 0), __double2loint(tt));
+        const double sv = fma(fma(fma(cc.c[11], t, cc.c[10]), t, cc.c[9]), t, cc.c[8]);
+        const double rq = C::kFast ? rcp_cubic(sv) : 1.0 / sv;
+        const double vb = fma(fma(fma(cc.c[7], t, cc.c[6]), t, cc.c[5]), t, cc.c[4]);
+        const double z = fma(-vb, mur[i], xm[i]) * rq;
+        z2[i] = z * z;
+        const double xi1 = fma(fma(fma(cc.c[3], t, cc.c[2]), t, cc.c[1]), t, cc.c[0]);
+        xq[i] = a.xw[kMaxNx + mi + i] * (xi1 * rq);
+    }
+#pragma unroll
+    for (int i = 0; i < U; ++i) g[i] = C::kFast ? gauss_tab<C::kExp>(z2[i], q.etab_s) : exp(-0.5 * z2[i]);
+#pragma unroll
+    for (int i = 0; i < U; ++i) acc = fma(xq[i], g[i], acc);
+}
+
+template <class C>
+__global__ void __launch_bounds__(256, C::kMinBlocks) k_multipoles(const __grid_constant__ K1Args a) {
+    constexpr int kU = C::kU;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const ModelDev &m = a.m;
     const int ncell = m.ncell, nx = m.nx;
@@ -329,28 +447,43 @@ __global__ void __launch_bounds__(256) k_multipoles(const __grid_constant__ K1Ar
     __syncthreads();
 
     // ---- quadrature: thread <-> (s_j, mu_k), loop over the velocity nodes in registers ----
-    const double sperp_f = scal[1], spar_f = scal[2], kappa = scal[3];
+    const double sperp_f = scal[1], spar_f = scal[2];
     const int nmu = a.nmu;
     const int npairs = jn * nmu;
-    const unsigned nbm1 = (unsigned)(m.nbucket - 1);
-    const double inv_h = pin_f64(m.inv_h);
-    const unsigned rec_s = pin_u32((unsigned)__cvta_generic_to_shared(rec));
-    const unsigned etab_s = pin_u32((unsigned)__cvta_generic_to_shared(etab));
-    const unsigned bb_s = pin_u32((unsigned)__cvta_generic_to_shared(bbase));
+    QuadCtx q;
+    q.kappa = scal[3];
+    q.inv_h = pin_f64(m.inv_h);
+    q.nbm1 = (unsigned)(m.nbucket - 1);
+    q.rec_s = pin_u32((unsigned)__cvta_generic_to_shared(rec));
+    q.etab_s = pin_u32((unsigned)__cvta_generic_to_shared(etab));
+    q.bb_s = pin_u32((unsigned)__cvta_generic_to_shared(bbase));
+    q.upper = upper;
+    q.maxscan = m.maxscan;
     for (int pidx = tid; pidx < npairs; pidx += nthr) {
         const int jl = pidx / nmu, k = pidx - jl * nmu;
         const double sj = a.s[j0 + jl];
         const double Sperp = sj * a.sqmu[k] * sperp_f;
-        const double Spar = sj * a.mu[k] * spar_f;
-        const double Sperp2 = Sperp * Sperp;
-        double acc = 0.0;
+        q.Spar = sj * a.mu[k] * spar_f;
+        q.Sperp2 = Sperp * Sperp;
+        double acc = 0.0, dummy = 0.0;
         int mi = 0;
-        for (; mi + kU <= nx; mi += kU)
-            acc = quad_nodes<kFast, kFlags, kU>(a, mi, kappa, Spar, Sperp2, inv_h, nbm1, bb_s, rec_s, etab_s,
-                                                upper, acc);
-        for (; mi < nx; ++mi)
-            acc = quad_nodes<kFast, kFlags, 1>(a, mi, kappa, Spar, Sperp2, inv_h, nbm1, bb_s, rec_s, etab_s,
-                                               upper, acc);
+        if (C::kCache) {
+            CellCache cc;
+            cc.addr = 0xffffffffu;
+#pragma unroll
+            for (int i = 0; i < 12; ++i) cc.c[i] = 0.0;
+            cc.org = 0.0;
+            for (; mi + kU <= nx; mi += kU) quad_nodes_cached<C, kU>(a, q, mi, acc, cc);
+            for (; mi < nx; ++mi) quad_nodes_cached<C, 1>(a, q, mi, acc, cc);
+        } else if (C::kGroup) {
+            double accA = 0.0, accB = 0.0;
+            for (; mi < a.g0; ++mi) quad_nodes<C, 1, true>(a, q, mi, acc, dummy);
+            for (; mi < a.g1; mi += kU) quad_nodes<C, kU, false>(a, q, mi, accA, accB);
+            acc = fma(a.wA, accA, fma(a.wB, accB, acc));
+        } else {
+            for (; mi + kU <= nx; mi += kU) quad_nodes<C, kU, true>(a, q, mi, acc, dummy);
+        }
+        for (; mi < nx; ++mi) quad_nodes<C, 1, true>(a, q, mi, acc, dummy);
         stage[pidx] = acc - 1.0;  // ccf_model.py:690
     }
     __syncthreads();
@@ -513,9 +646,117 @@ __global__ void k_math_selftest(const double *x, long long n, const double *etab
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double v = x[i];
-    out[i] = gauss_tab(v, (unsigned)__cvta_generic_to_shared(tab));   // exp(-v/2)
+    out[i] = gauss_tab<6>(v, (unsigned)__cvta_generic_to_shared(tab));   // exp(-v/2)
     out[n + i] = fast_rsqrt(v);
     out[2 * n + i] = rcp_cubic(v);
+    out[3 * n + i] = gauss_tab<5>(v, (unsigned)__cvta_generic_to_shared(tab));
+}
+
+// ---------------------------------------------------------------------------------------
+// pipe probe: which issue pipe do the FP64 <-> int/float conversions use, and how exact are the
+// MUFU seeds?  mode 0: DFMA only; 1: cvt.rmi.s32.f64 only; 2: both interleaved 1:1;
+// 3: cvt.rn.f32.f64 only; 4: DFMA + cvt.rn.f32.f64; 5: I2F (s32 -> f64) only; 6: DFMA + I2F.
+// ---------------------------------------------------------------------------------------
+template <int kMode>
+__global__ void __launch_bounds__(256) k_pipe_probe(double *out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-3 + 1.0, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3;
+    double y0 = x0 * 0.5, y1 = x1 * 0.5, y2 = x2 * 0.5, y3 = x3 * 0.5;
+    int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
+    float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            if (kMode == 0 || kMode == 2 || kMode == 4 || kMode == 6) {
+                x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            }
+            if (kMode == 1 || kMode == 2) {
+                int t0, t1, t2, t3;
+                asm volatile("cvt.rmi.s32.f64 %0, %1;" : "=r"(t0) : "d"(y0));
+                asm volatile("cvt.rmi.s32.f64 %0, %1;" : "=r"(t1) : "d"(y1));
+                asm volatile("cvt.rmi.s32.f64 %0, %1;" : "=r"(t2) : "d"(y2));
+                asm volatile("cvt.rmi.s32.f64 %0, %1;" : "=r"(t3) : "d"(y3));
+                i0 ^= t0; i1 ^= t1; i2 ^= t2; i3 ^= t3;
+                // feed the result back into the low word of the next input (integer ops only)
+                y0 = __hiloint2double(__double2hiint(y0), i0 + r); y1 = __hiloint2double(__double2hiint(y1), i1 + r);
+                y2 = __hiloint2double(__double2hiint(y2), i2 + r); y3 = __hiloint2double(__double2hiint(y3), i3 + r);
+            }
+            if (kMode == 3 || kMode == 4) {
+                float t0, t1, t2, t3;
+                asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(t0) : "d"(y0));
+                asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(t1) : "d"(y1));
+                asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(t2) : "d"(y2));
+                asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(t3) : "d"(y3));
+                f0 += t0; f1 += t1; f2 += t2; f3 += t3;
+                y0 = __hiloint2double(__double2hiint(y0), __float_as_int(f0)); y1 = __hiloint2double(__double2hiint(y1), __float_as_int(f1));
+                y2 = __hiloint2double(__double2hiint(y2), __float_as_int(f2)); y3 = __hiloint2double(__double2hiint(y3), __float_as_int(f3));
+            }
+            if (kMode == 5 || kMode == 6) {
+                double t0, t1, t2, t3;
+                asm volatile("cvt.rn.f64.s32 %0, %1;" : "=d"(t0) : "r"(i0 + r));
+                asm volatile("cvt.rn.f64.s32 %0, %1;" : "=d"(t1) : "r"(i1 + r));
+                asm volatile("cvt.rn.f64.s32 %0, %1;" : "=d"(t2) : "r"(i2 + r));
+                asm volatile("cvt.rn.f64.s32 %0, %1;" : "=d"(t3) : "r"(i3 + r));
+                i0 ^= __double2loint(t0); i1 ^= __double2loint(t1); i2 ^= __double2loint(t2); i3 ^= __double2loint(t3);
+            }
+        }
+    }
+    double s = (x0 + x1) + (x2 + x3) + (double)(i0 + i1 + i2 + i3) + (double)(f0 + f1 + f2 + f3);
+    if (s == 12345.678) out[0] = s;
+}
+
+// DFMA issue model probe: kChains independent dependent-FMA chains per thread, with kMix other
+// instructions after every DFMA (kKind 0: integer IMAD, 1: LDS.64 broadcast, 2: DMUL with a
+// constant-bank operand instead of the plain DFMA).  128 threads per block = 1 warp per SMSP.
+template <int kChains, int kMix, int kKind>
+__global__ void __launch_bounds__(128) k_mix_probe(double *out, int iters, double a, double b, int ia) {
+    __shared__ double sh[64];
+    if (threadIdx.x < 64) sh[threadIdx.x] = 1.0 + threadIdx.x * 1e-9;
+    __syncthreads();
+    double x[kChains];
+    int n[kChains];
+    double acc = 0.0;
+#pragma unroll
+    for (int c = 0; c < kChains; ++c) {
+        x[c] = threadIdx.x * 1e-3 + c;
+        n[c] = threadIdx.x + c;
+    }
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(sh);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int c = 0; c < kChains; ++c) {
+                if (kKind == 2) x[c] = x[c] * kExpPoly[0] + b; else x[c] = fma(x[c], a, b);
+#pragma unroll
+                for (int k = 0; k < kMix; ++k) {
+                    if (kKind == 1) {
+                        n[c] += __double2loint(lds_f64(sbase + ((n[c] & 7) << 3))) + ia;
+                    } else {
+                        asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(n[c]) : "r"(ia), "r"(k));
+                    }
+                }
+            }
+        }
+    }
+    double s = acc;
+    int t = 0;
+#pragma unroll
+    for (int c = 0; c < kChains; ++c) {
+        s += x[c];
+        t += n[c];
+    }
+    if (s == 12345.678 || t == 123456789) out[0] = s + t;
+}
+
+// raw MUFU seeds (no refinement): out[0..n) = rsqrt.approx(x), out[n..2n) = rcp.approx(x)
+__global__ void k_seed_probe(const double *x, long long n, double *out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double y, q;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x[i]));
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(x[i]));
+    out[i] = y;
+    out[n + i] = q;
 }
 
 // ---------------------------------------------------------------------------------------
