@@ -45,7 +45,7 @@ enum { VB200_P_FSIGMA8 = 0, VB200_P_BETA, VB200_P_SIGMA_V, VB200_P_APERP, VB200_
 
 enum { VB200_OK = 0, VB200_EINVAL = -1, VB200_ECUDA = -2, VB200_ENOMEM = -3, VB200_EUNSUPPORTED = -4 };
 
-enum { VB200_RSD_STREAMING = 0, VB200_RSD_DISPERSION = 1, VB200_RSD_KAISER = 2 };
+enum { VB200_RSD_STREAMING = 0, VB200_RSD_DISPERSION = 1, VB200_RSD_KAISER = 2, VB200_RSD_EUCLID = 3 };
 enum { VB200_LIKE_LINEAR = 0, VB200_LIKE_LOG = 1 };
 
 #define VB200_MAX_POLES 3
@@ -70,6 +70,10 @@ typedef struct vb200_model_tables {
     int32_t nbeta;            /* length of beta_grid (>= 2) */
     int32_t nx;               /* velocity nodes */
     int32_t nresc;            /* nodes of the AP rescaling trapezoid (:609-610) */
+    int32_t realspace_from_data;  /* model['realspace_ccf']['from_data'] (:675-679) */
+    int32_t kaiser_approximation; /* (:737-741) */
+    int32_t kaiser_coord_shift;   /* (:696-703) */
+    int32_t niter;            /* fixed-point iterations of the dispersion / kaiser coordinate map (5) */
     const double *origin;     /* [ncell] */
     const double *upper;      /* [ncell], last = +inf */
     const int32_t *bucket_base; /* [nbucket] */
@@ -121,8 +125,9 @@ void vb200_destroy(vb200_ctx *ctx);
 
 /* Kernel variant switches (integers): "fast_math" (1 = hand-rolled rsqrt / rcp / exp, default;
  * 0 = CUDA libm), "nsplit" (blocks per parameter row; 0 = automatic), "threads" (block size),
- * "ilp" (velocity nodes per loop trip: 1, 2, 4), "exp_degree" (5 or 6), "group_weights"
- * (1 = apply the alternating Simpson weights once per class instead of once per node). */
+ * "ilp" (velocity nodes per loop trip: 1, 2, 4), "exp_degree" (5, default, or 6).  They select
+ * among the tuned streaming kernels; the general kernel (dispersion, kaiser, anisotropic or
+ * from-data real-space input) has one variant per rsd_model. */
 int vb200_set_option(vb200_ctx *ctx, const char *key, int64_t value);
 
 /* xi(s, mu) and / or its projections for n parameter rows.

@@ -218,6 +218,50 @@ def golden_boss(victor):
              beta_covmat=cmd.beta_covmat, **meta())
 
 
+def golden_more(victor):
+    """Option combinations beyond notebook cell 22: euclid_special, kaiser without the coordinate
+    shift / in the linear approximation (with M, Q), anisotropic input under the dispersion and
+    kaiser models, anisotropic input with from-data coordinates (measured model file)."""
+    model, data = boss_blocks()
+    ccf = victor.CCFFit(copy.deepcopy(model), copy.deepcopy(data))
+    P = np.vstack([synthetic_batch(65536)[:4], edge_rows(ccf.beta)[[0, 9]]])
+    MQ = np.array([[1.0, 1.0], [0.9, 1.1], [1.05, 0.8], [1.2, 1.0], [1.0, 1.3], [0.95, 0.9]])
+    out = dict(params=P, MQ=MQ)
+    cases = [("euclid", {"rsd_model": "euclid_special"}),
+             ("kaiser_noshift", {"rsd_model": "kaiser", "kaiser_coord_shift": False}),
+             ("kaiser_approx", {"rsd_model": "kaiser", "kaiser_approximation": True}),
+             ("kaiser_mq", {"rsd_model": "kaiser"}),
+             ("aniso_dispersion", {"rsd_model": "dispersion", "assume_isotropic": False}),
+             ("aniso_kaiser", {"rsd_model": "kaiser", "assume_isotropic": False})]
+    for name, kw in cases:
+        th, c2, ll = [], [], []
+        for row, mq in zip(P, MQ):
+            prm = row_to_params(row)
+            prm.update(M=float(mq[0]), Q=float(mq[1]))
+            th.append(ccf.theory_multipole_vector(ccf.s, dict(prm), ccf.poles_s, **kw))
+            a, b = ccf.log_likelihood(dict(prm), **kw)
+            ll.append(a)
+            c2.append(b)
+        out[f"{name}_theory"], out[f"{name}_chi2"], out[f"{name}_lnl"] = np.array(th), np.array(c2), np.array(ll)
+    mm = copy.deepcopy(model)
+    mm["input_model_data_file"] = ("data/BOSS_DR12_CMASS_data/"
+                                   "CMASS_zobovVoids_reconRs10_0.43z0.7_medianRvcut_measured_model.hdf5")
+    mm["realspace_ccf"]["from_data"] = True
+    mm["realspace_ccf"]["assume_isotropic"] = False
+    dm = copy.deepcopy(data)
+    dm["covariance_matrix"]["data_file"] = (
+        "data/BOSS_DR12_CMASS_data/"
+        "CMASS_zobovVoids_reconRs10_0.43z0.7_medianRvcut_variable_anisotropic_MD_covariance.hdf5")
+    cmd = victor.CCFFit(mm, dm)
+    Pm = P[:4].copy()
+    Pm[:, 1] = np.clip(Pm[:, 1], 0.25, 0.55)
+    for name, kw in (("measured_aniso", {}), ("measured_aniso_dispersion", {"rsd_model": "dispersion"})):
+        th, c2, ll = run_points(cmd, Pm, **kw)
+        out[f"{name}_theory"], out[f"{name}_chi2"], out[f"{name}_lnl"] = th, c2, ll
+    out["measured_params"] = Pm
+    np.savez(os.path.join(OUT, "boss_more_variants.npz"), **out, **meta())
+
+
 def golden_example(victor):
     with open(os.path.join(REF, "config/example_model_input.yaml")) as fh:
         model = yaml.full_load(fh)["model"]
@@ -245,7 +289,12 @@ def golden_example(victor):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     v = refshim.install(REF)
-    golden_boss(v)
-    golden_example(v)
+    which = sys.argv[1:] or ["boss", "more", "example"]
+    if "boss" in which:
+        golden_boss(v)
+    if "more" in which:
+        golden_more(v)
+    if "example" in which:
+        golden_example(v)
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))

@@ -70,45 +70,113 @@ def xi_cells(mt, beta):
     return np.moveaxis(c, 0, 1)                 # [n][n_ell][ncell][4]
 
 
+def _legendre_even(ell, x):
+    if ell == 0:
+        return np.ones_like(x)
+    if ell == 2:
+        return 1.5 * x * x - 0.5
+    return (4.375 * x * x - 3.75) * x * x + 0.375
+
+
+def _xi_real(mt, xc, idx, cell, t, mur):
+    """sum_l xi_l(u) L_l(mu_r) from the per-row cell coefficients xc [c][n_ell][ncell][4]."""
+    tot = 0.0
+    for li in range(mt.n_ell):
+        kl = xc[idx, li, cell]
+        xil = ((kl[..., 3] * t + kl[..., 2]) * t + kl[..., 1]) * t + kl[..., 0]
+        tot = tot + (xil if li == 0 else xil * _legendre_even(int(mt.ells[li]), mur))
+    return tot
+
+
 def theory_xi(mt, rows, s, mu, chunk=32):
-    """xi(s, mu) for each row: [n][nmu][ns].  Streaming model, isotropic template dispersion."""
-    if mt.rsd_model != T.RSD_STREAMING:
-        raise NotImplementedError("table_emul: streaming model only")
+    """xi(s, mu) for each row: [n][nmu][ns].  All rsd models of the kernels (streaming, dispersion,
+    kaiser, euclid_special), isotropic or anisotropic real-space input, model or from-data
+    coordinates; isotropic template dispersion.  Mirrors victor_b200/csrc/k1_general.cuh."""
     rows = np.asarray(rows, float)
     n = len(rows)
     out = np.empty((n, len(mu), len(s)))
     sq = np.sqrt(1 - mu ** 2)
+    rsd = mt.rsd_model
+    x = mt.x if rsd in (T.RSD_STREAMING, T.RSD_DISPERSION) else np.zeros(1)
     for a in range(0, n, chunk):
         R = rows[a:a + chunk]
         sc = point_scalars(mt, R)
         sig = R[:, 2]
         beta = R[:, 1] if mt.beta_dependent else np.full(len(R), mt.beta_fixed)
         xc = xi_cells(mt, beta)                                    # [c][n_ell][ncell][4]
-        Sperp = s[None, None, :] * sq[None, :, None] * (R[:, 3] / sc["f"])[:, None, None]
-        Spar = s[None, None, :] * mu[None, :, None] * (R[:, 4] / sc["f"])[:, None, None]
-        cm = mt.x[None, :] * (sig * sc["iaHt"] / sc["f"])[:, None]   # [c][nx]
-        Rpar = Spar[..., None] - cm[:, None, None, :]
-        u2 = Sperp[..., None] ** 2 + Rpar ** 2
-        with np.errstate(invalid="ignore", divide="ignore"):
-            u = np.sqrt(u2)
-            mur = Rpar / u
-        cell, t = _cells(mt, u)
-        svv = _horner(mt.sv, cell, t)
-        v0 = _horner(mt.v0, cell, t)
-        B = (sc["Av"] / sig)[:, None, None, None]
-        z = (mt.x[None, None, None, :] - B * v0 * mur) / svv
         idx = np.arange(len(R))[:, None, None, None]
-        k0 = xc[idx, 0, cell]                                       # [...,4]
-        xi0 = ((k0[..., 3] * t + k0[..., 2]) * t + k0[..., 1]) * t + k0[..., 0]
-        tot = xi0
-        for li in range(1, mt.n_ell):
-            kl = xc[idx, li, cell]
-            xil = ((kl[..., 3] * t + kl[..., 2]) * t + kl[..., 1]) * t + kl[..., 0]
-            ell = int(mt.ells[li])
-            pl = 0.5 * (3 * mur ** 2 - 1) if ell == 2 else (35 * mur ** 4 - 30 * mur ** 2 + 3) / 8
-            tot = tot + xil * pl
-        integrand = (1 + tot) * np.exp(-0.5 * z * z) / svv
-        out[a:a + chunk] = (integrand * mt.wx[None, None, None, :]).sum(axis=-1) - 1
+        f = sc["f"][:, None, None, None]
+        apar = R[:, 4][:, None, None, None]
+        Sperp = (s[None, None, :] * sq[None, :, None] * (R[:, 3] / sc["f"])[:, None, None])[..., None]
+        Spar = (s[None, None, :] * mu[None, :, None] * (R[:, 4] / sc["f"])[:, None, None])[..., None]
+        rt_data = (s[None, None, :] * sq[None, :, None] * np.ones(len(R))[:, None, None])[..., None]
+        kap = (sig * sc["iaHt"] / sc["f"])[:, None, None, None]
+        B = (sc["Av"] / sig)[:, None, None, None]
+        G = (sc["iaHt"] * sc["Av"] / sc["f"])[:, None, None, None]
+        xm = x[None, None, None, :]
+        Sperp2 = Sperp ** 2
+
+        def xi_at(rp, cell, t, mur):
+            if not mt.from_data:
+                return _xi_real(mt, xc, idx, cell, t, mur)
+            rpd = rp * f / apar
+            rd = np.sqrt(rpd ** 2 + rt_data ** 2)
+            cd, td = _cells(mt, rd + 0 * rp)
+            return _xi_real(mt, xc, idx, cd, td, rpd / rd)
+
+        with np.errstate(invalid="ignore", divide="ignore"):
+            if rsd == T.RSD_STREAMING:
+                rp = Spar - xm * kap
+                u = np.sqrt(Sperp2 + rp ** 2)
+                mur = rp / u
+                cell, t = _cells(mt, u)
+                svv = _horner(mt.sv, cell, t)
+                z = (xm - B * _horner(mt.v0, cell, t) * mur) / svv
+                integrand = (1 + xi_at(rp, cell, t, mur)) * np.exp(-0.5 * z * z) / svv
+                out[a:a + chunk] = (integrand * mt.wx[None, None, None, :]).sum(axis=-1) - 1
+            elif rsd == T.RSD_DISPERSION:
+                Strue = np.sqrt(Sperp2 + Spar ** 2)
+                c0, t0 = _cells(mt, Strue)
+                num = Spar - xm * kap
+                rp = num / (1 + G * _horner(mt.v0, c0, t0) / Strue)
+                for _ in range(mt.niter):
+                    u = np.sqrt(Sperp2 + rp ** 2)
+                    cell, t = _cells(mt, u)
+                    rp = num / (1 + G * _horner(mt.v0, cell, t) / u)
+                u = np.sqrt(Sperp2 + rp ** 2)
+                mur = rp / u
+                cell, t = _cells(mt, u)
+                svv = _horner(mt.sv, cell, t)
+                v0u = _horner(mt.v0, cell, t) / u
+                jac = 1 / (1 + G * v0u + G * mur ** 2 * (_horner(mt.d0, cell, t) - v0u))
+                z = xm / svv
+                integrand = (1 + xi_at(rp, cell, t, mur)) * jac * np.exp(-0.5 * z * z) / svv
+                out[a:a + chunk] = (integrand * mt.wx[None, None, None, :]).sum(axis=-1) - 1
+            else:
+                Mk = R[:, 6][:, None, None, None]
+                Qk = R[:, 7][:, None, None, None]
+                MG = Mk * G
+                rp = Spar + 0 * MG
+                if mt.kaiser_coord_shift:
+                    Strue = np.sqrt(Sperp2 + Spar ** 2)
+                    c0, t0 = _cells(mt, Strue)
+                    rp = Spar / (1 + MG * _horner(mt.v0, c0, t0) / Strue)
+                    for _ in range(mt.niter):
+                        u = np.sqrt(Sperp2 + rp ** 2)
+                        cell, t = _cells(mt, u)
+                        rp = Spar / (1 + MG * _horner(mt.v0, cell, t) / u)
+                u = np.sqrt(Sperp2 + rp ** 2)
+                mur = rp / u
+                cell, t = _cells(mt, u)
+                v0u = _horner(mt.v0, cell, t) / u
+                ca, cb = (3.0, 2.0) if rsd == T.RSD_EUCLID else (1.0, 1.0)
+                J = ca * MG * v0u + cb * MG * Qk * mur ** 2 * (_horner(mt.d0, cell, t) - v0u)
+                xi = xi_at(rp, cell, t, mur)
+                if rsd == T.RSD_EUCLID or mt.kaiser_approximation:
+                    res = Mk * xi - J
+                else:
+                    res = (1 + Mk * xi) / (1 + J) - 1
+                out[a:a + chunk] = res[..., 0]
     return out
 
 

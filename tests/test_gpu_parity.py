@@ -13,7 +13,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 RTOL, ATOL, CHI2_ATOL = 1e-9, 1e-13, 1e-6
-DEFAULT_EXP_DEGREE, DEFAULT_GROUP, DEFAULT_CACHE = 6, 0, 0   # library defaults (victor_b200/csrc/api.cu)
+DEFAULT_EXP_DEGREE = 5   # library default (victor_b200/csrc/api.cu)
 
 
 def assert_theory(got, want, ns=None):
@@ -83,15 +83,12 @@ def test_boss_streaming_golden(fit, golden, fast):
     np.testing.assert_allclose(lnl, g["lnl"], rtol=0, atol=CHI2_ATOL)
 
 
-@pytest.mark.parametrize("opts", [{"ilp": 1}, {"ilp": 2}, {"exp_degree": 5}, {"group_weights": 1},
-                                  {"exp_degree": 5, "group_weights": 1}, {"threads": 128},
-                                  {"cell_cache": 1}, {"cell_cache": 1, "ilp": 1}, {"cell_cache": 2, "ilp": 2}])
+@pytest.mark.parametrize("opts", [{"ilp": 1}, {"ilp": 2}, {"exp_degree": 6}, {"threads": 128}, {"threads": 64}])
 def test_kernel_variants_hold_parity(fit, golden, opts):
     """Every tuning variant of K1 must meet the same bar as the default."""
     g = golden("boss_streaming_points")
     eng, _ = fit._fit_engine({})
-    defaults = {"ilp": 4, "exp_degree": DEFAULT_EXP_DEGREE, "group_weights": DEFAULT_GROUP, "threads": 256,
-                "cell_cache": DEFAULT_CACHE}
+    defaults = {"ilp": 4, "exp_degree": DEFAULT_EXP_DEGREE, "threads": 256}
     try:
         for k, v in opts.items():
             eng.set_option(k, v)
@@ -258,3 +255,94 @@ def test_full_batch_properties(fit):
         cov = fit.get_interpolated_covariance(P[i, 1])
         want = -1000 * np.log(1 + chi2[i] / 999) / 2 - 0.5 * np.linalg.slogdet(cov)[1]
         assert abs(want - lnl[i]) < 1e-8
+
+
+# ---------------------------------------------------------------------------------------------
+# general kernel: dispersion, kaiser, euclid_special, anisotropic input, from-data coordinates
+# 
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,kw", [("dispersion", {"rsd_model": "dispersion"}), ("kaiser", {"rsd_model": "kaiser"}),
+                                     ("anisotropic", {"assume_isotropic": False})])
+def test_variant_models_golden(fit, golden, name, kw):
+    g = golden("boss_variant_points")
+    lnl, chi2, theory = fit.log_likelihood_batch(g["params"], return_theory=True, **kw)
+    assert_theory(theory, g[f"{name}_theory"], ns=len(fit.s))
+    np.testing.assert_allclose(chi2, g[f"{name}_chi2"], rtol=0, atol=CHI2_ATOL)
+    np.testing.assert_allclose(lnl, g[f"{name}_lnl"], rtol=0, atol=CHI2_ATOL)
+    a = golden("boss_notebook_anchors")
+    l0, c0 = fit.log_likelihood({"fsigma8": 0.47, "beta": 0.37, "sigma_v": 380, "epsilon": 1.0}, **kw)
+    assert abs(c0 - float(a[f"{name}_chi2"])) < CHI2_ATOL and abs(l0 - float(a[f"{name}_lnl"])) < CHI2_ATOL
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("euclid", {"rsd_model": "euclid_special"}),
+    ("kaiser_noshift", {"rsd_model": "kaiser", "kaiser_coord_shift": False}),
+    ("kaiser_approx", {"rsd_model": "kaiser", "kaiser_approximation": True}),
+    ("kaiser_mq", {"rsd_model": "kaiser"}),
+    ("aniso_dispersion", {"rsd_model": "dispersion", "assume_isotropic": False}),
+    ("aniso_kaiser", {"rsd_model": "kaiser", "assume_isotropic": False})])
+def test_more_variant_models_golden(fit, golden, name, kw):
+    g = golden("boss_more_variants")
+    P = dict(zip(("fsigma8", "beta", "sigma_v", "aperp", "apar"), g["params"].T))
+    P.update(M=g["MQ"][:, 0], Q=g["MQ"][:, 1])
+    lnl, chi2, theory = fit.log_likelihood_batch(P, return_theory=True, **kw)
+    assert_theory(theory, g[f"{name}_theory"], ns=len(fit.s))
+    np.testing.assert_allclose(chi2, g[f"{name}_chi2"], rtol=0, atol=CHI2_ATOL)
+    np.testing.assert_allclose(lnl, g[f"{name}_lnl"], rtol=0, atol=CHI2_ATOL)
+
+
+@pytest.mark.parametrize("aniso", [False, True])
+def test_measured_model_from_data(boss_blocks, golden, aniso):
+    from victor_b200 import CCFFit
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["input_model_data_file"] = "data/boss_dr12_cmass/cmass_measured_model.npz"
+    model["realspace_ccf"]["from_data"] = True
+    model["realspace_ccf"]["assume_isotropic"] = not aniso
+    kind = "anisotropic" if aniso else "isotropic"
+    data["covariance_matrix"]["data_file"] = f"data/boss_dr12_cmass/cmass_variable_{kind}_MD_covariance.npz"
+    fm = CCFFit(model, data)
+    if aniso:
+        g = golden("boss_more_variants")
+        cases = [("measured_aniso", {}), ("measured_aniso_dispersion", {"rsd_model": "dispersion"})]
+        P = g["measured_params"]
+    else:
+        g = golden("boss_measured_model")
+        cases = [(None, {})]
+        P = g["params"]
+    for name, kw in cases:
+        pre = f"{name}_" if name else ""
+        lnl, chi2, theory = fm.log_likelihood_batch(P, return_theory=True, **kw)
+        assert_theory(theory, g[f"{pre}theory"], ns=len(fm.s))
+        np.testing.assert_allclose(chi2, g[f"{pre}chi2"], rtol=0, atol=CHI2_ATOL)
+        np.testing.assert_allclose(lnl, g[f"{pre}lnl"], rtol=0, atol=CHI2_ATOL)
+    fm.close()
+
+
+def test_example_config_other_models(example_block, golden):
+    from victor_b200 import CCFModel
+    g = golden("example_points")
+    m = CCFModel(copy.deepcopy(example_block))
+    P = {"fsigma8": g["params"][:, 0], "sigma_v": g["params"][:, 1], "epsilon": g["params"][:, 2]}
+    for name in ("dispersion", "kaiser"):
+        th = m.theory_multipole_vector_batch(g["s"], P, poles=[0, 2, 4], rsd_model=name)
+        assert_theory(th, g[f"{name}_theory"], ns=len(g["s"]))
+    m.close()
+
+
+def test_general_kernel_agrees_with_tuned_on_streaming(fit, golden):
+    """The general kernel's streaming branch (used for anisotropic / from-data input) against the
+    tuned kernel on the same rows: an anisotropic table with a zero quadrupole is the isotropic model."""
+    g = golden("boss_streaming_points")
+    eng_iso, _ = fit._fit_engine({})
+    mt = eng_iso.model_tables
+    import dataclasses
+    from victor_b200.engine import Engine
+    xi2 = np.zeros((2,) + mt.xi_tab.shape[1:])
+    xi2[0] = mt.xi_tab[0]
+    mt2 = dataclasses.replace(mt, n_ell=2, ells=np.array([0, 2], dtype=np.int32), xi_tab=xi2)
+    eng = Engine(mt2, fit._fit_tables(fit._merged_options({})), device=None)
+    from victor_b200.model import params_to_rows
+    th2, c2, l2 = eng.likelihood(params_to_rows(g["params"]), want_theory=True)
+    assert_theory(th2, g["theory"], ns=len(fit.s))
+    np.testing.assert_allclose(c2, g["chi2"], rtol=0, atol=CHI2_ATOL)
+    eng.close()

@@ -223,3 +223,80 @@ def test_no_cpu_fallback_without_a_gpu(fit):
         pytest.skip("a GPU is visible")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         fit.log_likelihood({"fsigma8": 0.47, "beta": 0.37, "sigma_v": 380, "epsilon": 1.0})
+
+
+VARIANTS = [("dispersion", {"rsd_model": "dispersion"}), ("kaiser", {"rsd_model": "kaiser"}),
+            ("anisotropic", {"assume_isotropic": False})]
+MORE = [("euclid", {"rsd_model": "euclid_special"}),
+        ("kaiser_noshift", {"rsd_model": "kaiser", "kaiser_coord_shift": False}),
+        ("kaiser_approx", {"rsd_model": "kaiser", "kaiser_approximation": True}),
+        ("kaiser_mq", {"rsd_model": "kaiser"}),
+        ("aniso_dispersion", {"rsd_model": "dispersion", "assume_isotropic": False}),
+        ("aniso_kaiser", {"rsd_model": "kaiser", "assume_isotropic": False})]
+
+
+def _tables_vs_golden(fit, kw, rows, want_theory, want_chi2, want_lnl):
+    from victor_b200 import tables as T
+    opts = fit._merged_options(kw)
+    mt = T.build_model_tables(fit, opts)
+    ft = T.build_fit_tables(fit, fit.fit_options["likelihood"])
+    mu, W = T.mu_projection_weights(fit.poles_s)
+    mult, _ = E.theory_multipoles(mt, rows, np.asarray(fit.s, float), mu, W)
+    theory = mult.reshape(len(rows), -1)
+    np.testing.assert_allclose(theory, want_theory, rtol=RTOL, atol=ATOL)
+    chi2, lnl = E.chi2_lnl(ft, rows[:, 1], theory)
+    np.testing.assert_allclose(chi2, want_chi2, rtol=0, atol=C2_ATOL)
+    np.testing.assert_allclose(lnl, want_lnl, rtol=0, atol=C2_ATOL)
+
+
+@pytest.mark.parametrize("name,kw", VARIANTS)
+def test_tables_reproduce_reference_variants(fit, golden, name, kw):
+    """dispersion / kaiser / anisotropic input from the packed tables."""
+    from victor_b200.model import params_to_rows
+    g = golden("boss_variant_points")
+    _tables_vs_golden(fit, kw, params_to_rows(g["params"]), g[f"{name}_theory"], g[f"{name}_chi2"], g[f"{name}_lnl"])
+
+
+@pytest.mark.parametrize("name,kw", MORE)
+def test_tables_reproduce_reference_more_variants(fit, golden, name, kw):
+    from victor_b200.model import params_to_rows
+    g = golden("boss_more_variants")
+    rows = params_to_rows(g["params"])
+    rows[:, 6:8] = g["MQ"]
+    _tables_vs_golden(fit, kw, rows, g[f"{name}_theory"], g[f"{name}_chi2"], g[f"{name}_lnl"])
+
+
+@pytest.mark.parametrize("aniso", [False, True])
+def test_tables_measured_model_from_data(boss_blocks, golden, aniso):
+    """realspace_ccf from_data coordinates with the measured model file and the MD covariances."""
+    from victor_b200 import CCFFit
+    from victor_b200.model import params_to_rows
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["input_model_data_file"] = "data/boss_dr12_cmass/cmass_measured_model.npz"
+    model["realspace_ccf"]["from_data"] = True
+    model["realspace_ccf"]["assume_isotropic"] = not aniso
+    kind = "anisotropic" if aniso else "isotropic"
+    data["covariance_matrix"]["data_file"] = f"data/boss_dr12_cmass/cmass_variable_{kind}_MD_covariance.npz"
+    fm = CCFFit(model, data)
+    if aniso:
+        g = golden("boss_more_variants")
+        rows = params_to_rows(g["measured_params"])
+        _tables_vs_golden(fm, {}, rows, g["measured_aniso_theory"], g["measured_aniso_chi2"], g["measured_aniso_lnl"])
+        _tables_vs_golden(fm, {"rsd_model": "dispersion"}, rows, g["measured_aniso_dispersion_theory"],
+                          g["measured_aniso_dispersion_chi2"], g["measured_aniso_dispersion_lnl"])
+    else:
+        g = golden("boss_measured_model")
+        _tables_vs_golden(fm, {}, params_to_rows(g["params"]), g["theory"], g["chi2"], g["lnl"])
+
+
+def test_example_config_variants(example_block, golden):
+    from victor_b200 import CCFModel, tables as T
+    from victor_b200.model import params_to_rows
+    g = golden("example_points")
+    m = CCFModel(copy.deepcopy(example_block))
+    mu, W = T.mu_projection_weights([0, 2, 4])
+    P = {"fsigma8": g["params"][:, 0], "sigma_v": g["params"][:, 1], "epsilon": g["params"][:, 2]}
+    for name in ("dispersion", "kaiser"):
+        mt = T.build_model_tables(m, m._merged_options({"rsd_model": name}))
+        mult, _ = E.theory_multipoles(mt, params_to_rows(P), g["s"], mu, W)
+        np.testing.assert_allclose(mult.reshape(3, -1), g[f"{name}_theory"], rtol=RTOL, atol=ATOL)

@@ -164,3 +164,22 @@ def test_example_config(golden, example_block):
         pr = dict(fsigma8=row[0], sigma_v=row[1], epsilon=row[2])
         th = om.theory_multipole_vector(g["s"], pr, [0, 2, 4], **kw)
         np.testing.assert_allclose(th, g[f"{name}_theory"][1], rtol=1e-11, atol=1e-14)
+
+
+def test_more_variants(orc, golden):
+    """euclid_special, kaiser options with M and Q, anisotropic input under dispersion / kaiser."""
+    g = golden("boss_more_variants")
+    cases = {"euclid": {"rsd_model": "euclid_special"},
+             "kaiser_noshift": {"rsd_model": "kaiser", "kaiser_coord_shift": False},
+             "kaiser_approx": {"rsd_model": "kaiser", "kaiser_approximation": True},
+             "kaiser_mq": {"rsd_model": "kaiser"},
+             "aniso_dispersion": {"rsd_model": "dispersion", "assume_isotropic": False},
+             "aniso_kaiser": {"rsd_model": "kaiser", "assume_isotropic": False}}
+    for name, kw in cases.items():
+        for i in (1, 5):
+            prm = as_params(g["params"][i])
+            prm.update(M=float(g["MQ"][i, 0]), Q=float(g["MQ"][i, 1]))
+            th = orc.theory_multipole_vector(orc.s, dict(prm), orc.poles_s, **kw)
+            np.testing.assert_allclose(th, g[f"{name}_theory"][i], rtol=TH_RTOL, atol=TH_ATOL)
+            l, c = orc.log_likelihood(dict(prm), **kw)
+            assert abs(c - g[f"{name}_chi2"][i]) < C2_ATOL and abs(l - g[f"{name}_lnl"][i]) < C2_ATOL

@@ -25,9 +25,7 @@ def main():
     ap.add_argument("--threads", type=int, default=256)
     ap.add_argument("--nsplit", type=int, default=0)
     ap.add_argument("--ilp", type=int, default=4)
-    ap.add_argument("--expdeg", type=int, default=6)
-    ap.add_argument("--group", type=int, default=0)
-    ap.add_argument("--cache", type=int, default=0)
+    ap.add_argument("--expdeg", type=int, default=5)
     args = ap.parse_args()
     model, data = boss_blocks()
     fit = CCFFit(model, data, device=0)
@@ -37,8 +35,6 @@ def main():
     eng.set_option("nsplit", args.nsplit)
     eng.set_option("ilp", args.ilp)
     eng.set_option("exp_degree", args.expdeg)
-    eng.set_option("group_weights", args.group)
-    eng.set_option("cell_cache", args.cache)
     n = args.batch
     dev = torch.device("cuda", 0)
     d_params = torch.from_numpy(params_to_rows(synthetic_batch(n))).to(dev)
@@ -53,7 +49,7 @@ def main():
         b.record()
         torch.cuda.synchronize()
         times.append(a.elapsed_time(b))
-    print(f"batch={n} fast={args.fast} threads={args.threads} nsplit={args.nsplit} ilp={args.ilp} expdeg={args.expdeg} group={args.group} cache={args.cache} "
+    print(f"batch={n} fast={args.fast} threads={args.threads} nsplit={args.nsplit} ilp={args.ilp} expdeg={args.expdeg} "
           f"ms={['%.3f' % t for t in times]} evals/s={n / (min(times) * 1e-3):.4g} "
           f"chi2[0]={float(d_chi2[0]):.10f}")
     fit.close()

@@ -29,6 +29,8 @@ class ModelTablesC(ctypes.Structure):
         ("ells", c_int32 * MAX_POLES), ("beta_dependent", c_int32),
         ("ncell", c_int32), ("nbucket", c_int32), ("maxscan", c_int32),
         ("nbeta", c_int32), ("nx", c_int32), ("nresc", c_int32),
+        ("realspace_from_data", c_int32), ("kaiser_approximation", c_int32), ("kaiser_coord_shift", c_int32),
+        ("niter", c_int32),
         ("origin", c_double_p), ("upper", c_double_p), ("bucket_base", c_int32_p),
         ("beta_grid", c_double_p), ("xi_tab", c_double_p),
         ("v0", c_double_p), ("d0", c_double_p), ("sv", c_double_p),
@@ -122,6 +124,8 @@ def pack_model(mt):
     c.beta_dependent = int(mt.beta_dependent)
     c.ncell, c.nbucket, c.maxscan = int(mt.ncell), len(mt.bucket_base), int(mt.maxscan)
     c.nbeta, c.nx, c.nresc = len(mt.beta_grid), len(mt.x), len(mt.mu_resc)
+    c.realspace_from_data, c.kaiser_approximation = int(mt.from_data), int(mt.kaiser_approximation)
+    c.kaiser_coord_shift, c.niter = int(mt.kaiser_coord_shift), int(mt.niter)
     c.origin, c.upper = f64("origin", mt.origin), f64("upper", mt.upper)
     keep["bucket_base"] = np.ascontiguousarray(mt.bucket_base, dtype=np.int32)
     c.bucket_base = keep["bucket_base"].ctypes.data_as(c_int32_p)

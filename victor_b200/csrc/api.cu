@@ -8,7 +8,10 @@
 #include <vector>
 
 #include "../../include/victor_b200.h"
-#include "kernels.cuh"
+#include "k1_general.cuh"
+#include "k1_streaming.cuh"
+#include "k2_chi2.cuh"
+#include "probes.cuh"
 
 using namespace vb200;
 
@@ -89,9 +92,8 @@ struct vb200_ctx {
     std::vector<void *> owned;
     Scratch sc_params, sc_theory, sc_chi2, sc_lnl, sc_xi, sc_mult, sc_grid;
     // options
-    int opt_fast = 1, opt_nsplit = 0, opt_threads = 256, opt_ilp = 4, opt_expdeg = 6, opt_group = 0, opt_cache = 0;
-    int g0 = 0, g1 = 0;           // velocity nodes [g0, g1) whose weights alternate wA, wB
-    double wA = 0.0, wB = 0.0;
+    int opt_fast = 1, opt_nsplit = 0, opt_threads = 256, opt_ilp = 4, opt_expdeg = 5;
+    bool tuned = false;           // streaming + isotropic xi + model coordinates: the tuned kernel applies
     long long launches = 0;
     size_t k1_smem_limit = 0;
     double xw[2 * kMaxNx] = {0};  // host copy of x_m | w_m for the kernel-parameter table
@@ -118,11 +120,9 @@ int check_model(const vb200_model_tables *m) {
     if (m->n_ell < 1 || m->n_ell > VB200_MAX_POLES) return fail(VB200_EINVAL, "model tables: bad n_ell");
     if (m->nx > kMaxNx) return fail(VB200_EUNSUPPORTED, "more than 128 velocity nodes");
     if (m->ncell > 32767) return fail(VB200_EUNSUPPORTED, "too many spline cells");
-    if (m->rsd_model != VB200_RSD_STREAMING)
-        return fail(VB200_EUNSUPPORTED, "only rsd_model 'streaming' has a kernel in this build");
-    if (m->n_ell != 1)
-        return fail(VB200_EUNSUPPORTED, "anisotropic real-space input (assume_isotropic: False) has no kernel "
-                                        "in this build");
+    if (m->rsd_model < VB200_RSD_STREAMING || m->rsd_model > VB200_RSD_EUCLID)
+        return fail(VB200_EINVAL, "model tables: unknown rsd_model");
+    if (m->niter < 0 || m->niter > 64) return fail(VB200_EINVAL, "model tables: bad niter");
     if (!(m->inv_h > 0.0) || !(m->iaH > 0.0) || !(m->template_sigma8 > 0.0))
         return fail(VB200_EINVAL, "model tables: bad scalars");
     return VB200_OK;
@@ -130,29 +130,23 @@ int check_model(const vb200_model_tables *m) {
 
 typedef void (*k1_fn)(const K1Args);
 
-// Kernel variants that exist in this build.  The tuned path is <fast, U = 4>; the others are
-// kept for parity tests (libm math) and for measurement (ILP, exp degree, weight grouping).
-k1_fn pick_k1(bool fast, bool flags, int ilp, int expdeg, bool group, int cache = 0) {
-    if (fast && !flags && cache == 1) {
-        if (ilp == 1) return k_multipoles<K1Cfg<true, false, 1, 5, false, true>>;
-        if (ilp == 2) return k_multipoles<K1Cfg<true, false, 2, 5, false, true>>;
-        return k_multipoles<K1Cfg<true, false, 4, 5, false, true>>;
-    }
-    if (fast && !flags && cache >= 2) {  // same, compiled for 4 resident blocks (64 registers)
-        if (ilp == 1) return k_multipoles<K1Cfg<true, false, 1, 5, false, true, 4>>;
-        if (ilp == 2) return k_multipoles<K1Cfg<true, false, 2, 5, false, true, 4>>;
-        return k_multipoles<K1Cfg<true, false, 4, 5, false, true, 4>>;
-    }
-    if (!fast) return flags ? k_multipoles<K1Cfg<false, true, 1>> : k_multipoles<K1Cfg<false, false, 1>>;
+// Tuned streaming kernel variants in this build.  The default is <fast, U = 4, degree-5 exp>; the
+// others exist for parity tests (libm math) and for measurement (ILP, exp degree).
+k1_fn pick_k1(bool fast, bool flags, int ilp, int expdeg) {
+    if (!fast) return flags ? k_multipoles<K1Cfg<false, true, 1, 6>> : k_multipoles<K1Cfg<false, false, 1, 6>>;
     if (flags) {
-        if (ilp < 4) return k_multipoles<K1Cfg<true, true, 1>>;
+        if (ilp < 4) return k_multipoles<K1Cfg<true, true, 1, 5>>;
         return expdeg == 5 ? k_multipoles<K1Cfg<true, true, 4, 5>> : k_multipoles<K1Cfg<true, true, 4, 6>>;
     }
-    if (ilp == 1) return k_multipoles<K1Cfg<true, false, 1>>;
-    if (ilp == 2) return k_multipoles<K1Cfg<true, false, 2>>;
-    if (group)
-        return expdeg == 5 ? k_multipoles<K1Cfg<true, false, 4, 5, true>> : k_multipoles<K1Cfg<true, false, 4, 6, true>>;
+    if (ilp == 1) return k_multipoles<K1Cfg<true, false, 1, 5>>;
+    if (ilp == 2) return k_multipoles<K1Cfg<true, false, 2, 5>>;
     return expdeg == 5 ? k_multipoles<K1Cfg<true, false, 4, 5>> : k_multipoles<K1Cfg<true, false, 4, 6>>;
+}
+
+k1_fn pick_general(int rsd_model) {
+    if (rsd_model == kRsdStreaming) return k_multipoles_general<kRsdStreaming>;
+    if (rsd_model == kRsdDispersion) return k_multipoles_general<kRsdDispersion>;
+    return k_multipoles_general<kRsdKaiser>;
 }
 
 int launch_k1(vb200_ctx *c, const double *d_params, long long n, const double *d_s, int ns,
@@ -172,7 +166,8 @@ int launch_k1(vb200_ctx *c, const double *d_params, long long n, const double *d
     const int npairs = jper * nmu;
     int threads = std::min(c->opt_threads, ((npairs + 31) / 32) * 32);
     threads = std::max(32, std::min(threads, 256));
-    const size_t smem = k1_smem_bytes(c->md.ncell, jper, nmu, c->md.nbucket);
+    const size_t smem = c->tuned ? k1_smem_bytes(c->md.ncell, jper, nmu, c->md.nbucket)
+                                 : k1g_smem_bytes(c->md.ncell, jper, nmu, c->md.nbucket);
     if (smem > c->k1_smem_limit)
         return fail(VB200_EUNSUPPORTED, "grids too large for one block's shared memory (reduce len(s) * len(mu))");
     const long long blocks = n * nsplit;
@@ -194,12 +189,8 @@ int launch_k1(vb200_ctx *c, const double *d_params, long long n, const double *d
     a.xi_out = d_xi;
     a.mult_out = d_mult;
     memcpy(a.xw, c->xw, sizeof(a.xw));
-    a.g0 = c->g0;
-    a.g1 = c->g1;
-    a.wA = c->wA;
-    a.wB = c->wB;
-    const bool group = c->opt_group && c->g1 - c->g0 >= 8;
-    auto fn = pick_k1(c->opt_fast != 0, c->has_flags, c->opt_ilp, c->opt_expdeg, group, c->opt_cache);
+    auto fn = c->tuned ? pick_k1(c->opt_fast != 0, c->has_flags, c->opt_ilp, c->opt_expdeg)
+                       : pick_general(c->md.rsd_model);
     void *kargs[] = {(void *)&a};
     CK(cudaLaunchKernel((const void *)fn, dim3((unsigned)blocks), dim3(threads), kargs, smem, st));
     CK(cudaGetLastError());
@@ -223,35 +214,6 @@ int launch_k2(vb200_ctx *c, const double *d_params, const double *d_theory, long
     CK(cudaGetLastError());
     c->launches++;
     return VB200_OK;
-}
-
-// Longest run [g0, g1) of velocity nodes whose weights alternate between two values (the interior
-// of a composite Simpson rule: 4/3, 2/3, 4/3, ... times h); its length is cut to a multiple of 4.
-// Weights within 4 ulp of each other count as equal and their mean is used.
-void find_weight_groups(vb200_ctx *c, const double *w, int nx) {
-    auto same = [](double a, double b) { return std::fabs(a - b) <= 1e-15 * std::fabs(a + b); };
-    int best0 = 0, best1 = 0;
-    for (int s0 = 0; s0 + 3 < nx; ++s0) {
-        int e = s0 + 2;
-        while (e < nx && same(w[e], w[e - 2])) ++e;
-        if (e - s0 > best1 - best0) {
-            best0 = s0;
-            best1 = e;
-        }
-    }
-    best1 = best0 + ((best1 - best0) / 4) * 4;
-    c->g0 = best0;
-    c->g1 = best1;
-    if (best1 > best0) {
-        double sa = 0.0, sb = 0.0;
-        for (int i = best0; i < best1; i += 2) {
-            sa += w[i];
-            sb += w[i + 1];
-        }
-        const int half = (best1 - best0) / 2;
-        c->wA = sa / half;
-        c->wB = sb / half;
-    }
 }
 
 void fill_exp_table(double *t) {
@@ -336,6 +298,12 @@ int vb200_create(const vb200_model_tables *m, const vb200_fit_tables *f, int dev
     d.nbeta = m->nbeta;
     d.nx = m->nx;
     d.nresc = m->nresc;
+    d.from_data = m->realspace_from_data;
+    d.kaiser_approx = m->kaiser_approximation;
+    d.kaiser_shift = m->kaiser_coord_shift;
+    d.niter = m->niter;
+    for (int i = 0; i < kMaxPoles; ++i) d.ells[i] = m->ells[i];
+    c->tuned = (m->rsd_model == VB200_RSD_STREAMING && m->n_ell == 1 && !m->realspace_from_data);
     const size_t nc4 = (size_t)m->ncell * 4;
     if ((rc = upload(c, m->origin, (size_t)m->ncell, &d.origin))) return bail(rc);
     if ((rc = upload(c, m->upper, (size_t)m->ncell, &d.upper))) return bail(rc);
@@ -357,7 +325,6 @@ int vb200_create(const vb200_model_tables *m, const vb200_fit_tables *f, int dev
         c->xw[i] = m->x[i];
         c->xw[kMaxNx + i] = m->wx[i];
     }
-    find_weight_groups(c, m->wx, m->nx);
 
     if (f) {
         if (f->ns < 1 || f->npoles < 1 || f->npoles > VB200_MAX_POLES || f->nmu < 2 || f->nbeta_ccf < 2 ||
@@ -400,10 +367,11 @@ int vb200_create(const vb200_model_tables *m, const vb200_fit_tables *f, int dev
 
     // allow the large dynamic shared memory carve-out (dense mu grids stage up to ~200 KB)
     c->k1_smem_limit = std::min<size_t>((size_t)prop.sharedMemPerBlockOptin, (size_t)200 * 1024);
-    for (int v = 0; v < 256; ++v) {
-        const int ilp = 1 << (v & 3);  // 1, 2, 4, (8 -> 4)
-        cudaError_t e = cudaFuncSetAttribute((const void *)pick_k1(v & 4, v & 8, ilp, (v & 16) ? 5 : 6, v & 32, v >> 6),
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k1_smem_limit);
+    std::vector<const void *> fns;
+    for (int v = 0; v < 32; ++v) fns.push_back((const void *)pick_k1(v & 1, v & 2, 1 << ((v >> 2) & 3), (v & 16) ? 5 : 6));
+    for (int r = 0; r < 3; ++r) fns.push_back((const void *)pick_general(r));
+    for (const void *fn : fns) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k1_smem_limit);
         if (e != cudaSuccess)
             return bail(fail(VB200_ECUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)));
     }
@@ -419,9 +387,7 @@ int vb200_set_option(vb200_ctx *c, const char *key, int64_t value) {
     else if (!strcmp(key, "exp_degree")) {
         if (value != 5 && value != 6) return fail(VB200_EINVAL, "exp_degree must be 5 or 6");
         c->opt_expdeg = (int)value;
-    } else if (!strcmp(key, "group_weights")) c->opt_group = value ? 1 : 0;
-    else if (!strcmp(key, "cell_cache")) c->opt_cache = (int)std::max<int64_t>(0, std::min<int64_t>(2, value));
-    else if (!strcmp(key, "threads")) {
+    } else if (!strcmp(key, "threads")) {
         if (value < 32 || value > 256 || value % 32) return fail(VB200_EINVAL, "threads must be 32..256, multiple of 32");
         c->opt_threads = (int)value;
     } else

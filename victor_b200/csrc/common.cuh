@@ -1,0 +1,260 @@
+// Shared definitions of the victor_b200 CUDA kernels (sm_100a): device-side table views,
+// kernel argument structs and the hand-rolled FP64 math.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace vb200 {
+
+constexpr int kMaxPoles = 3;
+constexpr int kExpTab = 32;
+constexpr int kMaxNx = 128;       // velocity nodes that fit in the kernel-parameter table
+constexpr int kBucketFlag = (int)0x80000000;
+
+enum { kRsdStreaming = 0, kRsdDispersion = 1, kRsdKaiser = 2, kRsdEuclid = 3 };
+
+struct ModelDev {
+    double iaH, s8t, beta_fixed, inv_h;
+    int vel_indep_AP, rsd_model, n_ell, beta_dependent;
+    int ncell, nbucket, maxscan, nbeta, nx, nresc;
+    int from_data, kaiser_approx, kaiser_shift, niter;
+    int ells[kMaxPoles];
+    const double *origin, *upper;
+    const int *bucket_base;
+    const double *beta_grid, *xi_tab, *v0, *d0, *sv, *x, *wx, *mu_resc, *w_resc;
+    const double *exp_tab;  // [kExpTab] 2^(j/32)
+};
+
+struct K1Args {
+    ModelDev m;
+    const double *params;
+    long long n;
+    const double *s, *mu, *sqmu, *wmu;  // [ns], [nmu], [nmu] sqrt(1-mu^2), [L][nmu]
+    int ns, nmu, L;
+    int jper, nsplit;
+    double *xi_out;    // [n][nmu][ns] or null
+    double *mult_out;  // [n][L][ns]  or null
+    double xw[2 * kMaxNx];  // x_m then Simpson weight / sqrt(2 pi): read through the constant bank
+};
+
+struct FitDev {
+    int p, data_beta_dependent, nbeta_ccf, cov_fixed, nbeta_cov, like_kind, use_logdet;
+    double like_a, like_nm1;
+    const double *beta_ccf, *data_tab, *beta_cov, *icov, *logdet, *lam;
+};
+
+struct K2Args {
+    FitDev f;
+    const double *params;
+    const double *theory;  // [n][p]
+    long long n;
+    double *chi2, *lnl;    // either may be null
+};
+
+// ---------------------------------------------------------------------------------------
+// hand-rolled FP64 math: MUFU seed + polynomial refinement, no slow paths (arguments on this
+// path are positive, finite and far from the denormal range; NaN still propagates).
+// Measured on B200 (profiles/r01e_probe_pipes.json): both MUFU seeds are good to 2^-20.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double fast_rsqrt(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    // one Halley step: y (1 + e/2 + 3 e^2 / 8), e = 1 - a y^2  (cubic convergence)
+    double ay = a * y;
+    double e = fma(-ay, y, 1.0);
+    double p = fma(0.375, e, 0.5);
+    double pe = p * e;
+    return fma(y, pe, y);
+}
+
+template <bool kFast>
+__device__ __forceinline__ void radius(double u2, double rp, double &u, double &mur) {
+    if (kFast) {
+        double y = fast_rsqrt(u2);
+        u = u2 * y;
+        mur = rp * y;
+    } else {
+        u = sqrt(u2);
+        mur = rp / u;
+    }
+}
+
+// 1/a: MUFU seed (rel. error e ~ 2^-20) then y (1 + e + e^2): cubic convergence
+__device__ __forceinline__ double rcp_cubic(double a) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double e = fma(-a, y, 1.0);
+    return fma(y, fma(e, e, e), y);
+}
+
+__device__ __forceinline__ double horner3(const double *c, double t) {
+    return fma(fma(fma(c[3], t, c[2]), t, c[1]), t, c[0]);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// interval k with grid[k] <= b < grid[k+1], clamped to [0, n-2] (PCHIP extrapolates with its
+// end polynomials: scipy PchipInterpolator(extrapolate=True), ccf_model.py:326, ccf_fit.py:193)
+__device__ __forceinline__ int beta_interval(const double *grid, int n, double b) {
+    int k = 0;
+    for (int i = 1; i < n - 1; ++i) k += (b >= grid[i]) ? 1 : 0;
+    return k;
+}
+
+__device__ __forceinline__ double2 lds_f64x2(unsigned addr) {
+    double2 v;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int lds_s32(unsigned addr) {
+    int v;
+    asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// exp(r ln2/32) on |r| <= 1/2 -- coefficients in constant memory so that the FP64 pipe reads
+// them as c[bank][offset] operands (a DFMA with a constant operand issues every 2.0 cycles,
+// with three register operands every 2.2: profiles/r01e_probe_mix.txt).
+//   kExpPoly  : degree-6 Taylor (truncation 3e-18)
+//   kExpPoly5 : degree-5 economised fit at Chebyshev nodes (max relative error 1.4e-16; from a
+//               60-digit mpmath solve), one FMA less
+__constant__ double kExpPoly[6] = {2.166084939249829e-02, 2.3459619820224677e-04, 1.6938509724371819e-06,
+                                   9.172562701824643e-09, 3.9737099845494154e-11, 1.4345655584131932e-13};
+__constant__ double kExpPoly5[5] = {2.166084939249829e-02, 2.345961981994449e-04, 1.6938509724285119e-06,
+                                    9.172607532092245e-09, 3.9737238568525983e-11};
+
+// exp(-z2/2) from the 2^(j/32) table at 32-bit shared address `etab_s`
+template <int kDeg>
+__device__ __forceinline__ double gauss_tab(double z2, unsigned etab_s) {
+    const double kMagic = 6755399441055744.0;   // 1.5 * 2^52
+    const double kScale = -23.083120654223414;   // -16 log2(e)
+    const double tn = fma(z2, kScale, kMagic);
+    const int ni = __double2loint(tn);
+    const double nf = tn - kMagic;
+    const double r = fma(z2, kScale, -nf);
+    double p;
+    if (kDeg == 6) {
+        p = fma(kExpPoly[5], r, kExpPoly[4]);
+        p = fma(p, r, kExpPoly[3]);
+        p = fma(p, r, kExpPoly[2]);
+        p = fma(p, r, kExpPoly[1]);
+        p = fma(p, r, kExpPoly[0]);
+    } else {
+        p = fma(kExpPoly5[4], r, kExpPoly5[3]);
+        p = fma(p, r, kExpPoly5[2]);
+        p = fma(p, r, kExpPoly5[1]);
+        p = fma(p, r, kExpPoly5[0]);
+    }
+    p = fma(p, r, 1.0);
+    const int n = max(ni >> 5, -1000);
+    double t = lds_f64(etab_s + ((ni & (kExpTab - 1)) << 3));
+    t = __hiloint2double(__double2hiint(t) + (n << 20), __double2loint(t));
+    return p * t;
+}
+
+// keep a value in a register: the compiler cannot re-derive the result of a volatile asm, so it
+// stops re-materialising loop invariants (shared-window base, reciprocal spacing) inside the loop
+__device__ __forceinline__ unsigned pin_u32(unsigned v) {
+    unsigned r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+__device__ __forceinline__ double pin_f64(double v) {
+    double r;
+    asm volatile("mov.f64 %0, %1;" : "=d"(r) : "d"(v));
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------
+// pieces shared by both K1 kernels
+// ---------------------------------------------------------------------------------------
+struct RowScalars {
+    double f;        // template rescaling factor (ccf_model.py:606-613)
+    double sperp_f;  // aperp / f
+    double spar_f;   // apar / f
+    double kappa;    // sigma_v iaH apar / f : displacement in u-units per unit x
+    double B;        // A_v / sigma_v, A_v = -(fs8 / s8_t) / (3 iaH apar)      (:419, 435, 449)
+    double G;        // iaH apar A_v / f = -(fs8 / s8_t) / (3 f)   (dispersion / kaiser terms)
+    double apar, aperp;
+};
+
+// warp 0 of the block computes the scalars of parameter row `pr` into shared `scal[8]`
+__device__ __forceinline__ void row_scalars_to_shared(const ModelDev &m, const double *pr, double *scal, int tid) {
+    const double fs8 = pr[0], sigv = pr[2], aperp = pr[3], apar = pr[4], astar = pr[5];
+    if (tid < 32) {
+        const double eps = aperp / apar;
+        double f;
+        if (m.vel_indep_AP) {
+            f = astar;
+        } else {
+            double part = 0.0;
+            for (int i = tid; i < m.nresc; i += 32) {
+                double mm = m.mu_resc[i];
+                part += m.w_resc[i] * (apar * sqrt(1.0 + (1.0 - mm * mm) * (eps * eps - 1.0)));
+            }
+            f = warp_sum(part);
+        }
+        if (tid == 0) {
+            const double iaHt = m.iaH * apar;
+            const double g = fs8 / m.s8t;
+            const double Av = -g / (3.0 * iaHt);
+            scal[0] = f;
+            scal[1] = aperp / f;
+            scal[2] = apar / f;
+            scal[3] = sigv * iaHt / f;
+            scal[4] = Av / sigv;
+            scal[5] = -g / (3.0 * f);
+            scal[6] = apar;
+            scal[7] = aperp;
+        }
+    }
+}
+
+// xi(s_j, mu_k) staged in shared memory -> outputs: the xi block itself and / or its projection
+// onto L <= 3 multipoles (one warp per s_j, lane-strided FMAs + shuffle reduction).
+// ccf_model.py:824-825, utils.py:45-56, ccf_model.py:856-858.
+__device__ __forceinline__ void write_outputs(const K1Args &a, const double *stage, long long row, int j0, int jn,
+                                              int tid, int nthr) {
+    const int nmu = a.nmu;
+    const int npairs = jn * nmu;
+    if (a.xi_out) {
+        double *xo = a.xi_out + (size_t)row * nmu * a.ns;
+        for (int pidx = tid; pidx < npairs; pidx += nthr) {
+            const int jl = pidx / nmu, k = pidx - jl * nmu;
+            xo[(size_t)k * a.ns + j0 + jl] = stage[pidx];
+        }
+    }
+    if (a.mult_out) {
+        const int warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
+        double *mo = a.mult_out + (size_t)row * a.L * a.ns;
+        for (int jl = warp; jl < jn; jl += nwarp) {
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+            for (int k = lane; k < nmu; k += 32) {
+                const double v = stage[jl * nmu + k];
+                s0 = fma(a.wmu[k], v, s0);
+                if (a.L > 1) s1 = fma(a.wmu[nmu + k], v, s1);
+                if (a.L > 2) s2 = fma(a.wmu[2 * nmu + k], v, s2);
+            }
+            s0 = warp_sum(s0);
+            if (a.L > 1) s1 = warp_sum(s1);
+            if (a.L > 2) s2 = warp_sum(s2);
+            if (lane == 0) {
+                mo[j0 + jl] = s0;
+                if (a.L > 1) mo[a.ns + j0 + jl] = s1;
+                if (a.L > 2) mo[2 * a.ns + j0 + jl] = s2;
+            }
+        }
+    }
+}
+
+}  // namespace vb200

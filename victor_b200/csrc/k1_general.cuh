@@ -1,0 +1,234 @@
+// K1 (general): every model option of the path that the tuned streaming kernel does not cover --
+//   rsd_model 'dispersion'                      victor/ccf_model.py:659-671
+//   rsd_model 'kaiser' / 'euclid_special'       victor/ccf_model.py:692-741
+//   anisotropic real-space input                victor/ccf_model.py:684-687  (assume_isotropic: False)
+//   real-space ccf measured from data           victor/ccf_model.py:675-679  (realspace_ccf.from_data)
+// and the streaming model combined with the last two.  Same tiling as the tuned kernel (one block
+// per parameter row x s-range, one thread per (s_j, mu_k) pair, velocity nodes in registers), plain
+// CUDA libm arithmetic (sqrt, divide, exp): these variants are written for parity first.
+#pragma once
+#include "common.cuh"
+
+namespace vb200 {
+
+// per-cell record of the general kernel:
+//   xi_l cubics (3 x 4, unused ones zero) | V0 (4) | D0 (4) | SV (4) | origin | pad
+constexpr int kRecG = 26;
+constexpr int kGXi = 0, kGV0 = 12, kGD0 = 16, kGSV = 20, kGOrg = 24;
+
+__host__ __device__ inline size_t k1g_smem_bytes(int ncell, int jper, int nmu, int nbucket) {
+    size_t d = (size_t)ncell * (kRecG + 1) + (size_t)jper * nmu + 8;
+    return d * sizeof(double) + (size_t)nbucket * sizeof(int);
+}
+
+struct GenCtx {
+    const double *rec, *upper;
+    const int *bbase;
+    int nbucket, maxscan, n_ell;
+    int ell1, ell2;
+    double inv_h;
+};
+
+// cell of coordinate u and the local coordinate inside it; below the first knot t = 0 (every
+// spline is its boundary value there, FITPACK ext=3)
+__device__ __forceinline__ const double *locate(const GenCtx &g, double u, double &t) {
+    const double bf = floor(u * g.inv_h);
+    int b = 0;
+    if (bf >= 0.0) b = (bf < (double)(g.nbucket - 1)) ? (int)bf : g.nbucket - 1;   // NaN -> bucket 0
+    int cell = g.bbase[b];
+    if (cell < 0) {
+        cell &= ~kBucketFlag;
+        for (int sc = 0; sc < g.maxscan; ++sc) cell += (u >= g.upper[cell]) ? 1 : 0;
+    }
+    const double *r = g.rec + cell * kRecG;
+    const double tt = u - r[kGOrg];
+    t = (tt < 0.0) ? 0.0 : tt;      // NaN stays NaN
+    return r;
+}
+
+__device__ __forceinline__ double legendre_even(int ell, double x) {
+    // Horner forms of scipy.special.legendre(ell) (ccf_model.py:683, 687)
+    const double x2 = x * x;
+    if (ell == 0) return 1.0;
+    if (ell == 2) return 1.5 * x2 - 0.5;
+    return (4.375 * x2 - 3.75) * x2 + 0.375;
+}
+
+// real-space xi at (u, mu_r): sum_l xi_l(u) L_l(mu_r)                 ccf_model.py:681-687
+__device__ __forceinline__ double xi_real(const GenCtx &g, const double *r, double t, double mur) {
+    double xi = horner3(r + kGXi, t);
+    if (g.n_ell > 1) xi += horner3(r + kGXi + 4, t) * legendre_even(g.ell1, mur);
+    if (g.n_ell > 2) xi += horner3(r + kGXi + 8, t) * legendre_even(g.ell2, mur);
+    return xi;
+}
+
+template <int kModel>
+__global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constant__ K1Args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const ModelDev &m = a.m;
+    const int ncell = m.ncell, nx = m.nx;
+    double *rec = reinterpret_cast<double *>(smem_raw);
+    double *stage = rec + (size_t)ncell * kRecG;
+    double *scal = stage + (size_t)a.jper * a.nmu;
+    double *upper = scal + 8;
+    int *bbase = reinterpret_cast<int *>(upper + ncell);
+
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const long long row = blockIdx.x / a.nsplit;
+    const int split = blockIdx.x - (int)(row * a.nsplit);
+    const int j0 = split * a.jper;
+    const int jn = min(a.jper, a.ns - j0);
+    if (jn <= 0) return;
+
+    const double *pr = a.params + row * 8;
+    const double beta = m.beta_dependent ? pr[1] : m.beta_fixed;
+    const double Mk = pr[6], Qk = pr[7];
+
+    row_scalars_to_shared(m, pr, scal, tid);
+    for (int i = tid; i < ncell; i += nthr) upper[i] = m.upper[i];
+    for (int i = tid; i < m.nbucket; i += nthr) bbase[i] = m.bucket_base[i];
+    {
+        int kb = 0;
+        double tb = 0.0;
+        if (m.beta_dependent) {
+            kb = beta_interval(m.beta_grid, m.nbeta, beta);
+            tb = beta - m.beta_grid[kb];
+        }
+        const int per = ncell * 4;
+        const size_t ell_stride = (size_t)(m.nbeta - 1) * 4 * per;
+        for (int i = tid; i < per; i += nthr) {
+            const int cell = i >> 2, c = i & 3;
+            double *r = rec + cell * kRecG;
+            for (int l = 0; l < kMaxPoles; ++l) {
+                double v = 0.0;
+                if (l < m.n_ell) {
+                    const double *tab = m.xi_tab + l * ell_stride + (size_t)kb * 4 * per;
+                    v = fma(fma(fma(tab[3 * per + i], tb, tab[2 * per + i]), tb, tab[per + i]), tb, tab[i]);
+                }
+                r[kGXi + 4 * l + c] = v;
+            }
+            r[kGV0 + c] = m.v0[i];
+            r[kGD0 + c] = m.d0[i];
+            r[kGSV + c] = m.sv[i];
+            if (c == 0) {
+                r[kGOrg] = m.origin[cell];
+                r[kGOrg + 1] = 0.0;
+            }
+        }
+    }
+    __syncthreads();
+
+    const double f = scal[0], sperp_f = scal[1], spar_f = scal[2], kappa = scal[3], B = scal[4], G = scal[5];
+    const double apar = scal[6];
+    GenCtx g;
+    g.rec = rec;
+    g.upper = upper;
+    g.bbase = bbase;
+    g.nbucket = m.nbucket;
+    g.maxscan = m.maxscan;
+    g.n_ell = m.n_ell;
+    g.ell1 = m.ells[1];
+    g.ell2 = m.ells[2];
+    g.inv_h = m.inv_h;
+    const int nmu = a.nmu;
+    const int npairs = jn * nmu;
+    const double f_over_apar = f / apar;
+
+    for (int pidx = tid; pidx < npairs; pidx += nthr) {
+        const int jl = pidx / nmu, k = pidx - jl * nmu;
+        const double sj = a.s[j0 + jl];
+        const double Sperp = sj * a.sqmu[k] * sperp_f;
+        const double Spar = sj * a.mu[k] * spar_f;
+        const double Sperp2 = Sperp * Sperp;
+        const double rt_data = sj * a.sqmu[k];   // s_perp / aperp in real units (from_data, :676)
+        double result;
+
+        // real-space xi for a point with (u-unit) line-of-sight separation rp
+        auto xi_at = [&](double rp, double u, double mur, const double *rcell, double t) {
+            if (!m.from_data) return xi_real(g, rcell, t, mur);
+            const double rpd = rp * f_over_apar;                       // r_par / apar      (:675)
+            const double rd = sqrt(rpd * rpd + rt_data * rt_data);     // (:677)
+            double td;
+            const double *rc = locate(g, rd, td);
+            return xi_real(g, rc, td, rpd / rd);                       // (:678-687)
+        };
+
+        if (kModel == kRsdStreaming) {
+            double acc = 0.0;
+            for (int mi = 0; mi < nx; ++mi) {
+                const double xm = a.xw[mi], wm = a.xw[kMaxNx + mi];
+                const double rp = Spar - xm * kappa;                   // :648
+                const double u = sqrt(Sperp2 + rp * rp);               // :651
+                const double mur = rp / u;                             // :652
+                double t;
+                const double *rc = locate(g, u, t);
+                const double sv = horner3(rc + kGSV, t);               // :654-655
+                const double z = (xm - B * horner3(rc + kGV0, t) * mur) / sv;   // :656
+                const double xi = xi_at(rp, u, mur, rc, t);
+                acc += wm * (1.0 + xi) * exp(-0.5 * z * z) / sv;       // :690
+            }
+            result = acc - 1.0;
+        } else if (kModel == kRsdDispersion) {
+            // ccf_model.py:659-671
+            const double Strue = sqrt(Sperp2 + Spar * Spar);
+            double t0;
+            const double *r0 = locate(g, Strue, t0);
+            const double first = 1.0 + G * horner3(r0 + kGV0, t0) / Strue;
+            double acc = 0.0;
+            for (int mi = 0; mi < nx; ++mi) {
+                const double xm = a.xw[mi], wm = a.xw[kMaxNx + mi];
+                const double num = Spar - xm * kappa;
+                double rp = num / first;
+                double u, t;
+                const double *rc;
+                for (int it = 0; it < m.niter; ++it) {
+                    u = sqrt(Sperp2 + rp * rp);
+                    rc = locate(g, u, t);
+                    rp = num / (1.0 + G * horner3(rc + kGV0, t) / u);
+                }
+                u = sqrt(Sperp2 + rp * rp);
+                const double mur = rp / u;
+                rc = locate(g, u, t);
+                const double sv = horner3(rc + kGSV, t);
+                const double v0u = horner3(rc + kGV0, t) / u;
+                const double jac = 1.0 / (1.0 + G * v0u + G * mur * mur * (horner3(rc + kGD0, t) - v0u));
+                const double z = xm / sv;
+                const double xi = xi_at(rp, u, mur, rc, t);
+                acc += wm * (1.0 + xi) * jac * exp(-0.5 * z * z) / sv;
+            }
+            result = acc - 1.0;
+        } else {
+            // kaiser / euclid_special: ccf_model.py:692-741
+            const double MG = Mk * G;
+            double rp = Spar;
+            double u, t;
+            const double *rc;
+            if (m.kaiser_shift) {
+                const double Strue = sqrt(Sperp2 + Spar * Spar);
+                rc = locate(g, Strue, t);
+                rp = Spar / (1.0 + MG * horner3(rc + kGV0, t) / Strue);
+                for (int it = 0; it < m.niter; ++it) {
+                    u = sqrt(Sperp2 + rp * rp);
+                    rc = locate(g, u, t);
+                    rp = Spar / (1.0 + MG * horner3(rc + kGV0, t) / u);
+                }
+            }
+            u = sqrt(Sperp2 + rp * rp);
+            const double mur = rp / u;
+            rc = locate(g, u, t);
+            const double v0u = horner3(rc + kGV0, t) / u;
+            const double ca = (m.rsd_model == kRsdEuclid) ? 3.0 : 1.0, cb = (m.rsd_model == kRsdEuclid) ? 2.0 : 1.0;
+            const double J = ca * MG * v0u + cb * MG * Qk * mur * mur * (horner3(rc + kGD0, t) - v0u);
+            const double xi = xi_at(rp, u, mur, rc, t);
+            if (m.rsd_model == kRsdEuclid || m.kaiser_approx)
+                result = Mk * xi - J;
+            else
+                result = (1.0 + Mk * xi) / (1.0 + J) - 1.0;
+        }
+        stage[pidx] = result;
+    }
+    __syncthreads();
+    write_outputs(a, stage, row, j0, jn, tid, nthr);
+}
+
+}  // namespace vb200

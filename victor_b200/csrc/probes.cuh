@@ -1,0 +1,148 @@
+// Self-test and measurement kernels: hand-rolled math against the host, FP64 issue-rate probes.
+#pragma once
+#include "common.cuh"
+
+namespace vb200 {
+
+// ---------------------------------------------------------------------------------------
+// math self-test kernel
+// ---------------------------------------------------------------------------------------
+__global__ void k_math_selftest(const double *x, long long n, const double *etab, double *out) {
+    __shared__ double tab[kExpTab];
+    if (threadIdx.x < kExpTab) tab[threadIdx.x] = etab[threadIdx.x];
+    __syncthreads();
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = x[i];
+    out[i] = gauss_tab<6>(v, (unsigned)__cvta_generic_to_shared(tab));   // exp(-v/2)
+    out[n + i] = fast_rsqrt(v);
+    out[2 * n + i] = rcp_cubic(v);
+    out[3 * n + i] = gauss_tab<5>(v, (unsigned)__cvta_generic_to_shared(tab));
+}
+
+// ---------------------------------------------------------------------------------------
+// pipe probe: which issue pipe do the FP64 <-> int/float conversions use, and how exact are the
+// MUFU seeds?  mode 0: DFMA only; 1: cvt.rmi.s32.f64 only; 2: both interleaved 1:1;
+// 3: cvt.rn.f32.f64 only; 4: DFMA + cvt.rn.f32.f64; 5: I2F (s32 -> f64) only; 6: DFMA + I2F.
+// ---------------------------------------------------------------------------------------
+template <int kMode>
+__global__ void __launch_bounds__(256) k_pipe_probe(double *out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-3 + 1.0, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3;
+    double y0 = x0 * 0.5, y1 = x1 * 0.5, y2 = x2 * 0.5, y3 = x3 * 0.5;
+    int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
+    float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            if (kMode == 0 || kMode == 2 || kMode == 4 || kMode == 6) {
+                x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            }
+            if (kMode == 1 || kMode == 2) {
+                int t0, t1, t2, t3;
+                asm volatile("cvt.rmi.s32.f64 %0, %1;" : "=r"(t0) : "d"(y0));
+                asm volatile("cvt.rmi.s32.f64 %0, %1;" : "=r"(t1) : "d"(y1));
+                asm volatile("cvt.rmi.s32.f64 %0, %1;" : "=r"(t2) : "d"(y2));
+                asm volatile("cvt.rmi.s32.f64 %0, %1;" : "=r"(t3) : "d"(y3));
+                i0 ^= t0; i1 ^= t1; i2 ^= t2; i3 ^= t3;
+                // feed the result back into the low word of the next input (integer ops only)
+                y0 = __hiloint2double(__double2hiint(y0), i0 + r); y1 = __hiloint2double(__double2hiint(y1), i1 + r);
+                y2 = __hiloint2double(__double2hiint(y2), i2 + r); y3 = __hiloint2double(__double2hiint(y3), i3 + r);
+            }
+            if (kMode == 3 || kMode == 4) {
+                float t0, t1, t2, t3;
+                asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(t0) : "d"(y0));
+                asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(t1) : "d"(y1));
+                asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(t2) : "d"(y2));
+                asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(t3) : "d"(y3));
+                f0 += t0; f1 += t1; f2 += t2; f3 += t3;
+                y0 = __hiloint2double(__double2hiint(y0), __float_as_int(f0)); y1 = __hiloint2double(__double2hiint(y1), __float_as_int(f1));
+                y2 = __hiloint2double(__double2hiint(y2), __float_as_int(f2)); y3 = __hiloint2double(__double2hiint(y3), __float_as_int(f3));
+            }
+            if (kMode == 5 || kMode == 6) {
+                double t0, t1, t2, t3;
+                asm volatile("cvt.rn.f64.s32 %0, %1;" : "=d"(t0) : "r"(i0 + r));
+                asm volatile("cvt.rn.f64.s32 %0, %1;" : "=d"(t1) : "r"(i1 + r));
+                asm volatile("cvt.rn.f64.s32 %0, %1;" : "=d"(t2) : "r"(i2 + r));
+                asm volatile("cvt.rn.f64.s32 %0, %1;" : "=d"(t3) : "r"(i3 + r));
+                i0 ^= __double2loint(t0); i1 ^= __double2loint(t1); i2 ^= __double2loint(t2); i3 ^= __double2loint(t3);
+            }
+        }
+    }
+    double s = (x0 + x1) + (x2 + x3) + (double)(i0 + i1 + i2 + i3) + (double)(f0 + f1 + f2 + f3);
+    if (s == 12345.678) out[0] = s;
+}
+
+// DFMA issue model probe: kChains independent dependent-FMA chains per thread, with kMix other
+// instructions after every DFMA (kKind 0: integer IMAD, 1: LDS.64 broadcast, 2: DMUL with a
+// constant-bank operand instead of the plain DFMA).  128 threads per block = 1 warp per SMSP.
+template <int kChains, int kMix, int kKind>
+__global__ void __launch_bounds__(128) k_mix_probe(double *out, int iters, double a, double b, int ia) {
+    __shared__ double sh[64];
+    if (threadIdx.x < 64) sh[threadIdx.x] = 1.0 + threadIdx.x * 1e-9;
+    __syncthreads();
+    double x[kChains];
+    int n[kChains];
+    double acc = 0.0;
+#pragma unroll
+    for (int c = 0; c < kChains; ++c) {
+        x[c] = threadIdx.x * 1e-3 + c;
+        n[c] = threadIdx.x + c;
+    }
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(sh);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int c = 0; c < kChains; ++c) {
+                if (kKind == 2) x[c] = x[c] * kExpPoly[0] + b; else x[c] = fma(x[c], a, b);
+#pragma unroll
+                for (int k = 0; k < kMix; ++k) {
+                    if (kKind == 1) {
+                        n[c] += __double2loint(lds_f64(sbase + ((n[c] & 7) << 3))) + ia;
+                    } else {
+                        asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(n[c]) : "r"(ia), "r"(k));
+                    }
+                }
+            }
+        }
+    }
+    double s = acc;
+    int t = 0;
+#pragma unroll
+    for (int c = 0; c < kChains; ++c) {
+        s += x[c];
+        t += n[c];
+    }
+    if (s == 12345.678 || t == 123456789) out[0] = s + t;
+}
+
+// raw MUFU seeds (no refinement): out[0..n) = rsqrt.approx(x), out[n..2n) = rcp.approx(x)
+__global__ void k_seed_probe(const double *x, long long n, double *out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double y, q;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x[i]));
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(x[i]));
+    out[i] = y;
+    out[n + i] = q;
+}
+
+// ---------------------------------------------------------------------------------------
+// FP64 issue-rate probe: 8 independent DFMA chains per thread (roofline denominator measured
+// on the box the bench runs on; MEASURED_PEAKS.json has no FP64 figure)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
+           x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 12345.678) out[0] = s;  // keep the chains alive
+}
+
+}  // namespace vb200

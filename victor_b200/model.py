@@ -260,7 +260,8 @@ class CCFModel:
         from .engine import Engine
         key = (opts["rsd_model"], bool(opts["assume_isotropic"]), bool(opts["velocity_independent_of_AP"]),
                opts["matter_model"], opts["mean_model"], bool(opts["empirical_corr"]),
-               bool(opts["realspace_ccf_from_data"]), self._fit_key(opts) if need_fit else None)
+               bool(opts["realspace_ccf_from_data"]), bool(opts.get("kaiser_approximation", False)),
+               bool(opts.get("kaiser_coord_shift", True)), self._fit_key(opts) if need_fit else None)
         eng = self._engines.get(key)
         if eng is None:
             mt = _tables.build_model_tables(self, opts)

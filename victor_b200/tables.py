@@ -29,7 +29,7 @@ from scipy.special import legendre
 
 from .utils import InputError, trapezoid
 
-RSD_STREAMING, RSD_DISPERSION, RSD_KAISER = 0, 1, 2
+RSD_STREAMING, RSD_DISPERSION, RSD_KAISER, RSD_EUCLID = 0, 1, 2, 3
 LIKE_LINEAR, LIKE_LOG = 0, 1          # lnL = -a/2 chi2 + norm   |   lnL = -m/2 log(1 + chi2/(nm-1)) + norm
 MAX_POLES = 3
 NPAR = 8                               # fsigma8, beta, sigma_v, aperp, apar, astar, M, Q
@@ -219,6 +219,10 @@ class ModelTables:
     wx: np.ndarray                  # [nx]  Simpson weights / sqrt(2 pi)
     mu_resc: np.ndarray             # [50] nodes of the AP rescaling trapezoid
     w_resc: np.ndarray              # [50] its weights
+    from_data: bool = False         # real-space ccf measured from data: xi at (r_par/apar, s_perp/aperp)
+    kaiser_approximation: bool = False
+    kaiser_coord_shift: bool = True
+    niter: int = 5                  # fixed-point iterations of the dispersion / kaiser coordinate map
     extras: dict = field(default_factory=dict)
 
     @property
@@ -264,13 +268,9 @@ def build_model_tables(state, options, nx=50):
     if options["mean_model"] != "linear" or options["empirical_corr"]:
         raise NotImplementedError("only the 'linear' mean-velocity model without empirical correction "
                                   "has a B200 path")
-    if options["realspace_ccf_from_data"]:
-        raise NotImplementedError("realspace_ccf from_data coordinates have no B200 path yet")
-    rsd = {"streaming": RSD_STREAMING, "dispersion": RSD_DISPERSION, "kaiser": RSD_KAISER}.get(
-        options["rsd_model"])
+    rsd = {"streaming": RSD_STREAMING, "dispersion": RSD_DISPERSION, "kaiser": RSD_KAISER,
+           "euclid_special": RSD_EUCLID}.get(options["rsd_model"])
     if rsd is None:
-        if options["rsd_model"] == "euclid_special":
-            raise NotImplementedError("rsd_model 'euclid_special' has no B200 path")
         raise InputError(f"theory_xi: Unrecognised choice of model {options['rsd_model']}")
     if not state.sv_isotropic:
         raise NotImplementedError("anisotropic sigma_v(r, mu) templates have no B200 path yet")
@@ -329,7 +329,10 @@ def build_model_tables(state, options, nx=50):
         knots=knots, origin=origin, upper=upper, inv_h=inv_h,
         bucket_base=base, maxscan=maxscan, beta_grid=beta_grid,
         xi_tab=np.ascontiguousarray(xi_tab), v0=v0, d0=d0, sv=sv,
-        x=x, wx=w / np.sqrt(2 * np.pi), mu_resc=mu_resc, w_resc=w_resc)
+        x=x, wx=w / np.sqrt(2 * np.pi), mu_resc=mu_resc, w_resc=w_resc,
+        from_data=bool(options["realspace_ccf_from_data"]),
+        kaiser_approximation=bool(options.get("kaiser_approximation", False)),
+        kaiser_coord_shift=bool(options.get("kaiser_coord_shift", True)), niter=5)
 
 
 def likelihood_constants(like, p):
