@@ -42,12 +42,27 @@ METRIC = "likelihood evals/sec (multipoles+chi2), batch 64K"
 UNIT = "evals/s"
 WORKLOAD = "BOSS DR12 CMASS batched likelihood (config/boss_config.yaml), 65536 synthetic rows per GPU"
 NS, NMU, NX, L, P = 30, 100, 50, 2, 60
-# algorithmic flops per likelihood, SURVEY.md 8(d): 41 flop per quadrature point + tails
-FLOP_PER_EVAL = 41 * NS * NMU * NX + 8 * NS * NMU + 2 * L * NS * NMU + (3 * P * P + 2 * P * P + 2 * P) \
-    + (3 * P * P + P ** 3 // 3 + P) + 1500
-FLOP_K1_PER_EVAL = 41 * NS * NMU * NX + 8 * NS * NMU + 2 * L * NS * NMU + 1500
-BYTES_PER_EVAL = 64 + 8 * L * NS + 16   # parameter row in, theory + chi2 + lnL out
 FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12
+
+
+def flop_k1(ns, nmu, nx, npoles):
+    """Algorithmic flops of the multipole kernel per parameter row, SURVEY.md 8(d): 41 flop per
+    quadrature point + per-(s, mu) set-up + projection + per-row table preparation."""
+    return 41 * ns * nmu * nx + 8 * ns * nmu + 2 * npoles * ns * nmu + 1500
+
+
+def flop_k2(p):
+    """chi-square + log-det part per row."""
+    return (3 * p * p + 2 * p * p + 2 * p) + (3 * p * p + p ** 3 // 3 + p)
+
+
+FLOP_K1_PER_EVAL = flop_k1(NS, NMU, NX, L)
+FLOP_PER_EVAL = FLOP_K1_PER_EVAL + flop_k2(P)
+BYTES_PER_EVAL = 64 + 8 * L * NS + 16   # parameter row in, theory + chi2 + lnL out
+
+# BASELINE.json configs[3]: streaming model on a dense mu / velocity grid, l = 0, 2, 4 (multipoles only:
+# the data vector has no hexadecapole).  The reference hard-codes its grids; sizes per SURVEY.md 8(d).
+DENSE = {"nmu": 200, "nx": 100, "poles": [0, 2, 4]}
 
 
 def synthetic_batch(n, seed=SEED):
@@ -158,7 +173,8 @@ class ClockSampler:
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index = index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        self.index = vis.split(",")[index] if vis else index
         self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.proc = None
 
@@ -244,8 +260,7 @@ def run_gpu(args):
     for _ in range(args.warmup):
         step_device()
     barrier()
-    sampler = ClockSampler(local if "CUDA_VISIBLE_DEVICES" not in os.environ else
-                           os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local])
+    sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = eng.launch_count()
@@ -340,6 +355,177 @@ def run_gpu(args):
     return 0
 
 
+def _dist_setup():
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; victor_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return world, rank, local
+
+
+def run_dense(args):
+    """BASELINE.json configs[3]: dense-grid streaming multipoles (l = 0, 2, 4), rows sharded over the
+    GPUs.  Reported as evaluations (theory vectors) per second; no chi-square (no l = 4 data)."""
+    import torch
+    import torch.distributed as dist
+    from victor_b200 import CCFFit, tables as T
+    from victor_b200.model import params_to_rows
+
+    world, rank, local = _dist_setup()
+    dev = torch.device("cuda", local)
+    model, data = boss_blocks()
+    fit = CCFFit(model, data, device=local)
+    opts = fit._merged_options({"velocity_nodes": DENSE["nx"], "mu_nodes": DENSE["nmu"]})
+    eng = fit._engine(opts)
+    mu, W = T.mu_projection_weights(DENSE["poles"], nmu=DENSE["nmu"])
+    s = np.asarray(fit.s, dtype=np.float64)
+    n = args.batch
+    rows_host = params_to_rows(synthetic_batch(n, SEED + rank))
+    d_params = torch.from_numpy(rows_host).to(dev)
+    d_mult = torch.empty((n, len(DENSE["poles"]), len(s)), dtype=torch.float64, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def step():
+        eng.theory_ptr(d_params.data_ptr(), n, s, mu, W, None, d_mult.data_ptr(), None)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        step()
+        b.record()
+    barrier()
+    launches = eng.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    pinned = torch.from_numpy(rows_host).pin_memory().numpy()
+    fit.theory_multipole_vector_batch(s, pinned, DENSE["poles"], velocity_nodes=DENSE["nx"], mu_nodes=DENSE["nmu"])
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = fit.theory_multipole_vector_batch(s, pinned, DENSE["poles"], velocity_nodes=DENSE["nx"],
+                                                mu_nodes=DENSE["nmu"])
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+    if rank == 0:
+        evals = n * world * args.steps
+        fl = flop_k1(len(s), DENSE["nmu"], DENSE["nx"], len(DENSE["poles"]))
+        achieved = n * args.steps * fl / (total_ms * 1e-3) / 1e12
+        line = {"metric": "theory-vector evals/sec (streaming, dense grid, l=0,2,4)", "value": evals / (total_ms * 1e-3),
+                "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "BOSS tables, streaming model, dense grid (BASELINE.json configs[3])",
+                           "rows_per_gpu": n, "ns": len(s), "nmu": DENSE["nmu"], "nx": DENSE["nx"],
+                           "poles": DENSE["poles"], "l2": "flushed between timed steps (256 MiB write)",
+                           "parallelism": f"rows sharded over {world} GPU(s), no collective"},
+                "clocks": clocks,
+                "e2e": {"value": evals / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(n * 64),
+                        "d2h_bytes_per_step": int(out.nbytes), "api": "CCFModel.theory_multipole_vector_batch(host rows)"},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "fp64", "kernel": "k_multipoles<fast>", "achieved": achieved,
+                             "peak": FP64_NOMINAL_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_NOMINAL_TFLOPS,
+                             "peak_source": "nominal 148 SM x 64 lanes x 2 x 1.965 GHz", "flop_per_eval": fl,
+                             "traffic": None},
+                "cpu_baseline": None}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    fit.close()
+    return 0
+
+
+def run_mcmc(args):
+    """BASELINE.json configs[4]: one Metropolis chain per GPU, every step one n = 1 likelihood call
+    through the cobaya plugin's ``calculate``.  Reports calls per second (whole job) and latency."""
+    import torch
+    import torch.distributed as dist
+    from victor_b200.likelihoods import CCFLikelihood
+
+    world, rank, local = _dist_setup()
+    dev = torch.device("cuda", local)
+    model, data = boss_blocks()
+    like = CCFLikelihood({"model": model, "data": data, "device": local})
+    rng = np.random.default_rng(SEED + rank)
+    x = np.array([0.47, 0.37, 380.0, 1.0])
+    step_sz = np.array([0.02, 0.005, 10.0, 0.005])
+
+    def logp(v):
+        st = {}
+        like.calculate(st, fsigma8=float(v[0]), beta=float(v[1]), sigma_v=float(v[2]), epsilon=float(v[3]), alpha=1)
+        return st["logp"]
+
+    calls_per_step = 200
+    cur = logp(x)
+    lat = []
+
+    def chain(ncalls):
+        nonlocal x, cur
+        for _ in range(ncalls):
+            y = x + step_sz * rng.standard_normal(4)
+            t0 = time.perf_counter()
+            new = logp(y)
+            lat.append(time.perf_counter() - t0)
+            if np.log(rng.uniform()) < new - cur:
+                x, cur = y, new
+
+    for _ in range(args.warmup):
+        chain(calls_per_step)
+    lat.clear()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        chain(calls_per_step)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    t = torch.tensor([wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall = float(t[0])
+    if rank == 0:
+        calls = calls_per_step * args.steps * world
+        lat_us = np.array(lat) * 1e6
+        line = {"metric": "likelihood calls/sec (n=1 MCMC steps through CCFLikelihood.calculate)",
+                "value": calls / wall, "unit": "calls/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "Metropolis chain per GPU, BOSS config (BASELINE.json configs[4])",
+                           "calls_per_step": calls_per_step, "parallelism": f"{world} independent chain(s), replicas only"},
+                "latency_us": {"median": float(np.median(lat_us)), "p95": float(np.percentile(lat_us, 95)),
+                               "min": float(lat_us.min())},
+                "e2e": {"value": calls / wall, "unit": "calls/s", "h2d_bytes_per_step": calls_per_step * 64,
+                        "d2h_bytes_per_step": calls_per_step * 16, "api": "CCFLikelihood.calculate"},
+                "gpu_launches": int(2 * calls_per_step * args.steps), "final_logp": float(cur)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    like.ccf.close()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -348,9 +534,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="boss", choices=["boss", "dense", "mcmc"],
+                    help="boss: BASELINE metric (default); dense: configs[3]; mcmc: configs[4]")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "dense":
+        return run_dense(args)
+    if args.workload == "mcmc":
+        return run_mcmc(args)
     return run_gpu(args)
 
 

@@ -346,3 +346,41 @@ def test_general_kernel_agrees_with_tuned_on_streaming(fit, golden):
     assert_theory(th2, g["theory"], ns=len(fit.s))
     np.testing.assert_allclose(c2, g["chi2"], rtol=0, atol=CHI2_ATOL)
     eng.close()
+
+
+def test_dense_grid_against_restatement(fit):
+    """BASELINE configs[3]: 200 mu x 100 velocity nodes, poles 0/2/4.  The reference hard-codes its
+    grids, so the CPU reference here is the numpy table walk-through (oracle/table_emul.py), itself
+    pinned to the unmodified reference at the default sizes (tests/test_host_tables.py)."""
+    from oracle import table_emul as E
+    from victor_b200 import tables as T
+    from victor_b200.model import params_to_rows
+    from bench import synthetic_batch
+    P = synthetic_batch(65536)[:6]
+    kw = {"velocity_nodes": 100, "mu_nodes": 200}
+    got = fit.theory_multipole_vector_batch(fit.s, P, poles=[0, 2, 4], **kw)
+    mt = T.build_model_tables(fit, fit._merged_options(kw), nx=100)
+    mu, W = T.mu_projection_weights([0, 2, 4], nmu=200)
+    want, _ = E.theory_multipoles(mt, params_to_rows(P), np.asarray(fit.s, float), mu, W)
+    assert_theory(got, want.reshape(len(P), -1), ns=len(fit.s))
+    # and the denser quadrature moves the answer only at the level the default grid resolves
+    base = fit.theory_multipole_vector_batch(fit.s, P, poles=[0, 2, 4])
+    assert 1e-9 < np.abs(base - got).max() < 1e-4
+
+
+def test_multi_device_fit_single_gpu(boss_blocks, golden):
+    """MultiDeviceFit with every visible GPU: concatenated shard outputs == single-context output."""
+    import torch
+    from victor_b200 import CCFFit
+    from victor_b200.batch import MultiDeviceFit
+    model, data = boss_blocks
+    devices = list(range(torch.cuda.device_count()))
+    mf = MultiDeviceFit(lambda d: CCFFit(copy.deepcopy(model), copy.deepcopy(data), device=d), devices)
+    g = golden("boss_streaming_points")
+    lnl, chi2 = mf.log_likelihood_batch(g["params"])
+    np.testing.assert_allclose(chi2, g["chi2"], rtol=0, atol=CHI2_ATOL)
+    one = CCFFit(copy.deepcopy(model), copy.deepcopy(data), device=0)
+    l1, c1 = one.log_likelihood_batch(g["params"])
+    assert np.array_equal(c1, chi2) and np.array_equal(l1, lnl)     # bit-identical wherever a row lands
+    mf.close()
+    one.close()

@@ -105,6 +105,18 @@ class Engine:
         self._check(self.lib.vb200_likelihood(self.handle, params_ptr, int(n), theory_ptr, chi2_ptr, lnl_ptr,
                                               stream))
 
+    def theory_ptr(self, params_ptr, n, s, mu, wmu, xi_ptr, mult_ptr, stream=None):
+        """vb200_theory with caller-owned parameter / output buffers (host or device pointers);
+        ``s``, ``mu``, ``wmu`` are host arrays (staged by the library on every call)."""
+        s = np.ascontiguousarray(s, dtype=np.float64)
+        mu = np.ascontiguousarray(mu, dtype=np.float64)
+        L, wp = 0, None
+        if wmu is not None:
+            wmu = np.ascontiguousarray(wmu, dtype=np.float64)
+            L, wp = wmu.shape[0], wmu.ctypes.data
+        self._check(self.lib.vb200_theory(self.handle, params_ptr, int(n), s.ctypes.data, len(s), mu.ctypes.data,
+                                          len(mu), wp, L, xi_ptr, mult_ptr, stream))
+
     def close(self):
         if getattr(self, "handle", None):
             self.lib.vb200_destroy(self.handle)

@@ -176,7 +176,7 @@ class CCFFit(CCFModel):
 
     def _fit_tables(self, opts):
         like = opts.get("likelihood", self.fit_options["likelihood"])
-        mu, wmu = _tables.mu_projection_weights(self.poles_s)
+        mu, wmu = _tables.mu_projection_weights(self.poles_s, nmu=int(opts.get("mu_nodes", 100)))
         return {"ft": _tables.build_fit_tables(self, like), "s": np.asarray(self.s, dtype=np.float64),
                 "mu": mu, "wmu": wmu}
 

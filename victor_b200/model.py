@@ -128,6 +128,10 @@ class CCFModel:
             "empirical_corr": model["velocity_pdf"]["mean"].get("empirical_corr", False),
             "velocity_independent_of_AP":
                 model["velocity_pdf"].get("rescale_templates_independent_of_AP", True),
+            # quadrature sizes: the reference hard-codes 50 velocity nodes (ccf_model.py:570) and 100
+            # mu nodes (:819, :822); kept as options so that denser grids can be requested
+            "velocity_nodes": model.get("velocity_nodes", 50),
+            "mu_nodes": model.get("mu_nodes", 100),
         }
         self._device = device
         self._engines = {}
@@ -261,10 +265,11 @@ class CCFModel:
         key = (opts["rsd_model"], bool(opts["assume_isotropic"]), bool(opts["velocity_independent_of_AP"]),
                opts["matter_model"], opts["mean_model"], bool(opts["empirical_corr"]),
                bool(opts["realspace_ccf_from_data"]), bool(opts.get("kaiser_approximation", False)),
-               bool(opts.get("kaiser_coord_shift", True)), self._fit_key(opts) if need_fit else None)
+               bool(opts.get("kaiser_coord_shift", True)), int(opts.get("velocity_nodes", 50)),
+               int(opts.get("mu_nodes", 100)), self._fit_key(opts) if need_fit else None)
         eng = self._engines.get(key)
         if eng is None:
-            mt = _tables.build_model_tables(self, opts)
+            mt = _tables.build_model_tables(self, opts, nx=int(opts.get("velocity_nodes", 50)))
             fit = self._fit_tables(opts) if need_fit else None
             eng = Engine(mt, fit, device=self._device)
             self._engines[key] = eng
@@ -321,7 +326,7 @@ class CCFModel:
                              "reference, ccf_model.py:824)")
         if np.any(np.diff(s) <= 0):
             raise InputError("theory_multipoles: s must be strictly increasing")
-        mu, W = _tables.mu_projection_weights(poles)
+        mu, W = _tables.mu_projection_weights(poles, nmu=int(opts.get("mu_nodes", 100)))
         return self._engine(opts).theory(params_to_rows(params), s, mu, W)[1]
 
     def theory_multipoles(self, s, params, poles=[0, 2], **kwargs):

@@ -47,6 +47,8 @@ def velocity_nodes(nx=50):
     weights being whatever scipy's composite Simpson rule assigns on this grid (for an even
     number of points that includes its asymmetric end correction).
     """
+    if not 3 <= nx <= 128:
+        raise InputError("velocity_nodes must be between 3 and 128")
     x = np.linspace(-6, 6, nx)
     w = simpson(np.eye(nx), x=x, axis=1)
     return x, w
