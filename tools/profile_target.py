@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--nsplit", type=int, default=0)
     ap.add_argument("--ilp", type=int, default=4)
     ap.add_argument("--expdeg", type=int, default=5)
+    ap.add_argument("--sigma-v", type=float, default=None, help="override the sigma_v column (access-pattern probe)")
     args = ap.parse_args()
     model, data = boss_blocks()
     fit = CCFFit(model, data, device=0)
@@ -37,7 +38,10 @@ def main():
     eng.set_option("exp_degree", args.expdeg)
     n = args.batch
     dev = torch.device("cuda", 0)
-    d_params = torch.from_numpy(params_to_rows(synthetic_batch(n))).to(dev)
+    rows = params_to_rows(synthetic_batch(n))
+    if args.sigma_v is not None:
+        rows[:, 2] = args.sigma_v
+    d_params = torch.from_numpy(rows).to(dev)
     d_theory = torch.empty((n, P), dtype=torch.float64, device=dev)
     d_chi2 = torch.empty(n, dtype=torch.float64, device=dev)
     d_lnl = torch.empty(n, dtype=torch.float64, device=dev)
@@ -49,7 +53,7 @@ def main():
         b.record()
         torch.cuda.synchronize()
         times.append(a.elapsed_time(b))
-    print(f"batch={n} fast={args.fast} threads={args.threads} nsplit={args.nsplit} ilp={args.ilp} expdeg={args.expdeg} "
+    print(f"batch={n} fast={args.fast} threads={args.threads} nsplit={args.nsplit} ilp={args.ilp} expdeg={args.expdeg} sigma_v={args.sigma_v} "
           f"ms={['%.3f' % t for t in times]} evals/s={n / (min(times) * 1e-3):.4g} "
           f"chi2[0]={float(d_chi2[0]):.10f}")
     fit.close()

@@ -18,6 +18,7 @@ using namespace vb200;
 namespace {
 
 thread_local std::string g_err;
+constexpr int64_t kSmallCall = 256;   // rows: calls up to this size go through pinned staging
 
 int fail(int code, const std::string &msg) {
     g_err = msg;
@@ -94,6 +95,8 @@ struct vb200_ctx {
     // options
     int opt_fast = 1, opt_nsplit = 0, opt_threads = 256, opt_ilp = 4, opt_expdeg = 5;
     bool tuned = false;           // streaming + isotropic xi + model coordinates: the tuned kernel applies
+    // small-call path (MCMC steps): page-locked staging for the rows in and (chi2 | lnL) out
+    double *pin = nullptr, *d_small = nullptr;
     long long launches = 0;
     size_t k1_smem_limit = 0;
     double xw[2 * kMaxNx] = {0};  // host copy of x_m | w_m for the kernel-parameter table
@@ -257,6 +260,8 @@ void vb200_destroy(vb200_ctx *c) {
     c->sc_xi.release();
     c->sc_mult.release();
     c->sc_grid.release();
+    if (c->pin) cudaFreeHost(c->pin);
+    if (c->d_small) cudaFree(c->d_small);
     delete c;
 }
 
@@ -475,8 +480,31 @@ int vb200_likelihood(vb200_ctx *c, const double *params, int64_t n, double *theo
     bool host_io = false;
     int rc;
 
+    const bool params_on_host = !is_device_ptr(params);
+    if (n <= kSmallCall && !theory && chi2 && lnlike && params_on_host && !is_device_ptr(chi2) &&
+        !is_device_ptr(lnlike)) {
+        // one pinned H2D of the rows, two launches, one pinned D2H of (chi2 | lnL), one sync
+        if (!c->pin) {
+            CK(cudaMallocHost(&c->pin, (size_t)kSmallCall * (VB200_NPAR + 2) * sizeof(double)));
+            CK(cudaMalloc(&c->d_small, (size_t)kSmallCall * (VB200_NPAR + 2) * sizeof(double)));
+        }
+        if ((rc = c->sc_theory.ensure((size_t)n * p))) return rc;
+        double *h_out = c->pin + (size_t)kSmallCall * VB200_NPAR, *d_out = c->d_small + (size_t)kSmallCall * VB200_NPAR;
+        memcpy(c->pin, params, (size_t)n * VB200_NPAR * sizeof(double));
+        CK(cudaMemcpyAsync(c->d_small, c->pin, (size_t)n * VB200_NPAR * sizeof(double), cudaMemcpyHostToDevice, st));
+        if ((rc = launch_k1(c, c->d_small, n, c->fit_s, c->fit_ns, c->fit_mu, c->fit_sqmu, c->fit_wmu, c->fit_nmu,
+                            c->fit_L, nullptr, c->sc_theory.ptr, st)))
+            return rc;
+        if ((rc = launch_k2(c, c->d_small, c->sc_theory.ptr, n, d_out, d_out + n, st))) return rc;
+        CK(cudaMemcpyAsync(h_out, d_out, (size_t)2 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        memcpy(chi2, h_out, (size_t)n * sizeof(double));
+        memcpy(lnlike, h_out + n, (size_t)n * sizeof(double));
+        return VB200_OK;
+    }
+
     const double *d_params = params;
-    if (!is_device_ptr(params)) {
+    if (params_on_host) {
         host_io = true;
         if ((rc = c->sc_params.ensure((size_t)n * VB200_NPAR))) return rc;
         CK(cudaMemcpyAsync(c->sc_params.ptr, params, (size_t)n * VB200_NPAR * sizeof(double),
@@ -589,6 +617,8 @@ int vb200_mix_probe(int device, int chains, int mix, int kind, int blocks_per_sm
     VB_MIX(4, 1, 0) VB_MIX(4, 2, 0) VB_MIX(8, 1, 0) VB_MIX(2, 1, 0)
     VB_MIX(4, 1, 1) VB_MIX(8, 1, 1) VB_MIX(2, 1, 1)
     VB_MIX(4, 0, 2) VB_MIX(8, 0, 2)
+    VB_MIX(4, 0, 3) VB_MIX(4, 0, 4)
+    VB_MIX(8, 0, 5) VB_MIX(8, 0, 6) VB_MIX(8, 0, 7) VB_MIX(4, 0, 5) VB_MIX(4, 0, 6) VB_MIX(4, 0, 7)
 #undef VB_MIX
     if (!fn) return fail(VB200_EINVAL, "no such probe variant");
     cudaEvent_t e0, e1;

@@ -89,6 +89,51 @@ __global__ void __launch_bounds__(128) k_mix_probe(double *out, int iters, doubl
         n[c] = threadIdx.x + c;
     }
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(sh);
+    if (kKind == 5 || kKind == 6 || kKind == 7) {
+        // register-operand bandwidth: kind 5 = DFMA with three distinct register operands per chain,
+        // kind 6 = two distinct register operands + an immediate, kind 7 = DMUL of two registers
+        double y[kChains], z[kChains];
+#pragma unroll
+        for (int c = 0; c < kChains; ++c) {
+            y[c] = a + c * 1e-7;
+            z[c] = b + c * 1e-10;
+        }
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+#pragma unroll
+                for (int c = 0; c < kChains; ++c) {
+                    if (kKind == 5) x[c] = fma(x[c], y[c], z[c]);
+                    else if (kKind == 6) x[c] = fma(x[c], y[c], 1e-9);
+                    else x[c] = x[c] * y[c];
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < kChains; ++c) acc += y[c] + z[c];
+    } else if (kKind == 3 || kKind == 4) {
+        // kind 3: the chains one after the other, 6 dependent DFMAs each (how ptxas orders the exp
+        // polynomial of an unrolled loop); kind 4: the same work in interleaved order.  volatile asm
+        // pins the order.
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                if (kKind == 3) {
+#pragma unroll
+                    for (int c = 0; c < kChains; ++c)
+#pragma unroll
+                        for (int k = 0; k < 6; ++k)
+                            asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(x[c]) : "d"(a), "d"(b));
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k)
+#pragma unroll
+                        for (int c = 0; c < kChains; ++c)
+                            asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(x[c]) : "d"(a), "d"(b));
+                }
+            }
+        }
+    } else
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
         for (int r = 0; r < 8; ++r) {

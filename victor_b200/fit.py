@@ -183,11 +183,18 @@ class CCFFit(CCFModel):
     def _fit_engine(self, kwargs):
         # the reference feeds the same kwargs to the fit options and to the model options
         # (ccf_fit.py:379-381, 444)
+        if not kwargs:   # the MCMC step: no overrides, reuse the resolved engine
+            cached = getattr(self, "_default_engine", None)
+            if cached is not None and cached[0].handle:
+                return cached
         fit_options = dict(self.fit_options)
         fit_options.update(kwargs)
         opts = self._merged_options(kwargs)
         opts["likelihood"] = fit_options["likelihood"]
-        return self._engine(opts, need_fit=True), fit_options
+        out = (self._engine(opts, need_fit=True), fit_options)
+        if not kwargs:
+            self._default_engine = out
+        return out
 
     def log_likelihood_batch(self, params, return_theory=False, **kwargs):
         """(lnlike[n], chisq[n]) for every parameter row, optionally with the theory vectors."""

@@ -52,6 +52,21 @@ def params_to_rows(params, n_hint=None):
     defaults = {"fsigma8": np.nan, "beta": np.nan, "sigma_v": 380.0, "aperp": 1.0, "apar": 1.0,
                 "astar": 1.0, "M": 1.0, "Q": 1.0}
     if isinstance(params, dict):
+        # fast path for one parameter point given as plain numbers (the MCMC step): no array work
+        get = params.get
+        try:
+            fs8, beta, sig = float(get("fsigma8", np.nan)), float(get("beta", np.nan)), float(get("sigma_v", 380.0))
+            if "epsilon" in params:
+                eps = float(params["epsilon"])
+                apar = float(get("alpha", 1.0)) * eps ** (-2 / 3)
+                aperp = eps * apar
+            else:
+                aperp, apar = float(get("aperp", 1.0)), float(get("apar", 1.0))
+            row = [fs8, beta, sig, aperp, apar, float(get("astar", 1.0)), float(get("M", 1.0)), float(get("Q", 1.0))]
+            if not n_hint or n_hint == 1:
+                return np.array([row], dtype=np.float64)
+        except TypeError:      # some value is an array: general path below
+            pass
         cols = {}
         lens = [np.size(v) for k, v in params.items()
                 if k in defaults or k in ("epsilon", "alpha")]
