@@ -74,6 +74,10 @@ typedef struct vb200_model_tables {
     int32_t kaiser_approximation; /* (:737-741) */
     int32_t kaiser_coord_shift;   /* (:696-703) */
     int32_t niter;            /* fixed-point iterations of the dispersion / kaiser coordinate map (5) */
+    int32_t sv_ny;            /* mu intervals of a sigma_v(r, mu) template; 0 = isotropic template */
+    int32_t vd_beta_dependent; /* v0 / d0 are power tables in beta like xi_tab (matter model linear_bias) */
+    int32_t growth_mode;      /* 0: growth = fsigma8 / template_sigma8; 1: beta * bias (:425-435) */
+    double bias;              /* model['bias'] (linear_bias with from-data input) */
     const double *origin;     /* [ncell] */
     const double *upper;      /* [ncell], last = +inf */
     const int32_t *bucket_base; /* [nbucket] */
@@ -81,7 +85,10 @@ typedef struct vb200_model_tables {
     const double *xi_tab;     /* [n_ell][nbeta-1][4 powers of (beta-beta_k)][ncell][4] */
     const double *v0;         /* [ncell][4]  spline of r * Delta(r)               (:449, 635) */
     const double *d0;         /* [ncell][4]  spline of 3 (delta - 2 Delta / 3)    (:450, 636) */
+                              /* both [nbeta-1][4][ncell][4] when vd_beta_dependent */
     const double *sv;         /* [ncell][4]  normalised sigma_v(r) template       (:654) */
+    const double *sv2d;       /* [ncell][sv_ny][4][4] bicubic sigma_v(r, mu) patches, t^q w^p (NULL if sv_ny = 0) */
+    const double *sv_ybreaks; /* [sv_ny + 1] mu breakpoints of sv2d */
     const double *x;          /* [nx] linspace(-6, 6) (:570) */
     const double *wx;         /* [nx] Simpson weights / sqrt(2 pi) (:690, :656) */
     const double *mu_resc;    /* [nresc] */

@@ -262,6 +262,69 @@ def golden_more(victor):
     np.savez(os.path.join(OUT, "boss_more_variants.npz"), **out, **meta())
 
 
+def golden_sv2d(victor):
+    """sigma_v(r, mu) dispersion template (3 template keys): no shipped file has one, so the BOSS
+    model file is extended with a synthetic anisotropic template.  The inputs are saved next to
+    the outputs (tests/golden/model_sv2d_inputs.npz) so the product reads the very same arrays."""
+    import tempfile
+    model, data = boss_blocks()
+    from victor_b200.io_hdf5 import read_hdf5
+    src = read_hdf5(os.path.join(REF, model["input_model_data_file"]))
+    rng = np.random.default_rng(SEED + 7)
+    musv = np.concatenate([[0.0], np.sort(rng.uniform(0.05, 0.95, 8)), [1.0]])       # non-uniform, 10 knots
+    base = src["sigmav"]
+    sv2d = base[:, None] * (1 + 0.15 * musv[None, :] ** 2 - 0.05 * musv[None, :]) \
+        * (1 + 0.01 * rng.standard_normal((len(base), len(musv))))
+    inputs = dict(src)
+    inputs["musv"] = musv
+    inputs["sigmav2d"] = sv2d
+    np.savez(os.path.join(OUT, "model_sv2d_inputs.npz"), **inputs)
+    tmp = tempfile.mkdtemp()
+    np.save(os.path.join(tmp, "model_sv2d.npy"), inputs, allow_pickle=True)
+    mm = copy.deepcopy(model)
+    mm["dir"] = tmp
+    mm["input_model_data_file"] = "model_sv2d.npy"
+    mm["velocity_pdf"]["dispersion"]["template_keys"] = ["rsv", "musv", "sigmav2d"]
+    ccf = victor.CCFFit(mm, copy.deepcopy(data))
+    P = np.vstack([synthetic_batch(65536)[:5], edge_rows(ccf.beta)[[0, 8, 13]]])
+    out = dict(params=P, sv_rmu=ccf.sv_rmu, mu_for_sv=ccf.mu_for_sv)
+    for name, kw in (("streaming", {}), ("dispersion", {"rsd_model": "dispersion"}),
+                     ("aniso_streaming", {"assume_isotropic": False})):
+        th, c2, ll = run_points(ccf, P, **kw)
+        out[f"{name}_theory"], out[f"{name}_chi2"], out[f"{name}_lnl"] = th, c2, ll
+    np.savez(os.path.join(OUT, "boss_sv2d.npz"), **out, **meta())
+
+
+def golden_linear_bias(victor):
+    """matter_ccf model 'linear_bias' (ccf_model.py:358-370): delta and Delta from the real-space
+    monopole itself; growth term fsigma8 / sigma8_template, or beta * bias with from-data input."""
+    model, data = boss_blocks()
+    mm = copy.deepcopy(model)
+    mm["matter_ccf"]["model"] = "linear_bias"
+    ccf = victor.CCFFit(mm, copy.deepcopy(data))
+    P = np.vstack([synthetic_batch(65536)[:5], edge_rows(ccf.beta)[[0, 4, 9]]])
+    out = dict(params=P)
+    for name, kw in (("streaming", {}), ("dispersion", {"rsd_model": "dispersion"}), ("kaiser", {"rsd_model": "kaiser"}),
+                     ("bias25", {"bias": 2.5})):
+        th, c2, ll = run_points(ccf, P, **kw)
+        out[f"{name}_theory"], out[f"{name}_chi2"], out[f"{name}_lnl"] = th, c2, ll
+    md = copy.deepcopy(mm)
+    md["input_model_data_file"] = ("data/BOSS_DR12_CMASS_data/"
+                                   "CMASS_zobovVoids_reconRs10_0.43z0.7_medianRvcut_measured_model.hdf5")
+    md["realspace_ccf"]["from_data"] = True
+    dm = copy.deepcopy(data)
+    dm["covariance_matrix"]["data_file"] = (
+        "data/BOSS_DR12_CMASS_data/"
+        "CMASS_zobovVoids_reconRs10_0.43z0.7_medianRvcut_variable_isotropic_MD_covariance.hdf5")
+    cmd = victor.CCFFit(md, dm)
+    Pm = P[:4].copy()
+    Pm[:, 1] = np.clip(Pm[:, 1], 0.25, 0.55)
+    th, c2, ll = run_points(cmd, Pm)
+    out["measured_params"] = Pm
+    out["measured_theory"], out["measured_chi2"], out["measured_lnl"] = th, c2, ll
+    np.savez(os.path.join(OUT, "boss_linear_bias.npz"), **out, **meta())
+
+
 def golden_example(victor):
     with open(os.path.join(REF, "config/example_model_input.yaml")) as fh:
         model = yaml.full_load(fh)["model"]
@@ -289,11 +352,15 @@ def golden_example(victor):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     v = refshim.install(REF)
-    which = sys.argv[1:] or ["boss", "more", "example"]
+    which = sys.argv[1:] or ["boss", "more", "sv2d", "linear_bias", "example"]
     if "boss" in which:
         golden_boss(v)
     if "more" in which:
         golden_more(v)
+    if "sv2d" in which:
+        golden_sv2d(v)
+    if "linear_bias" in which:
+        golden_linear_bias(v)
     if "example" in which:
         golden_example(v)
     for fn in sorted(os.listdir(OUT)):

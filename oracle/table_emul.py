@@ -53,7 +53,8 @@ def point_scalars(mt, rows):
     else:
         y = apar[:, None] * np.sqrt(1 + (1 - mt.mu_resc[None, :] ** 2) * (eps[:, None] ** 2 - 1))
         f = (y * mt.w_resc[None, :]).sum(axis=1)
-    Av = -(fs8 / mt.template_sigma8) / (3 * iaHt)
+    growth = beta * mt.bias if mt.growth_mode else fs8 / mt.template_sigma8
+    Av = -growth / (3 * iaHt)
     return dict(eps=eps, iaHt=iaHt, f=f, Av=Av)
 
 
@@ -68,6 +69,27 @@ def xi_cells(mt, beta):
     tt = t[None, :, None, None]
     c = ((tab[:, :, 3] * tt + tab[:, :, 2]) * tt + tab[:, :, 1]) * tt + tab[:, :, 0]
     return np.moveaxis(c, 0, 1)                 # [n][n_ell][ncell][4]
+
+
+def _sv(mt, cell, t, mur):
+    """Normalised dispersion template: 1-D cubic, or the bicubic patch with mu clamped."""
+    if mt.sv2d is None:
+        return _horner(mt.sv, cell, t)
+    yb = mt.sv_ybreaks
+    mc = np.clip(mur, yb[0], yb[-1])
+    yc = np.clip(np.searchsorted(yb, np.nan_to_num(mc, nan=yb[0]), side="right") - 1, 0, len(yb) - 2)
+    w = mc - yb[yc]
+    K = mt.sv2d[cell, yc]                       # [..., q, p]
+    py = ((K[..., 3] * w[..., None] + K[..., 2]) * w[..., None] + K[..., 1]) * w[..., None] + K[..., 0]
+    return ((py[..., 3] * t + py[..., 2]) * t + py[..., 1]) * t + py[..., 0]
+
+
+def _beta_cells(mt, tab, beta):
+    """Per-row [n][ncell][4] cubics from a [nbint][4][ncell][4] beta power table."""
+    k, t = _beta_interval(mt.beta_grid, beta)
+    T4 = tab[k]
+    tt = t[:, None, None]
+    return ((T4[:, 3] * tt + T4[:, 2]) * tt + T4[:, 1]) * tt + T4[:, 0]
 
 
 def _legendre_even(ell, x):
@@ -105,6 +127,20 @@ def theory_xi(mt, rows, s, mu, chunk=32):
         beta = R[:, 1] if mt.beta_dependent else np.full(len(R), mt.beta_fixed)
         xc = xi_cells(mt, beta)                                    # [c][n_ell][ncell][4]
         idx = np.arange(len(R))[:, None, None, None]
+        if mt.vd_beta_dependent:
+            v0c, d0c = _beta_cells(mt, mt.v0, beta), _beta_cells(mt, mt.d0, beta)
+        else:
+            v0c = np.broadcast_to(mt.v0, (len(R),) + mt.v0.shape)
+            d0c = np.broadcast_to(mt.d0, (len(R),) + mt.d0.shape)
+
+        def V0(cell, t):
+            k = v0c[idx, cell]
+            return ((k[..., 3] * t + k[..., 2]) * t + k[..., 1]) * t + k[..., 0]
+
+        def D0(cell, t):
+            k = d0c[idx, cell]
+            return ((k[..., 3] * t + k[..., 2]) * t + k[..., 1]) * t + k[..., 0]
+
         f = sc["f"][:, None, None, None]
         apar = R[:, 4][:, None, None, None]
         Sperp = (s[None, None, :] * sq[None, :, None] * (R[:, 3] / sc["f"])[:, None, None])[..., None]
@@ -130,25 +166,25 @@ def theory_xi(mt, rows, s, mu, chunk=32):
                 u = np.sqrt(Sperp2 + rp ** 2)
                 mur = rp / u
                 cell, t = _cells(mt, u)
-                svv = _horner(mt.sv, cell, t)
-                z = (xm - B * _horner(mt.v0, cell, t) * mur) / svv
+                svv = _sv(mt, cell, t, mur)
+                z = (xm - B * V0(cell, t) * mur) / svv
                 integrand = (1 + xi_at(rp, cell, t, mur)) * np.exp(-0.5 * z * z) / svv
                 out[a:a + chunk] = (integrand * mt.wx[None, None, None, :]).sum(axis=-1) - 1
             elif rsd == T.RSD_DISPERSION:
                 Strue = np.sqrt(Sperp2 + Spar ** 2)
                 c0, t0 = _cells(mt, Strue)
                 num = Spar - xm * kap
-                rp = num / (1 + G * _horner(mt.v0, c0, t0) / Strue)
+                rp = num / (1 + G * V0(c0, t0) / Strue)
                 for _ in range(mt.niter):
                     u = np.sqrt(Sperp2 + rp ** 2)
                     cell, t = _cells(mt, u)
-                    rp = num / (1 + G * _horner(mt.v0, cell, t) / u)
+                    rp = num / (1 + G * V0(cell, t) / u)
                 u = np.sqrt(Sperp2 + rp ** 2)
                 mur = rp / u
                 cell, t = _cells(mt, u)
-                svv = _horner(mt.sv, cell, t)
-                v0u = _horner(mt.v0, cell, t) / u
-                jac = 1 / (1 + G * v0u + G * mur ** 2 * (_horner(mt.d0, cell, t) - v0u))
+                svv = _sv(mt, cell, t, mur)
+                v0u = V0(cell, t) / u
+                jac = 1 / (1 + G * v0u + G * mur ** 2 * (D0(cell, t) - v0u))
                 z = xm / svv
                 integrand = (1 + xi_at(rp, cell, t, mur)) * jac * np.exp(-0.5 * z * z) / svv
                 out[a:a + chunk] = (integrand * mt.wx[None, None, None, :]).sum(axis=-1) - 1
@@ -160,17 +196,17 @@ def theory_xi(mt, rows, s, mu, chunk=32):
                 if mt.kaiser_coord_shift:
                     Strue = np.sqrt(Sperp2 + Spar ** 2)
                     c0, t0 = _cells(mt, Strue)
-                    rp = Spar / (1 + MG * _horner(mt.v0, c0, t0) / Strue)
+                    rp = Spar / (1 + MG * V0(c0, t0) / Strue)
                     for _ in range(mt.niter):
                         u = np.sqrt(Sperp2 + rp ** 2)
                         cell, t = _cells(mt, u)
-                        rp = Spar / (1 + MG * _horner(mt.v0, cell, t) / u)
+                        rp = Spar / (1 + MG * V0(cell, t) / u)
                 u = np.sqrt(Sperp2 + rp ** 2)
                 mur = rp / u
                 cell, t = _cells(mt, u)
-                v0u = _horner(mt.v0, cell, t) / u
+                v0u = V0(cell, t) / u
                 ca, cb = (3.0, 2.0) if rsd == T.RSD_EUCLID else (1.0, 1.0)
-                J = ca * MG * v0u + cb * MG * Qk * mur ** 2 * (_horner(mt.d0, cell, t) - v0u)
+                J = ca * MG * v0u + cb * MG * Qk * mur ** 2 * (D0(cell, t) - v0u)
                 xi = xi_at(rp, cell, t, mur)
                 if rsd == T.RSD_EUCLID or mt.kaiser_approximation:
                     res = Mk * xi - J

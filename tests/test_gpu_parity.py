@@ -384,3 +384,50 @@ def test_multi_device_fit_single_gpu(boss_blocks, golden):
     assert np.array_equal(c1, chi2) and np.array_equal(l1, lnl)     # bit-identical wherever a row lands
     mf.close()
     one.close()
+
+
+@pytest.mark.parametrize("name,kw", [("streaming", {}), ("dispersion", {"rsd_model": "dispersion"}),
+                                     ("aniso_streaming", {"assume_isotropic": False})])
+def test_sigma_v_r_mu_template(boss_blocks, golden, name, kw):
+    """3-key dispersion template: bicubic sigma_v(r, mu) with mu clamped below 0."""
+    from victor_b200 import CCFFit
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["input_model_data_file"] = "tests/golden/model_sv2d_inputs.npz"
+    model["velocity_pdf"]["dispersion"]["template_keys"] = ["rsv", "musv", "sigmav2d"]
+    fm = CCFFit(model, data)
+    g = golden("boss_sv2d")
+    lnl, chi2, theory = fm.log_likelihood_batch(g["params"], return_theory=True, **kw)
+    assert_theory(theory, g[f"{name}_theory"], ns=len(fm.s))
+    np.testing.assert_allclose(chi2, g[f"{name}_chi2"], rtol=0, atol=CHI2_ATOL)
+    np.testing.assert_allclose(lnl, g[f"{name}_lnl"], rtol=0, atol=CHI2_ATOL)
+    fm.close()
+
+
+@pytest.mark.parametrize("name,kw", [("streaming", {}), ("dispersion", {"rsd_model": "dispersion"}),
+                                     ("kaiser", {"rsd_model": "kaiser"}), ("bias25", {"bias": 2.5})])
+def test_linear_bias_matter_model(boss_blocks, golden, name, kw):
+    from victor_b200 import CCFFit
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["matter_ccf"]["model"] = "linear_bias"
+    fm = CCFFit(model, data)
+    g = golden("boss_linear_bias")
+    lnl, chi2, theory = fm.log_likelihood_batch(g["params"], return_theory=True, **kw)
+    assert_theory(theory, g[f"{name}_theory"], ns=len(fm.s))
+    np.testing.assert_allclose(chi2, g[f"{name}_chi2"], rtol=0, atol=CHI2_ATOL)
+    np.testing.assert_allclose(lnl, g[f"{name}_lnl"], rtol=0, atol=CHI2_ATOL)
+    fm.close()
+
+
+def test_linear_bias_from_data(boss_blocks, golden):
+    from victor_b200 import CCFFit
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["matter_ccf"]["model"] = "linear_bias"
+    model["input_model_data_file"] = "data/boss_dr12_cmass/cmass_measured_model.npz"
+    model["realspace_ccf"]["from_data"] = True
+    data["covariance_matrix"]["data_file"] = "data/boss_dr12_cmass/cmass_variable_isotropic_MD_covariance.npz"
+    fm = CCFFit(model, data)
+    g = golden("boss_linear_bias")
+    lnl, chi2, theory = fm.log_likelihood_batch(g["measured_params"], return_theory=True)
+    assert_theory(theory, g["measured_theory"], ns=len(fm.s))
+    np.testing.assert_allclose(chi2, g["measured_chi2"], rtol=0, atol=CHI2_ATOL)
+    fm.close()

@@ -300,3 +300,67 @@ def test_example_config_variants(example_block, golden):
         mt = T.build_model_tables(m, m._merged_options({"rsd_model": name}))
         mult, _ = E.theory_multipoles(mt, params_to_rows(P), g["s"], mu, W)
         np.testing.assert_allclose(mult.reshape(3, -1), g[f"{name}_theory"], rtol=RTOL, atol=ATOL)
+
+
+def sv2d_blocks(boss_blocks):
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["input_model_data_file"] = "tests/golden/model_sv2d_inputs.npz"
+    model["velocity_pdf"]["dispersion"]["template_keys"] = ["rsv", "musv", "sigmav2d"]
+    return model, data
+
+
+def test_bicubic_dispersion_patches_match_scipy(boss_blocks):
+    """sigma_v(r, mu) template: patches == RectBivariateSpline.ev with bispeu's argument clamping."""
+    from scipy.interpolate import RectBivariateSpline
+    from victor_b200 import CCFFit, tables as T
+    fm = CCFFit(*sv2d_blocks(boss_blocks))
+    assert not fm.sv_isotropic and fm.sv_rmu.shape == (10, 25)
+    mt = T.build_model_tables(fm, fm.model)
+    spl = RectBivariateSpline(fm.r_for_sv, fm.mu_for_sv, fm.sv_rmu.T)
+    rng = np.random.default_rng(2)
+    u = np.concatenate([rng.uniform(0, 170, 20000), mt.knots])
+    m = np.concatenate([rng.uniform(-1, 1, 20000), np.linspace(-1, 1, len(mt.knots))])
+    cell, t = E._cells(mt, u)
+    np.testing.assert_allclose(E._sv(mt, cell, t, m), spl.ev(u, m), rtol=1e-13, atol=1e-15)
+
+
+@pytest.mark.parametrize("name,kw", [("streaming", {}), ("dispersion", {"rsd_model": "dispersion"}),
+                                     ("aniso_streaming", {"assume_isotropic": False})])
+def test_tables_sigma_v_r_mu_template(boss_blocks, golden, name, kw):
+    from victor_b200 import CCFFit
+    from victor_b200.model import params_to_rows
+    fm = CCFFit(*sv2d_blocks(boss_blocks))
+    g = golden("boss_sv2d")
+    np.testing.assert_allclose(fm.sv_rmu, g["sv_rmu"], rtol=1e-14)
+    _tables_vs_golden(fm, kw, params_to_rows(g["params"]), g[f"{name}_theory"], g[f"{name}_chi2"], g[f"{name}_lnl"])
+
+
+LB_CASES = [("streaming", {}), ("dispersion", {"rsd_model": "dispersion"}), ("kaiser", {"rsd_model": "kaiser"}),
+            ("bias25", {"bias": 2.5})]
+
+
+@pytest.mark.parametrize("name,kw", LB_CASES)
+def test_tables_linear_bias_matter_model(boss_blocks, golden, name, kw):
+    """matter_ccf model 'linear_bias' (ccf_model.py:358-370): V0 / D0 become beta power tables."""
+    from victor_b200 import CCFFit
+    from victor_b200.model import params_to_rows
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["matter_ccf"]["model"] = "linear_bias"
+    fm = CCFFit(model, data)
+    g = golden("boss_linear_bias")
+    _tables_vs_golden(fm, kw, params_to_rows(g["params"]), g[f"{name}_theory"], g[f"{name}_chi2"], g[f"{name}_lnl"])
+
+
+def test_tables_linear_bias_from_data(boss_blocks, golden):
+    """linear_bias with the measured model: growth term beta * bias (ccf_model.py:429-430)."""
+    from victor_b200 import CCFFit
+    from victor_b200.model import params_to_rows
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["matter_ccf"]["model"] = "linear_bias"
+    model["input_model_data_file"] = "data/boss_dr12_cmass/cmass_measured_model.npz"
+    model["realspace_ccf"]["from_data"] = True
+    data["covariance_matrix"]["data_file"] = "data/boss_dr12_cmass/cmass_variable_isotropic_MD_covariance.npz"
+    fm = CCFFit(model, data)
+    g = golden("boss_linear_bias")
+    _tables_vs_golden(fm, {}, params_to_rows(g["measured_params"]), g["measured_theory"], g["measured_chi2"],
+                      g["measured_lnl"])

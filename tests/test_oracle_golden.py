@@ -183,3 +183,25 @@ def test_more_variants(orc, golden):
             np.testing.assert_allclose(th, g[f"{name}_theory"][i], rtol=TH_RTOL, atol=TH_ATOL)
             l, c = orc.log_likelihood(dict(prm), **kw)
             assert abs(c - g[f"{name}_chi2"][i]) < C2_ATOL and abs(l - g[f"{name}_lnl"][i]) < C2_ATOL
+
+
+def test_sigma_v_r_mu_template(golden, boss_blocks):
+    g = golden("boss_sv2d")
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["input_model_data_file"] = "tests/golden/model_sv2d_inputs.npz"
+    model["velocity_pdf"]["dispersion"]["template_keys"] = ["rsv", "musv", "sigmav2d"]
+    om = OracleFit(model, data)
+    np.testing.assert_allclose(om.sv_rmu, g["sv_rmu"], rtol=1e-14)
+    for name, kw in (("streaming", {}), ("dispersion", {"rsd_model": "dispersion"})):
+        check_rows(om, g["params"][[1, 6]], g[f"{name}_theory"][[1, 6]], g[f"{name}_chi2"][[1, 6]],
+                   g[f"{name}_lnl"][[1, 6]], **kw)
+
+
+def test_linear_bias_matter_model(golden, boss_blocks):
+    g = golden("boss_linear_bias")
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["matter_ccf"]["model"] = "linear_bias"
+    om = OracleFit(model, data)
+    for name, kw in (("streaming", {}), ("kaiser", {"rsd_model": "kaiser"}), ("bias25", {"bias": 2.5})):
+        check_rows(om, g["params"][[2, 7]], g[f"{name}_theory"][[2, 7]], g[f"{name}_chi2"][[2, 7]],
+                   g[f"{name}_lnl"][[2, 7]], **kw)

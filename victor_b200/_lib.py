@@ -30,10 +30,12 @@ class ModelTablesC(ctypes.Structure):
         ("ncell", c_int32), ("nbucket", c_int32), ("maxscan", c_int32),
         ("nbeta", c_int32), ("nx", c_int32), ("nresc", c_int32),
         ("realspace_from_data", c_int32), ("kaiser_approximation", c_int32), ("kaiser_coord_shift", c_int32),
-        ("niter", c_int32),
+        ("niter", c_int32), ("sv_ny", c_int32), ("vd_beta_dependent", c_int32), ("growth_mode", c_int32),
+        ("bias", c_double),
         ("origin", c_double_p), ("upper", c_double_p), ("bucket_base", c_int32_p),
         ("beta_grid", c_double_p), ("xi_tab", c_double_p),
         ("v0", c_double_p), ("d0", c_double_p), ("sv", c_double_p),
+        ("sv2d", c_double_p), ("sv_ybreaks", c_double_p),
         ("x", c_double_p), ("wx", c_double_p), ("mu_resc", c_double_p), ("w_resc", c_double_p),
     ]
 
@@ -131,6 +133,12 @@ def pack_model(mt):
     c.bucket_base = keep["bucket_base"].ctypes.data_as(c_int32_p)
     c.beta_grid, c.xi_tab = f64("beta_grid", mt.beta_grid), f64("xi_tab", mt.xi_tab)
     c.v0, c.d0, c.sv = f64("v0", mt.v0), f64("d0", mt.d0), f64("sv", mt.sv)
+    c.vd_beta_dependent, c.growth_mode, c.bias = int(mt.vd_beta_dependent), int(mt.growth_mode), float(mt.bias)
+    if mt.sv2d is not None:
+        c.sv_ny = int(mt.sv2d.shape[1])
+        c.sv2d, c.sv_ybreaks = f64("sv2d", mt.sv2d), f64("sv_ybreaks", mt.sv_ybreaks)
+    else:
+        c.sv_ny = 0
     c.x, c.wx = f64("x", mt.x), f64("wx", mt.wx)
     c.mu_resc, c.w_resc = f64("mu_resc", mt.mu_resc), f64("w_resc", mt.w_resc)
     return c, keep

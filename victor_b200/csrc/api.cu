@@ -126,6 +126,8 @@ int check_model(const vb200_model_tables *m) {
     if (m->rsd_model < VB200_RSD_STREAMING || m->rsd_model > VB200_RSD_EUCLID)
         return fail(VB200_EINVAL, "model tables: unknown rsd_model");
     if (m->niter < 0 || m->niter > 64) return fail(VB200_EINVAL, "model tables: bad niter");
+    if (m->sv_ny < 0 || (m->sv_ny > 0 && (!m->sv2d || !m->sv_ybreaks)))
+        return fail(VB200_EINVAL, "model tables: bad sigma_v(r, mu) template");
     if (!(m->inv_h > 0.0) || !(m->iaH > 0.0) || !(m->template_sigma8 > 0.0))
         return fail(VB200_EINVAL, "model tables: bad scalars");
     return VB200_OK;
@@ -308,16 +310,26 @@ int vb200_create(const vb200_model_tables *m, const vb200_fit_tables *f, int dev
     d.kaiser_shift = m->kaiser_coord_shift;
     d.niter = m->niter;
     for (int i = 0; i < kMaxPoles; ++i) d.ells[i] = m->ells[i];
-    c->tuned = (m->rsd_model == VB200_RSD_STREAMING && m->n_ell == 1 && !m->realspace_from_data);
+    c->tuned = (m->rsd_model == VB200_RSD_STREAMING && m->n_ell == 1 && !m->realspace_from_data && m->sv_ny == 0 &&
+                !m->vd_beta_dependent);
     const size_t nc4 = (size_t)m->ncell * 4;
     if ((rc = upload(c, m->origin, (size_t)m->ncell, &d.origin))) return bail(rc);
     if ((rc = upload(c, m->upper, (size_t)m->ncell, &d.upper))) return bail(rc);
     if ((rc = upload(c, m->bucket_base, (size_t)m->nbucket, &d.bucket_base))) return bail(rc);
     if ((rc = upload(c, m->beta_grid, (size_t)m->nbeta, &d.beta_grid))) return bail(rc);
     if ((rc = upload(c, m->xi_tab, (size_t)m->n_ell * (m->nbeta - 1) * 4 * nc4, &d.xi_tab))) return bail(rc);
-    if ((rc = upload(c, m->v0, nc4, &d.v0))) return bail(rc);
-    if ((rc = upload(c, m->d0, nc4, &d.d0))) return bail(rc);
+    d.vd_beta_dep = m->vd_beta_dependent;
+    d.growth_mode = m->growth_mode;
+    d.bias = m->bias;
+    const size_t nvd = m->vd_beta_dependent ? (size_t)(m->nbeta - 1) * 4 * nc4 : nc4;
+    if ((rc = upload(c, m->v0, nvd, &d.v0))) return bail(rc);
+    if ((rc = upload(c, m->d0, nvd, &d.d0))) return bail(rc);
     if ((rc = upload(c, m->sv, nc4, &d.sv))) return bail(rc);
+    d.sv_ny = m->sv_ny;
+    if (m->sv_ny > 0) {
+        if ((rc = upload(c, m->sv2d, (size_t)m->ncell * m->sv_ny * 16, &d.sv2d))) return bail(rc);
+        if ((rc = upload(c, m->sv_ybreaks, (size_t)m->sv_ny + 1, &d.sv_yb))) return bail(rc);
+    }
     if ((rc = upload(c, m->x, (size_t)m->nx, &d.x))) return bail(rc);
     if ((rc = upload(c, m->wx, (size_t)m->nx, &d.wx))) return bail(rc);
     if ((rc = upload(c, m->mu_resc, (size_t)m->nresc, &d.mu_resc))) return bail(rc);

@@ -24,6 +24,11 @@ struct ModelDev {
     const int *bucket_base;
     const double *beta_grid, *xi_tab, *v0, *d0, *sv, *x, *wx, *mu_resc, *w_resc;
     const double *exp_tab;  // [kExpTab] 2^(j/32)
+    const double *sv2d;     // [ncell][sv_ny][4][4] bicubic sigma_v(u, mu) patches (sv_ny > 0), else null
+    const double *sv_yb;    // [sv_ny + 1] mu breakpoints
+    int sv_ny;
+    int vd_beta_dep, growth_mode;   // matter model linear_bias: v0 / d0 beta power tables; growth = beta * bias
+    double bias;
 };
 
 struct K1Args {
@@ -206,7 +211,7 @@ __device__ __forceinline__ void row_scalars_to_shared(const ModelDev &m, const d
         }
         if (tid == 0) {
             const double iaHt = m.iaH * apar;
-            const double g = fs8 / m.s8t;
+            const double g = m.growth_mode ? pr[1] * m.bias : fs8 / m.s8t;   // ccf_model.py:425-435
             const double Av = -g / (3.0 * iaHt);
             scal[0] = f;
             scal[1] = aperp / f;

@@ -3,6 +3,7 @@
 //   rsd_model 'kaiser' / 'euclid_special'       victor/ccf_model.py:692-741
 //   anisotropic real-space input                victor/ccf_model.py:684-687  (assume_isotropic: False)
 //   real-space ccf measured from data           victor/ccf_model.py:675-679  (realspace_ccf.from_data)
+//   sigma_v(r, mu) dispersion templates         victor/ccf_model.py:654-655, 667-668 (3 template keys)
 // and the streaming model combined with the last two.  Same tiling as the tuned kernel (one block
 // per parameter row x s-range, one thread per (s_j, mu_k) pair, velocity nodes in registers), plain
 // CUDA libm arithmetic (sqrt, divide, exp): these variants are written for parity first.
@@ -27,6 +28,8 @@ struct GenCtx {
     int nbucket, maxscan, n_ell;
     int ell1, ell2;
     double inv_h;
+    const double *sv2d, *sv_yb;
+    int sv_ny;
 };
 
 // cell of coordinate u and the local coordinate inside it; below the first knot t = 0 (every
@@ -44,6 +47,26 @@ __device__ __forceinline__ const double *locate(const GenCtx &g, double u, doubl
     const double tt = u - r[kGOrg];
     t = (tt < 0.0) ? 0.0 : tt;      // NaN stays NaN
     return r;
+}
+
+// normalised dispersion template at (cell record r, local coordinate t, mu_r): the 1-D cubic, or
+// for a sigma_v(r, mu) template the bicubic patch with mu clamped to the template's range
+// (RectBivariateSpline.ev -> FITPACK bispeu clamps both arguments)
+__device__ __forceinline__ double sv_at(const GenCtx &g, const double *r, double t, double mur) {
+    if (g.sv_ny == 0) return horner3(r + kGSV, t);
+    const int cell = (int)((r - g.rec) / kRecG);
+    const double *yb = g.sv_yb;
+    double mc = mur;
+    if (mc < yb[0]) mc = yb[0];
+    if (mc > yb[g.sv_ny]) mc = yb[g.sv_ny];
+    int yc = 0;
+    for (int i = 1; i < g.sv_ny; ++i) yc += (mc >= yb[i]) ? 1 : 0;
+    const double w = mc - yb[yc];
+    const double *T = g.sv2d + ((size_t)cell * g.sv_ny + yc) * 16;
+    double py[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) py[q] = horner3(T + 4 * q, w);
+    return horner3(py, t);
 }
 
 __device__ __forceinline__ double legendre_even(int ell, double x) {
@@ -107,8 +130,14 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
                 }
                 r[kGXi + 4 * l + c] = v;
             }
-            r[kGV0 + c] = m.v0[i];
-            r[kGD0 + c] = m.d0[i];
+            if (m.vd_beta_dep) {   // linear_bias: V0, D0 follow the monopole's beta dependence
+                const double *tv = m.v0 + (size_t)kb * 4 * per, *td = m.d0 + (size_t)kb * 4 * per;
+                r[kGV0 + c] = fma(fma(fma(tv[3 * per + i], tb, tv[2 * per + i]), tb, tv[per + i]), tb, tv[i]);
+                r[kGD0 + c] = fma(fma(fma(td[3 * per + i], tb, td[2 * per + i]), tb, td[per + i]), tb, td[i]);
+            } else {
+                r[kGV0 + c] = m.v0[i];
+                r[kGD0 + c] = m.d0[i];
+            }
             r[kGSV + c] = m.sv[i];
             if (c == 0) {
                 r[kGOrg] = m.origin[cell];
@@ -130,6 +159,9 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
     g.ell1 = m.ells[1];
     g.ell2 = m.ells[2];
     g.inv_h = m.inv_h;
+    g.sv2d = m.sv2d;
+    g.sv_yb = m.sv_yb;
+    g.sv_ny = m.sv_ny;
     const int nmu = a.nmu;
     const int npairs = jn * nmu;
     const double f_over_apar = f / apar;
@@ -162,7 +194,7 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
                 const double mur = rp / u;                             // :652
                 double t;
                 const double *rc = locate(g, u, t);
-                const double sv = horner3(rc + kGSV, t);               // :654-655
+                const double sv = sv_at(g, rc, t, mur);                // :654-655
                 const double z = (xm - B * horner3(rc + kGV0, t) * mur) / sv;   // :656
                 const double xi = xi_at(rp, u, mur, rc, t);
                 acc += wm * (1.0 + xi) * exp(-0.5 * z * z) / sv;       // :690
@@ -189,7 +221,7 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
                 u = sqrt(Sperp2 + rp * rp);
                 const double mur = rp / u;
                 rc = locate(g, u, t);
-                const double sv = horner3(rc + kGSV, t);
+                const double sv = sv_at(g, rc, t, mur);                // :667-668
                 const double v0u = horner3(rc + kGV0, t) / u;
                 const double jac = 1.0 / (1.0 + G * v0u + G * mur * mur * (horner3(rc + kGD0, t) - v0u));
                 const double z = xm / sv;

@@ -118,6 +118,7 @@ class CCFModel:
         input_data = load_input_file(input_fn)
 
         self._load_realspace_ccf(model["realspace_ccf"], input_data)
+        self.template_sigma8 = None
         self.matter_model = model["matter_ccf"].get("model", "linear_bias")
         self.realspace_ccf_from_data = model["realspace_ccf"].get("from_data", False)
         if self.matter_model == "linear_bias" and not self.realspace_ccf_from_data:
@@ -281,7 +282,8 @@ class CCFModel:
                opts["matter_model"], opts["mean_model"], bool(opts["empirical_corr"]),
                bool(opts["realspace_ccf_from_data"]), bool(opts.get("kaiser_approximation", False)),
                bool(opts.get("kaiser_coord_shift", True)), int(opts.get("velocity_nodes", 50)),
-               int(opts.get("mu_nodes", 100)), self._fit_key(opts) if need_fit else None)
+               int(opts.get("mu_nodes", 100)), float(opts.get("bias", 1.9)),
+               self._fit_key(opts) if need_fit else None)
         eng = self._engines.get(key)
         if eng is None:
             mt = _tables.build_model_tables(self, opts, nx=int(opts.get("velocity_nodes", 50)))

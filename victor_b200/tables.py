@@ -101,41 +101,78 @@ def _shift_cubic(c_desc, delta):
     return np.array([n0, n1, n2, c3], dtype=np.float64)
 
 
-def spline_cells(x, y, knots):
-    """Cubic coefficients (ascending, local coordinate t = u - cell_origin) of the ext=3 spline
-    ``InterpolatedUnivariateSpline(x, y, ext=3)`` on every cell of ``knots``.
+def bspline_cells(tck, knots, lo, hi):
+    """Cubic coefficients (ascending, local coordinate t = u - cell_origin) on every cell of
+    ``knots`` of the cubic B-spline ``tck`` clamped to its boundary values outside [lo, hi]
+    (FITPACK ``ext=3`` / the argument clamping of ``bispeu``).
 
     Cells: 0 = (-inf, knots[0]), i = [knots[i-1], knots[i]), last = [knots[-1], inf).
-    Cell origins: knots[0] for cell 0, knots[i-1] otherwise.  ``x`` must be a subset of
-    ``knots`` so that no cell straddles a knot of this spline.
+    Cell origins: knots[0] for cell 0, knots[i-1] otherwise.  The interior knots of the spline
+    must be a subset of ``knots`` so that no cell straddles one of them.
     """
-    x = np.asarray(x, float)
-    spl = InterpolatedUnivariateSpline(x, y, k=3)
-    pp = PPoly.from_spline(spl._eval_args)
+    from scipy.interpolate import BSpline
+    t, c, k = tck
+    n = len(t) - k - 1
+    bs = BSpline(t, np.asarray(c, float)[:n], k, extrapolate=False)
+    pp = PPoly.from_spline((t, np.asarray(c, float), k))
     brk, coef = pp.x, pp.c                      # coef[:, i] on [brk[i], brk[i+1]]
     ncell = len(knots) + 1
     out = np.zeros((ncell, 4))
-    lo_val, hi_val = float(spl(x[0])), float(spl(x[-1]))
-    for c in range(ncell):
-        a = knots[0] if c == 0 else knots[c - 1]
-        if c == 0 or a < x[0]:
-            # whole cell below the spline's range?  (cell [a, b) with b <= x[0])
-            b = knots[0] if c == 0 else (knots[c] if c < len(knots) else np.inf)
-            if b <= x[0]:
-                out[c, 0] = lo_val
+    lo_val, hi_val = float(bs(lo)), float(bs(hi))
+    for cidx in range(ncell):
+        a = knots[0] if cidx == 0 else knots[cidx - 1]
+        if cidx == 0 or a < lo:
+            # whole cell below the spline's range?  (cell [a, b) with b <= lo)
+            b = knots[0] if cidx == 0 else (knots[cidx] if cidx < len(knots) else np.inf)
+            if b <= lo:
+                out[cidx, 0] = lo_val
                 continue
             raise InputError("spline_cells: cell straddles the first knot of a spline")
-        if a >= x[-1]:
-            out[c, 0] = hi_val
+        if a >= hi:
+            out[cidx, 0] = hi_val
             continue
-        b = knots[c] if c < len(knots) else np.inf
-        mid = 0.5 * (a + min(b, x[-1]))
+        b = knots[cidx] if cidx < len(knots) else np.inf
+        mid = 0.5 * (a + min(b, hi))
         i = int(np.searchsorted(brk, mid, side="right") - 1)
         i = min(max(i, 0), coef.shape[1] - 1)
         while brk[i + 1] <= brk[i]:             # skip zero-length end intervals
             i += 1
-        out[c] = _shift_cubic(coef[:, i], a - brk[i])
+        out[cidx] = _shift_cubic(coef[:, i], a - brk[i])
     return out
+
+
+def spline_cells(x, y, knots):
+    """Per-cell cubics of ``InterpolatedUnivariateSpline(x, y, ext=3)``, see bspline_cells."""
+    x = np.asarray(x, float)
+    spl = InterpolatedUnivariateSpline(x, y, k=3)
+    return bspline_cells(spl._eval_args, knots, x[0], x[-1])
+
+
+def sv2d_cells(r_sv, mu_sv, sv_rmu, knots):
+    """Bicubic patches of ``RectBivariateSpline(r_sv, mu_sv, sv_rmu.T)`` (ccf_model.py:654, 667)
+    on (radial cell of ``knots``) x (mu interval): T[cell][ycell][q][p] multiplies t^q w^p with
+    t = u - cell origin, w = mu - ybreaks[ycell].  ``.ev`` clamps both arguments to the knot
+    range (``bispeu``), which is the boundary-constant rule in u and an explicit clamp in mu."""
+    from scipy.interpolate import RectBivariateSpline
+    r_sv, mu_sv = np.asarray(r_sv, float), np.asarray(mu_sv, float)
+    spl = RectBivariateSpline(r_sv, mu_sv, np.asarray(sv_rmu, float).T)
+    tx, ty, c = spl.tck
+    nxb, nyb = len(tx) - 4, len(ty) - 4
+    C = np.asarray(c, float).reshape(nxb, nyb)
+    ncell = len(knots) + 1
+    A = np.empty((ncell, 4, nyb))
+    for j in range(nyb):
+        A[:, :, j] = bspline_cells((tx, np.concatenate([C[:, j], np.zeros(4)]), 3), knots, r_sv[0], r_sv[-1])
+    ybreaks = np.unique(ty)
+    nyc = len(ybreaks) - 1
+    T = np.zeros((ncell, nyc, 4, 4))
+    for cell in range(ncell):
+        for q in range(4):
+            pp = PPoly.from_spline((ty, np.concatenate([A[cell, q], np.zeros(4)]), 3))
+            keep = np.nonzero(np.diff(pp.x) > 0)[0]
+            assert len(keep) == nyc
+            T[cell, :, q, :] = pp.c[::-1, keep].T
+    return np.ascontiguousarray(T), ybreaks
 
 
 def union_knots(*grids):
@@ -221,6 +258,11 @@ class ModelTables:
     wx: np.ndarray                  # [nx]  Simpson weights / sqrt(2 pi)
     mu_resc: np.ndarray             # [50] nodes of the AP rescaling trapezoid
     w_resc: np.ndarray              # [50] its weights
+    vd_beta_dependent: bool = False # v0 / d0 are [nbint][4][ncell][4] power tables in beta (linear_bias)
+    growth_mode: int = 0            # 0: fsigma8 / template_sigma8;  1: beta * bias (:429-430)
+    bias: float = 1.9
+    sv2d: np.ndarray = None         # [ncell][nyc][4][4] bicubic sigma_v(u, mu) patches, or None (isotropic)
+    sv_ybreaks: np.ndarray = None   # [nyc + 1] mu breakpoints of sv2d
     from_data: bool = False         # real-space ccf measured from data: xi at (r_par/apar, s_perp/aperp)
     kaiser_approximation: bool = False
     kaiser_coord_shift: bool = True
@@ -250,6 +292,22 @@ class FitTables:
     use_logdet: bool
 
 
+def linear_bias_maps(r, r_eval):
+    """Matrices taking the real-space monopole values at ``r`` to  xi_0(r_eval)  and to
+    3 / r_eval^3 * trapz_{100}(xi_0 r'^2)  (ccf_model.py:362-369; divide by the bias for delta, Delta)."""
+    r = np.asarray(r, float)
+    Ld = np.empty((len(r_eval), len(r)))
+    LD = np.empty_like(Ld)
+    eye = np.eye(len(r))
+    for j in range(len(r)):
+        xir = InterpolatedUnivariateSpline(r, eye[j], ext=3)
+        Ld[:, j] = xir(r_eval)
+        for i, ri in enumerate(r_eval):
+            rr = np.linspace(0, ri, 100)
+            LD[i, j] = 3 * trapezoid(xir(rr) * rr ** 2, rr) / ri ** 3
+    return Ld, LD
+
+
 def pchip_power_table(grid, values):
     """PCHIP over ``grid`` of ``values`` [ngrid][...] -> (coef[nint][4 ascending][...]).
 
@@ -264,9 +322,9 @@ def pchip_power_table(grid, values):
 
 def build_model_tables(state, options, nx=50):
     """``state``: a loaded victor_b200.model.CCFModel; ``options``: its merged model dict."""
-    if options["matter_model"] != "template":
+    if options["matter_model"] not in ("template", "linear_bias"):
         raise NotImplementedError(
-            f"matter_model '{options['matter_model']}' has no B200 path yet (only 'template')")
+            f"matter_model '{options['matter_model']}' has no B200 path (only 'template' and 'linear_bias')")
     if options["mean_model"] != "linear" or options["empirical_corr"]:
         raise NotImplementedError("only the 'linear' mean-velocity model without empirical correction "
                                   "has a B200 path")
@@ -274,8 +332,6 @@ def build_model_tables(state, options, nx=50):
            "euclid_special": RSD_EUCLID}.get(options["rsd_model"])
     if rsd is None:
         raise InputError(f"theory_xi: Unrecognised choice of model {options['rsd_model']}")
-    if not state.sv_isotropic:
-        raise NotImplementedError("anisotropic sigma_v(r, mu) templates have no B200 path yet")
 
     r = np.asarray(state.r, float)
     r31 = np.append([0.01], r)
@@ -285,23 +341,51 @@ def build_model_tables(state, options, nx=50):
     upper = np.concatenate([knots, [np.inf]])
     inv_h, base, maxscan = bucket_map(knots)
 
-    # velocity templates (ccf_model.py:421-423, 449-450, 635-636): data at r31, knots r31
-    D31 = state.integrated_delta(r31)
-    d31 = state.delta(r31)
-    # velocity_terms() re-splines the profiles at their own abscissae before use (:422-423);
-    # an interpolating spline evaluated at its knots returns the data, so V0/D0 data are:
-    v0 = spline_cells(r31, r31 * D31, knots)
-    d0 = spline_cells(r31, 3.0 * (d31 - 2.0 * D31 / 3.0), knots)
+    beta_dep = not state.fixed_real_input
+    vd_beta_dep, growth_mode, bias = False, 0, float(options.get("bias", 1.9))
+    if options["matter_model"] == "template":
+        # velocity templates (ccf_model.py:421-423, 449-450, 635-636): data at r31, knots r31
+        D31 = state.integrated_delta(r31)
+        d31 = state.delta(r31)
+        # velocity_terms() re-splines the profiles at their own abscissae before use (:422-423);
+        # an interpolating spline evaluated at its knots returns the data, so V0/D0 data are:
+        v0 = spline_cells(r31, r31 * D31, knots)
+        d0 = spline_cells(r31, 3.0 * (d31 - 2.0 * D31 / 3.0), knots)
+    else:
+        # linear_bias (ccf_model.py:358-370): delta = xi_0 / b, Delta(r) = 3 / (b r^3) times a 100-point
+        # trapezoid of xi_0 r'^2 -- both linear in the monopole values, which are PCHIP cubics in beta:
+        # the V0 / D0 cell cubics are therefore, per beta interval, cubics in (beta - beta_k) too
+        Ld, LD = linear_bias_maps(r, r31)
+        if options["realspace_ccf_from_data"]:
+            growth_mode = 1                       # growth term beta * bias (:429-430)
+        mono = np.asarray(state.real_multipoles["0"], float)
+        if beta_dep:
+            vd_beta_dep = True
+            pw = pchip_power_table(np.asarray(state.beta, float), mono)      # (nbint, 4, nr)
+            v0 = np.zeros((pw.shape[0], 4, ncell, 4))
+            d0 = np.zeros_like(v0)
+            for k in range(pw.shape[0]):
+                for q in range(4):
+                    D31, d31 = LD @ pw[k, q] / bias, Ld @ pw[k, q] / bias
+                    v0[k, q] = spline_cells(r31, r31 * D31, knots)
+                    d0[k, q] = spline_cells(r31, 3.0 * (d31 - 2.0 * D31 / 3.0), knots)
+        else:
+            D31, d31 = LD @ mono / bias, Ld @ mono / bias
+            v0 = spline_cells(r31, r31 * D31, knots)
+            d0 = spline_cells(r31, 3.0 * (d31 - 2.0 * D31 / 3.0), knots)
 
     # sigma_v template: all mu rows identical -> 1-D cubic spline in u (FITPACK tensor spline of a
     # function constant in mu is that 1-D spline)
     sv = spline_cells(state.r_for_sv, state.sv_rmu[0], knots)
+    sv2d = sv_ybreaks = None
+    if not state.sv_isotropic:
+        # sigma_v(r, mu) template: true bicubic evaluation with FITPACK's argument clamping
+        sv2d, sv_ybreaks = sv2d_cells(state.r_for_sv, state.mu_for_sv, state.sv_rmu, knots)
 
     # real-space multipoles
     iso = bool(options["assume_isotropic"])
     ells = np.array([0]) if iso else np.asarray(state.poles_r)
     n_ell = len(ells)
-    beta_dep = not state.fixed_real_input
     if beta_dep:
         beta_grid = np.asarray(state.beta, float)
         nbint = len(beta_grid) - 1
@@ -325,14 +409,15 @@ def build_model_tables(state, options, nx=50):
     w_resc[1:] += d / 2
 
     return ModelTables(
-        iaH=float(state.iaH), template_sigma8=float(state.template_sigma8),
+        iaH=float(state.iaH), template_sigma8=float(state.template_sigma8 or 1.0),
         vel_indep_AP=bool(options["velocity_independent_of_AP"]), rsd_model=rsd,
         n_ell=n_ell, ells=ells.astype(np.int32), beta_dependent=beta_dep, beta_fixed=0.40,
         knots=knots, origin=origin, upper=upper, inv_h=inv_h,
         bucket_base=base, maxscan=maxscan, beta_grid=beta_grid,
         xi_tab=np.ascontiguousarray(xi_tab), v0=v0, d0=d0, sv=sv,
         x=x, wx=w / np.sqrt(2 * np.pi), mu_resc=mu_resc, w_resc=w_resc,
-        from_data=bool(options["realspace_ccf_from_data"]),
+        vd_beta_dependent=vd_beta_dep, growth_mode=growth_mode, bias=bias,
+        sv2d=sv2d, sv_ybreaks=sv_ybreaks, from_data=bool(options["realspace_ccf_from_data"]),
         kaiser_approximation=bool(options.get("kaiser_approximation", False)),
         kaiser_coord_shift=bool(options.get("kaiser_coord_shift", True)), niter=5)
 
