@@ -620,7 +620,12 @@ int vb200_mix_probe(int device, int chains, int mix, int kind, int blocks_per_sm
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     double *d = nullptr;
-    CK(cudaMalloc(&d, sizeof(double)));
+    CK(cudaMalloc(&d, 128 * sizeof(double)));
+    {
+        double h[128];
+        for (int i = 0; i < 128; ++i) h[i] = (i < 33) ? 0.999999 - 1e-9 * i : 1e-9 + 1e-12 * i;
+        CK(cudaMemcpy(d, h, sizeof(h), cudaMemcpyHostToDevice));
+    }
     const int blocks = prop.multiProcessorCount * blocks_per_sm;
     typedef void (*fn_t)(double *, int, double, double, int);
     fn_t fn = nullptr;

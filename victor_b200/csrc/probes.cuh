@@ -94,9 +94,9 @@ __global__ void __launch_bounds__(128) k_mix_probe(double *out, int iters, doubl
         // kind 6 = two distinct register operands + an immediate, kind 7 = DMUL of two registers
         double y[kChains], z[kChains];
 #pragma unroll
-        for (int c = 0; c < kChains; ++c) {
-            y[c] = a + c * 1e-7;
-            z[c] = b + c * 1e-10;
+        for (int c = 0; c < kChains; ++c) {   // values the compiler cannot relate to each other
+            y[c] = out[1 + 2 * c + (threadIdx.x & 1)];
+            z[c] = out[33 + 2 * c + (threadIdx.x & 1)];
         }
         for (int i = 0; i < iters; ++i) {
 #pragma unroll
