@@ -325,6 +325,30 @@ def golden_linear_bias(victor):
     np.savez(os.path.join(OUT, "boss_linear_bias.npz"), **out, **meta())
 
 
+def golden_misc(victor):
+    """Direct model calls the notebooks make: odd multipoles (mu grid [-1, 1]), a bare
+    integer ``poles``, arbitrary s grids, theory_xi on unsorted / meshgrid inputs."""
+    model, data = boss_blocks()
+    ccf = victor.CCFFit(copy.deepcopy(model), copy.deepcopy(data))
+    p0 = {"fsigma8": 0.47, "beta": 0.37, "sigma_v": 380, "epsilon": 1.0}
+    p1 = {"fsigma8": 0.8, "beta": 0.45, "sigma_v": 250, "aperp": 1.03, "apar": 0.96}
+    s_fine = np.linspace(0.01, 120, 120)       # usage-demo cell 12
+    out = dict(s_fine=s_fine)
+    for tag, prm in (("p0", p0), ("p1", p1)):
+        out[f"{tag}_odd_012"] = ccf.theory_multipole_vector(ccf.s, dict(prm), [0, 1, 2])
+        out[f"{tag}_pole1"] = ccf.theory_multipole_vector(ccf.s, dict(prm), 1)
+        out[f"{tag}_fine_024"] = ccf.theory_multipole_vector(s_fine, dict(prm), [0, 2, 4])
+        mp = ccf.theory_multipoles(s_fine, dict(prm), poles=2)
+        out[f"{tag}_fine_bare2"] = mp["2"]
+    mu_u = np.array([0.9, 0.1, 0.5, 0.3, 0.7])
+    s_u = np.array([40.0, 10.0, 25.0, 80.0])
+    S, M = np.meshgrid(s_u, mu_u)
+    out["xi_unsorted"] = ccf.theory_xi(S, M, dict(p1))
+    out["xi_unsorted_s"], out["xi_unsorted_mu"] = s_u, mu_u
+    out["xi_negmu"] = ccf.theory_xi(ccf.s, np.linspace(-1, 1, 11), dict(p1))
+    np.savez(os.path.join(OUT, "boss_misc_calls.npz"), **out, **meta())
+
+
 def golden_example(victor):
     with open(os.path.join(REF, "config/example_model_input.yaml")) as fh:
         model = yaml.full_load(fh)["model"]
@@ -352,7 +376,7 @@ def golden_example(victor):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     v = refshim.install(REF)
-    which = sys.argv[1:] or ["boss", "more", "sv2d", "linear_bias", "example"]
+    which = sys.argv[1:] or ["boss", "more", "sv2d", "linear_bias", "misc", "example"]
     if "boss" in which:
         golden_boss(v)
     if "more" in which:
@@ -361,6 +385,8 @@ if __name__ == "__main__":
         golden_sv2d(v)
     if "linear_bias" in which:
         golden_linear_bias(v)
+    if "misc" in which:
+        golden_misc(v)
     if "example" in which:
         golden_example(v)
     for fn in sorted(os.listdir(OUT)):

@@ -431,3 +431,34 @@ def test_linear_bias_from_data(boss_blocks, golden):
     assert_theory(theory, g["measured_theory"], ns=len(fm.s))
     np.testing.assert_allclose(chi2, g["measured_chi2"], rtol=0, atol=CHI2_ATOL)
     fm.close()
+
+
+def test_direct_model_calls(fit, golden):
+    """Notebook-style calls: odd poles, bare-integer poles, fine s grid, theory_xi on
+    unsorted meshgrid input (sorted / uniqued like the reference) and at negative mu."""
+    g = golden("boss_misc_calls")
+    prm = {"p0": {"fsigma8": 0.47, "beta": 0.37, "sigma_v": 380, "epsilon": 1.0},
+           "p1": {"fsigma8": 0.8, "beta": 0.45, "sigma_v": 250, "aperp": 1.03, "apar": 0.96}}
+    for tag, p in prm.items():
+        assert_theory(fit.theory_multipole_vector(fit.s, dict(p), [0, 1, 2]), g[f"{tag}_odd_012"], ns=30)
+        assert_theory(fit.theory_multipole_vector(fit.s, dict(p), 1), g[f"{tag}_pole1"], ns=30)
+        assert_theory(fit.theory_multipole_vector(g["s_fine"], dict(p), [0, 2, 4]), g[f"{tag}_fine_024"], ns=120)
+        mp = fit.theory_multipoles(g["s_fine"], dict(p), poles=2)
+        assert list(mp) == ["2"]
+        assert_theory(mp["2"], g[f"{tag}_fine_bare2"], ns=120)
+    S, M = np.meshgrid(g["xi_unsorted_s"], g["xi_unsorted_mu"])
+    np.testing.assert_allclose(fit.theory_xi(S, M, dict(prm["p1"])), g["xi_unsorted"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(fit.theory_xi(fit.s, np.linspace(-1, 1, 11), dict(prm["p1"])), g["xi_negmu"],
+                               rtol=RTOL, atol=ATOL)
+
+
+def test_empty_and_large_batches(fit):
+    """n = 0 returns empty arrays; a 300k-row table runs as one launch (bench batches are 65,536)."""
+    lnl, chi2 = fit.log_likelihood_batch(np.empty((0, 5)))
+    assert lnl.shape == (0,) and chi2.shape == (0,)
+    from bench import synthetic_batch
+    P = synthetic_batch(300000, seed=5)
+    lnl, chi2 = fit.log_likelihood_batch(P)
+    assert np.all(np.isfinite(lnl)) and chi2.min() > 0
+    l2, c2 = fit.log_likelihood_batch(P[123456:123460])
+    assert np.array_equal(c2, chi2[123456:123460]) and np.array_equal(l2, lnl[123456:123460])

@@ -364,3 +364,28 @@ def test_tables_linear_bias_from_data(boss_blocks, golden):
     g = golden("boss_linear_bias")
     _tables_vs_golden(fm, {}, params_to_rows(g["measured_params"]), g["measured_theory"], g["measured_chi2"],
                       g["measured_lnl"])
+
+
+def test_direct_model_calls_from_tables(fit, golden):
+    """Odd multipoles (mu grid [-1, 1]), a bare integer pole, a fine caller-supplied s grid, xi(s, mu)
+    at negative mu -- the notebook-style calls of SURVEY.md 3.4 -- from the packed tables."""
+    from victor_b200 import tables as T
+    from victor_b200.model import params_to_rows
+    g = golden("boss_misc_calls")
+    mt = T.build_model_tables(fit, fit.model)
+    prm = {"p0": {"fsigma8": 0.47, "beta": 0.37, "sigma_v": 380, "epsilon": 1.0},
+           "p1": {"fsigma8": 0.8, "beta": 0.45, "sigma_v": 250, "aperp": 1.03, "apar": 0.96}}
+    s = np.asarray(fit.s, float)
+    for tag, p in prm.items():
+        rows = params_to_rows(dict(p))
+        for poles, key, grid in (([0, 1, 2], "odd_012", s), ([1], "pole1", s), ([0, 2, 4], "fine_024", g["s_fine"]),
+                                 ([2], "fine_bare2", g["s_fine"])):
+            mu, W = T.mu_projection_weights(poles)
+            assert (mu[0] == -1.0) == any(ell % 2 for ell in poles)
+            mult, _ = E.theory_multipoles(mt, rows, grid, mu, W)
+            np.testing.assert_allclose(mult.reshape(-1), g[f"{tag}_{key}"], rtol=RTOL, atol=ATOL)
+    rows = params_to_rows(dict(prm["p1"]))
+    xi = E.theory_xi(mt, rows, s, np.linspace(-1, 1, 11))[0]
+    np.testing.assert_allclose(xi, g["xi_negmu"], rtol=RTOL, atol=ATOL)
+    xi = E.theory_xi(mt, rows, np.sort(g["xi_unsorted_s"]), np.sort(g["xi_unsorted_mu"]))[0]
+    np.testing.assert_allclose(xi, g["xi_unsorted"], rtol=RTOL, atol=ATOL)

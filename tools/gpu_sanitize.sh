@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python tools/sanitize_target.py > gpurun_out/sanitize_plain.log 2>&1 || { echo "plain run failed"; tail -20 gpurun_out/sanitize_plain.log; exit 1; }
+timeout 600 compute-sanitizer --tool memcheck --log-file gpurun_out/memcheck.log python tools/sanitize_target.py > gpurun_out/sanitize_run.log 2>&1
+echo "sanitizer rc=$?"
+tail -5 gpurun_out/sanitize_run.log; tail -8 gpurun_out/memcheck.log

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--nsplit", type=int, default=0)
     ap.add_argument("--ilp", type=int, default=4)
     ap.add_argument("--expdeg", type=int, default=5)
+    ap.add_argument("--newton", type=int, default=3)
     ap.add_argument("--sigma-v", type=float, default=None, help="override the sigma_v column (access-pattern probe)")
     args = ap.parse_args()
     model, data = boss_blocks()
@@ -36,6 +37,7 @@ def main():
     eng.set_option("nsplit", args.nsplit)
     eng.set_option("ilp", args.ilp)
     eng.set_option("exp_degree", args.expdeg)
+    eng.set_option("newton", args.newton)
     n = args.batch
     dev = torch.device("cuda", 0)
     rows = params_to_rows(synthetic_batch(n))
@@ -53,7 +55,7 @@ def main():
         b.record()
         torch.cuda.synchronize()
         times.append(a.elapsed_time(b))
-    print(f"batch={n} fast={args.fast} threads={args.threads} nsplit={args.nsplit} ilp={args.ilp} expdeg={args.expdeg} sigma_v={args.sigma_v} "
+    print(f"batch={n} fast={args.fast} threads={args.threads} nsplit={args.nsplit} ilp={args.ilp} expdeg={args.expdeg} newton={args.newton} sigma_v={args.sigma_v} "
           f"ms={['%.3f' % t for t in times]} evals/s={n / (min(times) * 1e-3):.4g} "
           f"chi2[0]={float(d_chi2[0]):.10f}")
     fit.close()

@@ -93,7 +93,7 @@ struct vb200_ctx {
     std::vector<void *> owned;
     Scratch sc_params, sc_theory, sc_chi2, sc_lnl, sc_xi, sc_mult, sc_grid;
     // options
-    int opt_fast = 1, opt_nsplit = 0, opt_threads = 256, opt_ilp = 4, opt_expdeg = 5;
+    int opt_fast = 1, opt_nsplit = 0, opt_threads = 256, opt_ilp = 4, opt_expdeg = 5, opt_newton = 3;
     bool tuned = false;           // streaming + isotropic xi + model coordinates: the tuned kernel applies
     // small-call path (MCMC steps): page-locked staging for the rows in and (chi2 | lnL) out
     double *pin = nullptr, *d_small = nullptr;
@@ -137,7 +137,9 @@ typedef void (*k1_fn)(const K1Args);
 
 // Tuned streaming kernel variants in this build.  The default is <fast, U = 4, degree-5 exp>; the
 // others exist for parity tests (libm math) and for measurement (ILP, exp degree).
-k1_fn pick_k1(bool fast, bool flags, int ilp, int expdeg) {
+k1_fn pick_k1(bool fast, bool flags, int ilp, int expdeg, int newton = 3) {
+    if (fast && newton == 2 && ilp >= 4 && expdeg == 5)
+        return flags ? k_multipoles<K1Cfg<true, true, 4, 5, 2>> : k_multipoles<K1Cfg<true, false, 4, 5, 2>>;
     if (!fast) return flags ? k_multipoles<K1Cfg<false, true, 1, 6>> : k_multipoles<K1Cfg<false, false, 1, 6>>;
     if (flags) {
         if (ilp < 4) return k_multipoles<K1Cfg<true, true, 1, 5>>;
@@ -194,7 +196,7 @@ int launch_k1(vb200_ctx *c, const double *d_params, long long n, const double *d
     a.xi_out = d_xi;
     a.mult_out = d_mult;
     memcpy(a.xw, c->xw, sizeof(a.xw));
-    auto fn = c->tuned ? pick_k1(c->opt_fast != 0, c->has_flags, c->opt_ilp, c->opt_expdeg)
+    auto fn = c->tuned ? pick_k1(c->opt_fast != 0, c->has_flags, c->opt_ilp, c->opt_expdeg, c->opt_newton)
                        : pick_general(c->md.rsd_model);
     void *kargs[] = {(void *)&a};
     CK(cudaLaunchKernel((const void *)fn, dim3((unsigned)blocks), dim3(threads), kargs, smem, st));
@@ -387,6 +389,7 @@ int vb200_create(const vb200_model_tables *m, const vb200_fit_tables *f, int dev
     std::vector<const void *> fns;
     for (int v = 0; v < 32; ++v) fns.push_back((const void *)pick_k1(v & 1, v & 2, 1 << ((v >> 2) & 3), (v & 16) ? 5 : 6));
     for (int r = 0; r < 3; ++r) fns.push_back((const void *)pick_general(r));
+    for (int fl = 0; fl < 2; ++fl) fns.push_back((const void *)pick_k1(true, fl, 4, 5, 2));
     for (const void *fn : fns) {
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k1_smem_limit);
         if (e != cudaSuccess)
@@ -400,7 +403,10 @@ int vb200_set_option(vb200_ctx *c, const char *key, int64_t value) {
     if (!c || !key) return fail(VB200_EINVAL, "null argument");
     if (!strcmp(key, "fast_math")) c->opt_fast = value ? 1 : 0;
     else if (!strcmp(key, "nsplit")) c->opt_nsplit = (int)value;
-    else if (!strcmp(key, "ilp")) c->opt_ilp = value >= 4 ? 4 : (value >= 2 ? 2 : 1);
+    else if (!strcmp(key, "newton")) {
+        if (value != 2 && value != 3) return fail(VB200_EINVAL, "newton must be 2 (one Newton step) or 3 (cubic step)");
+        c->opt_newton = (int)value;
+    } else if (!strcmp(key, "ilp")) c->opt_ilp = value >= 4 ? 4 : (value >= 2 ? 2 : 1);
     else if (!strcmp(key, "exp_degree")) {
         if (value != 5 && value != 6) return fail(VB200_EINVAL, "exp_degree must be 5 or 6");
         c->opt_expdeg = (int)value;

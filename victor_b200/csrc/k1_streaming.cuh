@@ -31,15 +31,17 @@ __host__ __device__ inline size_t k1_smem_bytes(int ncell, int jper, int nmu, in
 
 // Compile-time variant.
 //   kFast  : hand-rolled rsqrt / rcp / exp (else CUDA libm).
+//   kNewton: 3 = cubic-convergence refinement of the MUFU seeds (default), 2 = one Newton step.
 //   kFlags : some bucket holds a knot in its interior, so the cell search may need the
 //            comparison path (non-lattice knot sets).
 //   kU     : velocity nodes processed together per loop trip (instruction-level parallelism; a warp
 //            must keep >= 4 independent DFMAs in flight to reach the FP64 issue rate).
 //   kExp   : degree of the exp remainder polynomial (6 = Taylor, 5 = economised).
-template <bool kFast_, bool kFlags_, int kU_, int kExp_>
+template <bool kFast_, bool kFlags_, int kU_, int kExp_, int kNewton_ = 3>
 struct K1Cfg {
     static constexpr bool kFast = kFast_, kFlags = kFlags_;
     static constexpr int kU = kU_, kExp = kExp_;
+    static constexpr int kMath = kFast_ ? (kNewton_ == 2 ? 2 : 1) : 0;
 };
 
 // per-thread loop invariants of the quadrature
@@ -61,7 +63,7 @@ __device__ __forceinline__ double quad_nodes(const K1Args &a, const QuadCtx &q, 
         xm[i] = a.xw[mi + i];                                 // uniform: constant-bank read
         const double rp = fma(-xm[i], q.kappa, q.Spar);       // ccf_model.py:648-650
         const double u2 = fma(rp, rp, q.Sperp2);              // :651
-        radius<C::kFast>(u2, rp, u[i], mur[i]);               // :651-652
+        radius<C::kMath>(u2, rp, u[i], mur[i]);               // :651-652
     }
 #pragma unroll
     for (int i = 0; i < U; ++i) {
@@ -89,7 +91,7 @@ __device__ __forceinline__ double quad_nodes(const K1Args &a, const QuadCtx &q, 
     for (int i = 0; i < U; ++i) {
         const double2 c89 = lds_f64x2(ra[i] + 64), cab = lds_f64x2(ra[i] + 80);
         const double sv = fma(fma(fma(cab.y, t[i], cab.x), t[i], c89.y), t[i], c89.x);   // :654-655
-        rq[i] = C::kFast ? rcp_cubic(sv) : 1.0 / sv;
+        rq[i] = C::kMath == 1 ? rcp_cubic(sv) : (C::kMath == 2 ? rcp_newton(sv) : 1.0 / sv);
     }
 #pragma unroll
     for (int i = 0; i < U; ++i) {
