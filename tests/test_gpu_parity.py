@@ -265,10 +265,13 @@ def test_full_batch_properties(fit):
                                      ("anisotropic", {"assume_isotropic": False})])
 def test_variant_models_golden(fit, golden, name, kw):
     g = golden("boss_variant_points")
-    lnl, chi2, theory = fit.log_likelihood_batch(g["params"], return_theory=True, **kw)
-    assert_theory(theory, g[f"{name}_theory"], ns=len(fit.s))
-    np.testing.assert_allclose(chi2, g[f"{name}_chi2"], rtol=0, atol=CHI2_ATOL)
-    np.testing.assert_allclose(lnl, g[f"{name}_lnl"], rtol=0, atol=CHI2_ATOL)
+    eng, _ = fit._fit_engine(kw)
+    for fast in (0, 1):          # libm arithmetic, then the hand-rolled rsqrt / reciprocal / exp (default)
+        eng.set_option("fast_math", fast)
+        lnl, chi2, theory = fit.log_likelihood_batch(g["params"], return_theory=True, **kw)
+        assert_theory(theory, g[f"{name}_theory"], ns=len(fit.s))
+        np.testing.assert_allclose(chi2, g[f"{name}_chi2"], rtol=0, atol=CHI2_ATOL)
+        np.testing.assert_allclose(lnl, g[f"{name}_lnl"], rtol=0, atol=CHI2_ATOL)
     a = golden("boss_notebook_anchors")
     l0, c0 = fit.log_likelihood({"fsigma8": 0.47, "beta": 0.37, "sigma_v": 380, "epsilon": 1.0}, **kw)
     assert abs(c0 - float(a[f"{name}_chi2"])) < CHI2_ATOL and abs(l0 - float(a[f"{name}_lnl"])) < CHI2_ATOL
@@ -462,3 +465,40 @@ def test_empty_and_large_batches(fit):
     assert np.all(np.isfinite(lnl)) and chi2.min() > 0
     l2, c2 = fit.log_likelihood_batch(P[123456:123460])
     assert np.array_equal(c2, chi2[123456:123460]) and np.array_equal(l2, lnl[123456:123460])
+
+
+def test_hostile_rows_do_not_break_the_context(fit, golden):
+    """Rows far outside any prior (zeros, negatives, huge values, inf, NaN in every column): every
+    table index must stay in range -- a stray access would surface as a CUDA error here or corrupt the
+    golden check that follows (compute-sanitizer is closed on this GPU pool, so this is the bounds test)."""
+    rng = np.random.default_rng(99)
+    base = np.array([0.47, 0.37, 380.0, 1.0, 1.0])
+    rows = [base.copy()]
+    for col in range(5):
+        for val in (0.0, -1.0, 1e-300, 1e-8, 1e8, 1e300, np.inf, -np.inf, np.nan):
+            r = base.copy()
+            r[col] = val
+            rows.append(r)
+    rows += list(np.abs(rng.standard_cauchy((200, 5))) * np.array([1.0, 0.5, 400.0, 1.0, 1.0]))
+    P = np.array(rows)
+    for kw in ({}, {"rsd_model": "dispersion"}, {"rsd_model": "kaiser"}, {"assume_isotropic": False}):
+        lnl, chi2 = fit.log_likelihood_batch(P, **kw)
+        assert lnl.shape == (len(P),)
+        bad = ~np.isfinite(lnl)
+        assert np.all(chi2[bad] == np.inf) and np.all(lnl[bad] == -np.inf)      # ccf_fit.py:477-481
+    g = golden("boss_streaming_points")
+    lnl, chi2 = fit.log_likelihood_batch(g["params"])
+    np.testing.assert_allclose(chi2, g["chi2"], rtol=0, atol=CHI2_ATOL)
+
+
+def test_long_s_grids_split_over_blocks(fit):
+    """A 1500-point s grid for many rows: the library splits the s range over blocks by itself and
+    the rows agree with the same s values evaluated in short grids."""
+    s = np.linspace(1.0, 150.0, 1500)
+    from bench import synthetic_batch
+    P = synthetic_batch(65536)[:1000]
+    big = fit.theory_multipole_vector_batch(s, P, poles=[0, 2])
+    assert big.shape == (1000, 3000) and np.all(np.isfinite(big))
+    part = fit.theory_multipole_vector_batch(s[400:420], P[:7], poles=[0, 2])
+    np.testing.assert_array_equal(part[:, :20], big[:7, 400:420])
+    np.testing.assert_array_equal(part[:, 20:], big[:7, 1900:1920])

@@ -28,10 +28,17 @@ def main():
     ap.add_argument("--expdeg", type=int, default=5)
     ap.add_argument("--newton", type=int, default=3)
     ap.add_argument("--sigma-v", type=float, default=None, help="override the sigma_v column (access-pattern probe)")
+    ap.add_argument("--rsd", default="streaming", help="rsd_model (general kernel for anything but streaming)")
+    ap.add_argument("--aniso", type=int, default=0, help="1: assume_isotropic False (general kernel)")
     args = ap.parse_args()
     model, data = boss_blocks()
     fit = CCFFit(model, data, device=0)
-    eng, _ = fit._fit_engine({})
+    kw = {}
+    if args.rsd != "streaming":
+        kw["rsd_model"] = args.rsd
+    if args.aniso:
+        kw["assume_isotropic"] = False
+    eng, _ = fit._fit_engine(kw)
     eng.set_option("fast_math", args.fast)
     eng.set_option("threads", args.threads)
     eng.set_option("nsplit", args.nsplit)
@@ -55,7 +62,7 @@ def main():
         b.record()
         torch.cuda.synchronize()
         times.append(a.elapsed_time(b))
-    print(f"batch={n} fast={args.fast} threads={args.threads} nsplit={args.nsplit} ilp={args.ilp} expdeg={args.expdeg} newton={args.newton} sigma_v={args.sigma_v} "
+    print(f"batch={n} fast={args.fast} threads={args.threads} nsplit={args.nsplit} ilp={args.ilp} expdeg={args.expdeg} newton={args.newton} sigma_v={args.sigma_v} rsd={args.rsd} aniso={args.aniso} "
           f"ms={['%.3f' % t for t in times]} evals/s={n / (min(times) * 1e-3):.4g} "
           f"chi2[0]={float(d_chi2[0]):.10f}")
     fit.close()

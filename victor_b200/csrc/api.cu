@@ -7,6 +7,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/victor_b200.h"
 #include "k1_general.cuh"
 #include "k1_streaming.cuh"
@@ -31,6 +33,12 @@ int fail(int code, const std::string &msg) {
         if (e__ != cudaSuccess)                                                               \
             return fail(VB200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));    \
     } while (0)
+
+// NVTX range for the life of a call: shows up in Nsight tools, costs nothing without one attached
+struct Range {
+    explicit Range(const char *name) { nvtxRangePushA(name); }
+    ~Range() { nvtxRangePop(); }
+};
 
 struct DeviceGuard {
     int prev = -1;
@@ -150,10 +158,12 @@ k1_fn pick_k1(bool fast, bool flags, int ilp, int expdeg, int newton = 3) {
     return expdeg == 5 ? k_multipoles<K1Cfg<true, false, 4, 5>> : k_multipoles<K1Cfg<true, false, 4, 6>>;
 }
 
-k1_fn pick_general(int rsd_model) {
-    if (rsd_model == kRsdStreaming) return k_multipoles_general<kRsdStreaming>;
-    if (rsd_model == kRsdDispersion) return k_multipoles_general<kRsdDispersion>;
-    return k_multipoles_general<kRsdKaiser>;
+k1_fn pick_general(int rsd_model, bool fast) {
+    if (rsd_model == kRsdStreaming)
+        return fast ? k_multipoles_general<kRsdStreaming, true> : k_multipoles_general<kRsdStreaming, false>;
+    if (rsd_model == kRsdDispersion)
+        return fast ? k_multipoles_general<kRsdDispersion, true> : k_multipoles_general<kRsdDispersion, false>;
+    return fast ? k_multipoles_general<kRsdKaiser, true> : k_multipoles_general<kRsdKaiser, false>;
 }
 
 int launch_k1(vb200_ctx *c, const double *d_params, long long n, const double *d_s, int ns,
@@ -169,12 +179,19 @@ int launch_k1(vb200_ctx *c, const double *d_params, long long n, const double *d
     }
     nsplit = std::max(1, std::min(nsplit, ns));
     int jper = (ns + nsplit - 1) / nsplit;
+    auto smem_for = [&](int jp) {
+        return c->tuned ? k1_smem_bytes(c->md.ncell, jp, nmu, c->md.nbucket)
+                        : k1g_smem_bytes(c->md.ncell, jp, nmu, c->md.nbucket);
+    };
+    // long s grids: split further until a block's xi(s, mu) stage leaves room for 4 blocks per SM
+    // (or, failing that, at least fits)
+    const size_t want = std::min<size_t>(c->k1_smem_limit, (size_t)56 * 1024);
+    while (jper > 1 && smem_for(jper) > want) jper = (jper + 1) / 2;
     nsplit = (ns + jper - 1) / jper;
     const int npairs = jper * nmu;
     int threads = std::min(c->opt_threads, ((npairs + 31) / 32) * 32);
     threads = std::max(32, std::min(threads, 256));
-    const size_t smem = c->tuned ? k1_smem_bytes(c->md.ncell, jper, nmu, c->md.nbucket)
-                                 : k1g_smem_bytes(c->md.ncell, jper, nmu, c->md.nbucket);
+    const size_t smem = smem_for(jper);
     if (smem > c->k1_smem_limit)
         return fail(VB200_EUNSUPPORTED, "grids too large for one block's shared memory (reduce len(s) * len(mu))");
     const long long blocks = n * nsplit;
@@ -197,7 +214,7 @@ int launch_k1(vb200_ctx *c, const double *d_params, long long n, const double *d
     a.mult_out = d_mult;
     memcpy(a.xw, c->xw, sizeof(a.xw));
     auto fn = c->tuned ? pick_k1(c->opt_fast != 0, c->has_flags, c->opt_ilp, c->opt_expdeg, c->opt_newton)
-                       : pick_general(c->md.rsd_model);
+                       : pick_general(c->md.rsd_model, c->opt_fast != 0);
     void *kargs[] = {(void *)&a};
     CK(cudaLaunchKernel((const void *)fn, dim3((unsigned)blocks), dim3(threads), kargs, smem, st));
     CK(cudaGetLastError());
@@ -388,7 +405,7 @@ int vb200_create(const vb200_model_tables *m, const vb200_fit_tables *f, int dev
     c->k1_smem_limit = std::min<size_t>((size_t)prop.sharedMemPerBlockOptin, (size_t)200 * 1024);
     std::vector<const void *> fns;
     for (int v = 0; v < 32; ++v) fns.push_back((const void *)pick_k1(v & 1, v & 2, 1 << ((v >> 2) & 3), (v & 16) ? 5 : 6));
-    for (int r = 0; r < 3; ++r) fns.push_back((const void *)pick_general(r));
+    for (int r = 0; r < 6; ++r) fns.push_back((const void *)pick_general(r >> 1, r & 1));
     for (int fl = 0; fl < 2; ++fl) fns.push_back((const void *)pick_k1(true, fl, 4, 5, 2));
     for (const void *fn : fns) {
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k1_smem_limit);
@@ -434,6 +451,7 @@ int vb200_theory(vb200_ctx *c, const double *params, int64_t n, const double *s,
     if (mult_out && (!wmu || L < 1 || L > VB200_MAX_POLES)) return fail(VB200_EINVAL, "mult_out needs wmu and 1 <= L <= 3");
     if (!xi_out && !mult_out) return fail(VB200_EINVAL, "no output requested");
     if (n == 0) return VB200_OK;
+    Range range("vb200_theory");
     DeviceGuard g(c->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     bool host_io = false;
@@ -492,6 +510,7 @@ int vb200_likelihood(vb200_ctx *c, const double *params, int64_t n, double *theo
     if (n < 0 || !params) return fail(VB200_EINVAL, "bad arguments");
     if (!theory && !chi2 && !lnlike) return fail(VB200_EINVAL, "no output requested");
     if (n == 0) return VB200_OK;
+    Range range("vb200_likelihood");
     DeviceGuard g(c->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int p = c->fd.p;

@@ -6,7 +6,8 @@
 //   sigma_v(r, mu) dispersion templates         victor/ccf_model.py:654-655, 667-668 (3 template keys)
 // and the streaming model combined with the last two.  Same tiling as the tuned kernel (one block
 // per parameter row x s-range, one thread per (s_j, mu_k) pair, velocity nodes in registers), plain
-// CUDA libm arithmetic (sqrt, divide, exp): these variants are written for parity first.
+// the same hand-rolled rsqrt / reciprocal / exp as the tuned kernel (kFast) or CUDA libm (a test
+// variant: both must pass parity).  No instruction-level tuning beyond that.
 #pragma once
 #include "common.cuh"
 
@@ -18,7 +19,7 @@ constexpr int kRecG = 26;
 constexpr int kGXi = 0, kGV0 = 12, kGD0 = 16, kGSV = 20, kGOrg = 24;
 
 __host__ __device__ inline size_t k1g_smem_bytes(int ncell, int jper, int nmu, int nbucket) {
-    size_t d = (size_t)ncell * (kRecG + 1) + (size_t)jper * nmu + 8;
+    size_t d = (size_t)ncell * (kRecG + 1) + kExpTab + (size_t)jper * nmu + 8;
     return d * sizeof(double) + (size_t)nbucket * sizeof(int);
 }
 
@@ -85,13 +86,34 @@ __device__ __forceinline__ double xi_real(const GenCtx &g, const double *r, doub
     return xi;
 }
 
-template <int kModel>
+// arithmetic of the general kernel: hand-rolled (MUFU seed + cubic step, table exp) or libm
+template <bool kFast>
+struct GMath {
+    // u = sqrt(u2), iu = 1 / u
+    static __device__ __forceinline__ void root(double u2, double &u, double &iu) {
+        if (kFast) {
+            iu = fast_rsqrt(u2);
+            u = u2 * iu;
+        } else {
+            u = sqrt(u2);
+            iu = 1.0 / u;
+        }
+    }
+    static __device__ __forceinline__ double div(double a, double b) { return kFast ? a * rcp_cubic(b) : a / b; }
+    static __device__ __forceinline__ double gauss(double z2, unsigned etab_s) {
+        return kFast ? gauss_tab<5>(z2, etab_s) : exp(-0.5 * z2);
+    }
+};
+
+template <int kModel, bool kFast>
 __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constant__ K1Args a) {
+    using M = GMath<kFast>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const ModelDev &m = a.m;
     const int ncell = m.ncell, nx = m.nx;
     double *rec = reinterpret_cast<double *>(smem_raw);
-    double *stage = rec + (size_t)ncell * kRecG;
+    double *etab = rec + (size_t)ncell * kRecG;
+    double *stage = etab + kExpTab;
     double *scal = stage + (size_t)a.jper * a.nmu;
     double *upper = scal + 8;
     int *bbase = reinterpret_cast<int *>(upper + ncell);
@@ -110,6 +132,8 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
     row_scalars_to_shared(m, pr, scal, tid);
     for (int i = tid; i < ncell; i += nthr) upper[i] = m.upper[i];
     for (int i = tid; i < m.nbucket; i += nthr) bbase[i] = m.bucket_base[i];
+    if (tid < kExpTab) etab[tid] = m.exp_tab[tid];
+    const unsigned etab_s = (unsigned)__cvta_generic_to_shared(etab);
     {
         int kb = 0;
         double tb = 0.0;
@@ -179,10 +203,11 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
         auto xi_at = [&](double rp, double u, double mur, const double *rcell, double t) {
             if (!m.from_data) return xi_real(g, rcell, t, mur);
             const double rpd = rp * f_over_apar;                       // r_par / apar      (:675)
-            const double rd = sqrt(rpd * rpd + rt_data * rt_data);     // (:677)
+            double rd, ird;
+            M::root(rpd * rpd + rt_data * rt_data, rd, ird);           // (:677)
             double td;
             const double *rc = locate(g, rd, td);
-            return xi_real(g, rc, td, rpd / rd);                       // (:678-687)
+            return xi_real(g, rc, td, kFast ? rpd * ird : rpd / rd);   // (:678-687)
         };
 
         if (kModel == kRsdStreaming) {
@@ -190,43 +215,57 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
             for (int mi = 0; mi < nx; ++mi) {
                 const double xm = a.xw[mi], wm = a.xw[kMaxNx + mi];
                 const double rp = Spar - xm * kappa;                   // :648
-                const double u = sqrt(Sperp2 + rp * rp);               // :651
-                const double mur = rp / u;                             // :652
+                double u, iu;
+                M::root(Sperp2 + rp * rp, u, iu);                      // :651
+                const double mur = kFast ? rp * iu : rp / u;           // :652
                 double t;
                 const double *rc = locate(g, u, t);
                 const double sv = sv_at(g, rc, t, mur);                // :654-655
-                const double z = (xm - B * horner3(rc + kGV0, t) * mur) / sv;   // :656
+                const double isv = kFast ? rcp_cubic(sv) : 1.0 / sv;
+                const double d = xm - B * horner3(rc + kGV0, t) * mur;
+                const double z = kFast ? d * isv : d / sv;             // :656
                 const double xi = xi_at(rp, u, mur, rc, t);
-                acc += wm * (1.0 + xi) * exp(-0.5 * z * z) / sv;       // :690
+                const double pdf = M::gauss(z * z, etab_s);
+                acc += kFast ? wm * (1.0 + xi) * pdf * isv : wm * (1.0 + xi) * pdf / sv;   // :690
             }
             result = acc - 1.0;
         } else if (kModel == kRsdDispersion) {
             // ccf_model.py:659-671
-            const double Strue = sqrt(Sperp2 + Spar * Spar);
+            double Strue, iS;
+            M::root(Sperp2 + Spar * Spar, Strue, iS);
             double t0;
             const double *r0 = locate(g, Strue, t0);
-            const double first = 1.0 + G * horner3(r0 + kGV0, t0) / Strue;
+            const double first = kFast ? fma(G * horner3(r0 + kGV0, t0), iS, 1.0)
+                                       : 1.0 + G * horner3(r0 + kGV0, t0) / Strue;
+            const double ifirst = kFast ? rcp_cubic(first) : 0.0;
             double acc = 0.0;
             for (int mi = 0; mi < nx; ++mi) {
                 const double xm = a.xw[mi], wm = a.xw[kMaxNx + mi];
                 const double num = Spar - xm * kappa;
-                double rp = num / first;
-                double u, t;
+                double rp = kFast ? num * ifirst : num / first;
+                double u, iu, t;
                 const double *rc;
                 for (int it = 0; it < m.niter; ++it) {
-                    u = sqrt(Sperp2 + rp * rp);
+                    M::root(Sperp2 + rp * rp, u, iu);
                     rc = locate(g, u, t);
-                    rp = num / (1.0 + G * horner3(rc + kGV0, t) / u);
+                    rp = kFast ? num * rcp_cubic(fma(G * horner3(rc + kGV0, t), iu, 1.0))
+                               : num / (1.0 + G * horner3(rc + kGV0, t) / u);
                 }
-                u = sqrt(Sperp2 + rp * rp);
-                const double mur = rp / u;
+                M::root(Sperp2 + rp * rp, u, iu);
+                const double mur = kFast ? rp * iu : rp / u;
                 rc = locate(g, u, t);
                 const double sv = sv_at(g, rc, t, mur);                // :667-668
-                const double v0u = horner3(rc + kGV0, t) / u;
-                const double jac = 1.0 / (1.0 + G * v0u + G * mur * mur * (horner3(rc + kGD0, t) - v0u));
-                const double z = xm / sv;
+                const double v0u = kFast ? horner3(rc + kGV0, t) * iu : horner3(rc + kGV0, t) / u;
+                const double jd = 1.0 + G * v0u + G * mur * mur * (horner3(rc + kGD0, t) - v0u);
                 const double xi = xi_at(rp, u, mur, rc, t);
-                acc += wm * (1.0 + xi) * jac * exp(-0.5 * z * z) / sv;
+                if (kFast) {
+                    const double isv = rcp_cubic(sv);
+                    const double z = xm * isv;
+                    acc += wm * (1.0 + xi) * rcp_cubic(jd) * M::gauss(z * z, etab_s) * isv;
+                } else {
+                    const double z = xm / sv;
+                    acc += wm * (1.0 + xi) * (1.0 / jd) * exp(-0.5 * z * z) / sv;
+                }
             }
             result = acc - 1.0;
         } else {
@@ -235,27 +274,31 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
             double rp = Spar;
             double u, t;
             const double *rc;
+            double iu;
             if (m.kaiser_shift) {
-                const double Strue = sqrt(Sperp2 + Spar * Spar);
+                double Strue;
+                M::root(Sperp2 + Spar * Spar, Strue, iu);
                 rc = locate(g, Strue, t);
-                rp = Spar / (1.0 + MG * horner3(rc + kGV0, t) / Strue);
+                rp = kFast ? Spar * rcp_cubic(fma(MG * horner3(rc + kGV0, t), iu, 1.0))
+                           : Spar / (1.0 + MG * horner3(rc + kGV0, t) / Strue);
                 for (int it = 0; it < m.niter; ++it) {
-                    u = sqrt(Sperp2 + rp * rp);
+                    M::root(Sperp2 + rp * rp, u, iu);
                     rc = locate(g, u, t);
-                    rp = Spar / (1.0 + MG * horner3(rc + kGV0, t) / u);
+                    rp = kFast ? Spar * rcp_cubic(fma(MG * horner3(rc + kGV0, t), iu, 1.0))
+                               : Spar / (1.0 + MG * horner3(rc + kGV0, t) / u);
                 }
             }
-            u = sqrt(Sperp2 + rp * rp);
-            const double mur = rp / u;
+            M::root(Sperp2 + rp * rp, u, iu);
+            const double mur = kFast ? rp * iu : rp / u;
             rc = locate(g, u, t);
-            const double v0u = horner3(rc + kGV0, t) / u;
+            const double v0u = kFast ? horner3(rc + kGV0, t) * iu : horner3(rc + kGV0, t) / u;
             const double ca = (m.rsd_model == kRsdEuclid) ? 3.0 : 1.0, cb = (m.rsd_model == kRsdEuclid) ? 2.0 : 1.0;
             const double J = ca * MG * v0u + cb * MG * Qk * mur * mur * (horner3(rc + kGD0, t) - v0u);
             const double xi = xi_at(rp, u, mur, rc, t);
             if (m.rsd_model == kRsdEuclid || m.kaiser_approx)
                 result = Mk * xi - J;
             else
-                result = (1.0 + Mk * xi) / (1.0 + J) - 1.0;
+                result = M::div(1.0 + Mk * xi, 1.0 + J) - 1.0;
         }
         stage[pidx] = result;
     }
