@@ -213,6 +213,8 @@ int launch_k1(vb200_ctx *c, const double *d_params, long long n, const double *d
     a.xi_out = d_xi;
     a.mult_out = d_mult;
     memcpy(a.xw, c->xw, sizeof(a.xw));
+    if (c->tuned && c->opt_fast)   // the fast kernel's reciprocal of SV carries sqrt(16 log2 e): take it out of the weights
+        for (int i = 0; i < c->md.nx; ++i) a.xw[kMaxNx + i] = c->xw[kMaxNx + i] / kGaussScale;
     auto fn = c->tuned ? pick_k1(c->opt_fast != 0, c->has_flags, c->opt_ilp, c->opt_expdeg, c->opt_newton)
                        : pick_general(c->md.rsd_model, c->opt_fast != 0);
     void *kargs[] = {(void *)&a};

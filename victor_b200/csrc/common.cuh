@@ -189,6 +189,37 @@ __device__ __forceinline__ double gauss_tab(double z2, unsigned etab_s) {
     return p * t;
 }
 
+// the same with the argument pre-scaled: zs = z sqrt(16 log2 e), so that -z^2/2 = -(zs^2) ln2 / 32.
+// zs^2 only ever appears inside an FMA (exact product, one instruction and four register reads
+// fewer than forming z^2 first).  kGaussScale is folded into the sigma_v table by the caller.
+constexpr double kGaussScale = 4.804489635145799;   // sqrt(16 log2(e))
+template <int kDeg>
+__device__ __forceinline__ double gauss_tab_scaled(double zs, unsigned etab_s) {
+    const double kMagic = 6755399441055744.0;   // 1.5 * 2^52
+    const double tn = fma(-zs, zs, kMagic);
+    const int ni = __double2loint(tn);
+    const double nf = tn - kMagic;
+    const double r = fma(-zs, zs, -nf);
+    double p;
+    if (kDeg == 6) {
+        p = fma(kExpPoly[5], r, kExpPoly[4]);
+        p = fma(p, r, kExpPoly[3]);
+        p = fma(p, r, kExpPoly[2]);
+        p = fma(p, r, kExpPoly[1]);
+        p = fma(p, r, kExpPoly[0]);
+    } else {
+        p = fma(kExpPoly5[4], r, kExpPoly5[3]);
+        p = fma(p, r, kExpPoly5[2]);
+        p = fma(p, r, kExpPoly5[1]);
+        p = fma(p, r, kExpPoly5[0]);
+    }
+    p = fma(p, r, 1.0);
+    const int n = max(ni >> 5, -1000);
+    double t = lds_f64(etab_s + ((ni & (kExpTab - 1)) << 3));
+    t = __hiloint2double(__double2hiint(t) + (n << 20), __double2loint(t));
+    return p * t;
+}
+
 // keep a value in a register: the compiler cannot re-derive the result of a volatile asm, so it
 // stops re-materialising loop invariants (shared-window base, reciprocal spacing) inside the loop
 __device__ __forceinline__ unsigned pin_u32(unsigned v) {
@@ -205,16 +236,13 @@ __device__ __forceinline__ double pin_f64(double v) {
 // ---------------------------------------------------------------------------------------
 // pieces shared by both K1 kernels
 // ---------------------------------------------------------------------------------------
-struct RowScalars {
-    double f;        // template rescaling factor (ccf_model.py:606-613)
-    double sperp_f;  // aperp / f
-    double spar_f;   // apar / f
-    double kappa;    // sigma_v iaH apar / f : displacement in u-units per unit x
-    double B;        // A_v / sigma_v, A_v = -(fs8 / s8_t) / (3 iaH apar)      (:419, 435, 449)
-    double G;        // iaH apar A_v / f = -(fs8 / s8_t) / (3 f)   (dispersion / kaiser terms)
-    double apar, aperp;
-};
-
+// per-row scalars, scal[8] in shared memory:
+//   [0] f        template rescaling factor (ccf_model.py:606-613)
+//   [1] aperp/f  [2] apar/f
+//   [3] kappa    sigma_v iaH apar / f : displacement in u-units per unit x
+//   [4] B        A_v / sigma_v, A_v = -growth / (3 iaH apar)               (:419, 435, 449)
+//   [5] G        iaH apar A_v / f = -growth / (3 f)   (dispersion / kaiser terms)
+//   [6] apar     [7] aperp
 // warp 0 of the block computes the scalars of parameter row `pr` into shared `scal[8]`
 __device__ __forceinline__ void row_scalars_to_shared(const ModelDev &m, const double *pr, double *scal, int tid) {
     const double fs8 = pr[0], sigv = pr[2], aperp = pr[3], apar = pr[4], astar = pr[5];

@@ -56,7 +56,7 @@ struct QuadCtx {
 // dependency chains are interleaved in program order (DFMA latency 8.5 cycles, issue every 2.2).
 template <class C, int U>
 __device__ __forceinline__ double quad_nodes(const K1Args &a, const QuadCtx &q, int mi, double acc) {
-    double xm[U], u[U], mur[U], t[U], rq[U], z2[U], g[U];
+    double xm[U], u[U], mur[U], t[U], rq[U], z2[U], g[U];   // kFast: z2 holds zs = z sqrt(16 log2 e), not z^2
     unsigned ra[U];
 #pragma unroll
     for (int i = 0; i < U; ++i) {
@@ -97,11 +97,11 @@ __device__ __forceinline__ double quad_nodes(const K1Args &a, const QuadCtx &q, 
     for (int i = 0; i < U; ++i) {
         const double2 c45 = lds_f64x2(ra[i] + 32), c67 = lds_f64x2(ra[i] + 48);
         const double vb = fma(fma(fma(c67.y, t[i], c67.x), t[i], c45.y), t[i], c45.x);   // :635, :656
-        const double z = fma(-vb, mur[i], xm[i]) * rq[i];
-        z2[i] = z * z;
+        const double z = fma(-vb, mur[i], xm[i]) * rq[i];   // kFast: rq = sqrt(16 log2 e) / SV (scaled table)
+        z2[i] = C::kFast ? z : z * z;
     }
 #pragma unroll
-    for (int i = 0; i < U; ++i) g[i] = C::kFast ? gauss_tab<C::kExp>(z2[i], q.etab_s) : exp(-0.5 * z2[i]);
+    for (int i = 0; i < U; ++i) g[i] = C::kFast ? gauss_tab_scaled<C::kExp>(z2[i], q.etab_s) : exp(-0.5 * z2[i]);
 #pragma unroll
     for (int i = 0; i < U; ++i) {
         const double2 c01 = lds_f64x2(ra[i]), c23 = lds_f64x2(ra[i] + 16);
@@ -160,7 +160,9 @@ __global__ void __launch_bounds__(256, 4) k_multipoles(const __grid_constant__ K
             double *r = rec + cell * kRec;
             r[c] = v;
             r[4 + c] = B * m.v0[i];
-            r[8 + c] = m.sv[i];
+            // kFast: SV / sqrt(16 log2 e), so that its reciprocal carries the scale of the exp argument
+            // (the weights a.xw are divided by the same constant on the host)
+            r[8 + c] = C::kFast ? m.sv[i] * (1.0 / kGaussScale) : m.sv[i];
             if (c == 0) {
                 r[12] = m.origin[cell];
                 r[13] = 0.0;
