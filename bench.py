@@ -325,10 +325,14 @@ def run_gpu(args):
             "peak_nominal": FP64_NOMINAL_TFLOPS, "frac_of_nominal": achieved / FP64_NOMINAL_TFLOPS,
             "flop_per_eval": FLOP_K1_PER_EVAL, "kernel_ms": k1_avg_ms,
             # how full the FP64 pipe is under the issue model measured on this chip (tools/probe_mix.py,
-            # tools/sass_opcycles.py): 38 FP64 instructions per quadrature point, 11.2 of them with three
-            # register operands (3 cycles each, the others 2) = 87.2 pipe cycles per warp-point
-            "fp64_pipe": {"instr_per_point": 38.0, "model_cycles_per_warp_point": 87.2,
-                          "frac_of_pipe": (n * NS * NMU * NX / 32.0) * 87.2
+            # tools/sass_opcycles.py): 37 FP64 instructions per quadrature point, 10.5 of them with three
+            # register operands (3 cycles each, the others 2) = 84.5 pipe cycles per warp-point; and the
+            # register-file read model (tools/sass_regreads.py): 213.5 32-bit reads = 106.8 cycles
+            "fp64_pipe": {"instr_per_point": 37.0, "model_cycles_per_warp_point": 84.5,
+                          "regfile_cycles_per_warp_point": 106.8,
+                          "frac_of_regfile": (n * NS * NMU * NX / 32.0) * 106.8
+                          / (148 * 4 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6) / (k1_avg_ms * 1e-3),
+                          "frac_of_pipe": (n * NS * NMU * NX / 32.0) * 84.5
                           / (148 * 4 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6) / (k1_avg_ms * 1e-3)},
             "hbm_gbs_algorithmic": n * BYTES_PER_EVAL / (k1_avg_ms * 1e-3) / 1e9,
             "traffic": None,
