@@ -349,6 +349,49 @@ def golden_misc(victor):
     np.savez(os.path.join(OUT, "boss_misc_calls.npz"), **out, **meta())
 
 
+def golden_fixed(victor):
+    """No reconstruction anywhere: 1-D real-space multipoles, 1-D data multipoles, one covariance
+    matrix (ccf_model.py:105-111, ccf_fit.py:60-64, 130-133).  No shipped file is laid out like that, so
+    row 12 of the BOSS tables is written out as 1-D arrays; inputs saved next to the outputs."""
+    import tempfile
+    from victor_b200.io_hdf5 import read_hdf5
+    model, data = boss_blocks()
+    msrc = read_hdf5(os.path.join(REF, model["input_model_data_file"]))
+    dsrc = read_hdf5(os.path.join(REF, data["redshift_space_ccf"]["data_file"]))
+    csrc = read_hdf5(os.path.join(REF, "data/BOSS_DR12_CMASS_data/"
+                                       "CMASS_zobovVoids_reconRs10_0.43z0.7_medianRvcut_fixed_D_covariance.hdf5"))
+    minp = {k: v for k, v in msrc.items() if k != "beta"}
+    minp["monopole"], minp["quadrupole"] = msrc["monopole"][12], msrc["quadrupole"][12]
+    dinp = {"s": dsrc["s"], "monopole": dsrc["monopole"][12], "quadrupole": dsrc["quadrupole"][12]}
+    np.savez(os.path.join(OUT, "fixed_inputs_model.npz"), **minp)
+    np.savez(os.path.join(OUT, "fixed_inputs_data.npz"), **dinp)
+    np.savez(os.path.join(OUT, "fixed_inputs_cov.npz"), covmat=csrc["covmat"])
+    tmp = tempfile.mkdtemp()
+    for name, arrs in (("m.npy", minp), ("d.npy", dinp), ("c.npy", {"covmat": csrc["covmat"]})):
+        np.save(os.path.join(tmp, name), arrs, allow_pickle=True)
+    mm, dd = copy.deepcopy(model), copy.deepcopy(data)
+    mm["dir"] = dd["dir"] = tmp
+    mm["input_model_data_file"] = "m.npy"
+    mm["realspace_ccf"]["reconstruction"] = False
+    dd["redshift_space_ccf"].update(reconstruction=False, data_file="d.npy")
+    dd["covariance_matrix"] = {"data_file": "c.npy", "cov_key": "covmat"}
+    ccf = victor.CCFFit(mm, dd)
+    P = np.vstack([synthetic_batch(65536)[:5], edge_rows(ccf.r * 0 + 0.4)[[0, 8, 9]]])
+    out = dict(params=P)
+    for name, kw in (("streaming", {}), ("dispersion", {"rsd_model": "dispersion"}),
+                     ("gaussian", {"likelihood": {"form": "gaussian"}})):
+        th, c2, ll = [], [], []
+        for row in P:
+            prm = row_to_params(row)
+            del prm["beta"]                       # no beta anywhere: the reference must not need it
+            th.append(ccf.theory_multipole_vector(ccf.s, dict(prm), ccf.poles_s, **kw))
+            a, b = ccf.log_likelihood(dict(prm), **kw)
+            ll.append(a)
+            c2.append(b)
+        out[f"{name}_theory"], out[f"{name}_chi2"], out[f"{name}_lnl"] = np.array(th), np.array(c2), np.array(ll)
+    np.savez(os.path.join(OUT, "boss_fixed_everything.npz"), **out, **meta())
+
+
 def golden_example(victor):
     with open(os.path.join(REF, "config/example_model_input.yaml")) as fh:
         model = yaml.full_load(fh)["model"]
@@ -376,7 +419,7 @@ def golden_example(victor):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     v = refshim.install(REF)
-    which = sys.argv[1:] or ["boss", "more", "sv2d", "linear_bias", "misc", "example"]
+    which = sys.argv[1:] or ["boss", "more", "sv2d", "linear_bias", "misc", "fixed", "example"]
     if "boss" in which:
         golden_boss(v)
     if "more" in which:
@@ -387,6 +430,8 @@ if __name__ == "__main__":
         golden_linear_bias(v)
     if "misc" in which:
         golden_misc(v)
+    if "fixed" in which:
+        golden_fixed(v)
     if "example" in which:
         golden_example(v)
     for fn in sorted(os.listdir(OUT)):

@@ -503,3 +503,26 @@ def test_long_s_grids_split_over_blocks(fit):
     part = fit.theory_multipole_vector_batch(s[400:420], P[:7], poles=[0, 2])
     np.testing.assert_array_equal(part[:, :20], big[:7, 400:420])
     np.testing.assert_array_equal(part[:, 20:], big[:7, 1900:1920])
+
+
+@pytest.mark.parametrize("name,kw", [("streaming", {}), ("dispersion", {"rsd_model": "dispersion"}),
+                                     ("gaussian", {"likelihood": {"form": "gaussian"}})])
+def test_no_reconstruction_anywhere(boss_blocks, golden, name, kw):
+    """Fixed real-space input, fixed data vector, one covariance matrix; beta is not a parameter."""
+    from victor_b200 import CCFFit
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["input_model_data_file"] = "tests/golden/fixed_inputs_model.npz"
+    model["realspace_ccf"]["reconstruction"] = False
+    data["redshift_space_ccf"].update(reconstruction=False, data_file="tests/golden/fixed_inputs_data.npz")
+    data["covariance_matrix"] = {"data_file": "tests/golden/fixed_inputs_cov.npz", "cov_key": "covmat"}
+    fm = CCFFit(model, data)
+    g = golden("boss_fixed_everything")
+    P = {"fsigma8": g["params"][:, 0], "sigma_v": g["params"][:, 2], "aperp": g["params"][:, 3], "apar": g["params"][:, 4]}
+    lnl, chi2, theory = fm.log_likelihood_batch(P, return_theory=True, **kw)
+    assert_theory(theory, g[f"{name}_theory"], ns=len(fm.s))
+    np.testing.assert_allclose(chi2, g[f"{name}_chi2"], rtol=0, atol=CHI2_ATOL)
+    np.testing.assert_allclose(lnl, g[f"{name}_lnl"], rtol=0, atol=CHI2_ATOL)
+    one = {k: float(v[0]) for k, v in P.items()}
+    l1, c1 = fm.log_likelihood(one, **kw)                 # single point without a 'beta' key
+    assert abs(c1 - g[f"{name}_chi2"][0]) < CHI2_ATOL and abs(l1 - g[f"{name}_lnl"][0]) < CHI2_ATOL
+    fm.close()

@@ -389,3 +389,37 @@ def test_direct_model_calls_from_tables(fit, golden):
     np.testing.assert_allclose(xi, g["xi_negmu"], rtol=RTOL, atol=ATOL)
     xi = E.theory_xi(mt, rows, np.sort(g["xi_unsorted_s"]), np.sort(g["xi_unsorted_mu"]))[0]
     np.testing.assert_allclose(xi, g["xi_unsorted"], rtol=RTOL, atol=ATOL)
+
+
+def fixed_blocks(boss_blocks):
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["input_model_data_file"] = "tests/golden/fixed_inputs_model.npz"
+    model["realspace_ccf"]["reconstruction"] = False
+    data["redshift_space_ccf"].update(reconstruction=False, data_file="tests/golden/fixed_inputs_data.npz")
+    data["covariance_matrix"] = {"data_file": "tests/golden/fixed_inputs_cov.npz", "cov_key": "covmat"}
+    return model, data
+
+
+@pytest.mark.parametrize("name,kw", [("streaming", {}), ("dispersion", {"rsd_model": "dispersion"}),
+                                     ("gaussian", {"likelihood": {"form": "gaussian"}})])
+def test_tables_no_reconstruction_anywhere(boss_blocks, golden, name, kw):
+    """1-D real-space and data multipoles, one covariance matrix: no beta dependence, beta not even
+    required in the parameters (ccf_model.py:105-111, 585; ccf_fit.py:60-64, 130-133, 210-211)."""
+    from victor_b200 import CCFFit, tables as T
+    from victor_b200.model import params_to_rows
+    fm = CCFFit(*fixed_blocks(boss_blocks))
+    assert fm.fixed_real_input and fm.fixed_data and fm.fixed_covmat and fm.covmat.shape == (60, 60)
+    g = golden("boss_fixed_everything")
+    P = {"fsigma8": g["params"][:, 0], "sigma_v": g["params"][:, 2], "aperp": g["params"][:, 3], "apar": g["params"][:, 4]}
+    rows = params_to_rows(P)
+    assert np.all(np.isnan(rows[:, 1]))                 # beta absent -> NaN column, must not matter
+    opts = fm._merged_options({k: v for k, v in kw.items() if k != "likelihood"})
+    mt = T.build_model_tables(fm, opts)
+    ft = T.build_fit_tables(fm, kw.get("likelihood", fm.fit_options["likelihood"]))
+    mu, W = T.mu_projection_weights(fm.poles_s)
+    mult, _ = E.theory_multipoles(mt, rows, np.asarray(fm.s, float), mu, W)
+    theory = mult.reshape(len(rows), -1)
+    np.testing.assert_allclose(theory, g[f"{name}_theory"], rtol=RTOL, atol=ATOL)
+    chi2, lnl = E.chi2_lnl(ft, rows[:, 1], theory)
+    np.testing.assert_allclose(chi2, g[f"{name}_chi2"], rtol=0, atol=C2_ATOL)
+    np.testing.assert_allclose(lnl, g[f"{name}_lnl"], rtol=0, atol=C2_ATOL)
