@@ -58,7 +58,7 @@ def flop_k2(p):
 
 FLOP_K1_PER_EVAL = flop_k1(NS, NMU, NX, L)
 FLOP_PER_EVAL = FLOP_K1_PER_EVAL + flop_k2(P)
-BYTES_PER_EVAL = 64 + 8 * L * NS + 16   # parameter row in, theory + chi2 + lnL out
+BYTES_PER_EVAL = 80 + 8 * L * NS + 16   # parameter row in (10 doubles), theory + chi2 + lnL out
 
 # BASELINE.json configs[3]: streaming model on a dense mu / velocity grid, l = 0, 2, 4 (multipoles only:
 # the data vector has no hexadecapole).  The reference hard-codes its grids; sizes per SURVEY.md 8(d).
@@ -289,7 +289,7 @@ def run_gpu(args):
     k1_avg_ms = sum(k1_ms) / len(k1_ms)
 
     # --- end to end through the public API with pinned host arrays (`e2e`) ---
-    pinned = torch.from_numpy(rows_host).pin_memory()   # float64[n, 8] rows, page-locked
+    pinned = torch.from_numpy(rows_host).pin_memory()   # float64[n, 10] rows, page-locked
     host_rows = pinned.numpy()
     for _ in range(max(1, min(args.warmup, 3))):
         fit.log_likelihood_batch(host_rows)
@@ -350,7 +350,7 @@ def run_gpu(args):
                        "likelihood": "sellentin/1000", "l2": "flushed between timed steps (256 MiB write)",
                        "parallelism": f"rows sharded over {world} GPU(s), no collective"},
             "clocks": clocks,
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(n * 8 * 8),
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(rows_host.nbytes),
                     "d2h_bytes_per_step": int(n * 16), "api": "CCFFit.log_likelihood_batch(host rows)"},
             "gpu_launches": int(launches),
             "roofline": roofline,

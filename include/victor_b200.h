@@ -39,9 +39,11 @@
 extern "C" {
 #endif
 
-#define VB200_NPAR 8 /* columns of a parameter row, in this order: */
+#define VB200_NPAR 10 /* columns of a parameter row, in this order: */
 enum { VB200_P_FSIGMA8 = 0, VB200_P_BETA, VB200_P_SIGMA_V, VB200_P_APERP, VB200_P_APAR,
-       VB200_P_ASTAR, VB200_P_M, VB200_P_Q };
+       VB200_P_ASTAR, VB200_P_M, VB200_P_Q,
+       VB200_P_AV,   /* params.get('Av', 0): empirical correction of the mean velocity (ccf_model.py:453) */
+       VB200_P_BIAS  /* params.get('bias', model['bias']) (ccf_model.py:359, 430); NaN = use the model's */ };
 
 enum { VB200_OK = 0, VB200_EINVAL = -1, VB200_ECUDA = -2, VB200_ENOMEM = -3, VB200_EUNSUPPORTED = -4 };
 
@@ -76,8 +78,12 @@ typedef struct vb200_model_tables {
     int32_t niter;            /* fixed-point iterations of the dispersion / kaiser coordinate map (5) */
     int32_t sv_ny;            /* mu intervals of a sigma_v(r, mu) template; 0 = isotropic template */
     int32_t vd_beta_dependent; /* v0 / d0 are power tables in beta like xi_tab (matter model linear_bias) */
-    int32_t growth_mode;      /* 0: growth = fsigma8 / template_sigma8; 1: beta * bias (:425-435) */
-    double bias;              /* model['bias'] (linear_bias with from-data input) */
+    int32_t growth_mode;      /* 0: growth = fsigma8 / template_sigma8; 1: beta * bias (:425-435);
+                                 2: velocity template, v_r = v0(r) fsigma8 / template_fsigma8 * growth_scale / apar (:439-443, 484) */
+    int32_t linear_bias;      /* matter model linear_bias: v0 / d0 carry 1 / bias, a per-row bias rescales them (:359-367) */
+    double bias;              /* model['bias'] */
+    double template_fsigma8;  /* velocity_pdf.mean.template_fsigma8 (:229), growth_mode 2 only */
+    double growth_scale;      /* template_hubble_ratio (1 + z_sim) / (1 + z_eff) (:441-443), growth_mode 2 only */
     const double *origin;     /* [ncell] */
     const double *upper;      /* [ncell], last = +inf */
     const int32_t *bucket_base; /* [nbucket] */
@@ -85,7 +91,10 @@ typedef struct vb200_model_tables {
     const double *xi_tab;     /* [n_ell][nbeta-1][4 powers of (beta-beta_k)][ncell][4] */
     const double *v0;         /* [ncell][4]  spline of r * Delta(r)               (:449, 635) */
     const double *d0;         /* [ncell][4]  spline of 3 (delta - 2 Delta / 3)    (:450, 636) */
-                              /* both [nbeta-1][4][ncell][4] when vd_beta_dependent */
+                              /* both [nbeta-1][4][ncell][4] when vd_beta_dependent;
+                                 growth_mode 2: splines of the velocity template and of its finite-difference slope (:484-488) */
+    const double *v0b;        /* [ncell][4] or NULL: empirical correction, v0 + Av v0b = spline of r Delta (1 + Av delta) (:454) */
+    const double *d0b;        /* [ncell][4] or NULL: same for the slope term, d0 + Av d0b (:456-459) */
     const double *sv;         /* [ncell][4]  normalised sigma_v(r) template       (:654) */
     const double *sv2d;       /* [ncell][sv_ny][4][4] bicubic sigma_v(r, mu) patches, t^q w^p (NULL if sv_ny = 0) */
     const double *sv_ybreaks; /* [sv_ny + 1] mu breakpoints of sv2d */

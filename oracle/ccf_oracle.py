@@ -132,9 +132,8 @@ class OracleModel:
 
     # ---- loaders ------------------------------------------------------------------------
     def _read_real_ccf(self, spec, raw):
-        # ccf_model.py:99-153 (multipoles format only; 'rmu' input is out of scope)
-        if spec.get("format", "multipoles") != "multipoles":
-            raise NotImplementedError("oracle: only the 'multipoles' real-space format")
+        # ccf_model.py:99-181
+        fmt = spec.get("format", "multipoles")
         self.fixed_real_input = not spec.get("reconstruction", False)
         keys = np.atleast_1d(spec["ccf_keys"])
         if not self.fixed_real_input:
@@ -144,13 +143,31 @@ class OracleModel:
             self.beta = raw[bkey]
             if not np.all(np.diff(self.beta) > 0):
                 raise OracleInputError("Realspace beta grid must be strictly increasing")
-        if len(keys) < 2:
+        if (fmt == "multipoles" and len(keys) < 2) or (fmt == "rmu" and len(keys) != 3):
             raise OracleInputError("Wrong number of ccf keys")
         for k in keys:
             if k not in raw:
                 raise OracleInputError(f"Key {k} not found in input model data file")
         isim = spec.get("simulation_number", None)
         self.r = raw[keys[0]]
+        if fmt == "rmu":
+            # ccf_model.py:154-181: xi(r, mu) -> multipoles 0, 2, 4 through a (default: linear) interp2d
+            mu = raw[keys[1]]
+            ccf = raw[keys[2]] if isim is None else raw[keys[2]][isim]
+            self.poles_r = np.array([0, 2, 4])
+            if self.fixed_real_input:
+                if ccf.shape != (len(self.r), len(mu)):
+                    raise OracleInputError("Unexpected real-space ccf shape")
+                self.real_multipoles = legendre_moments(grid_interp(self.r, mu, ccf.T, 1), self.r, self.poles_r)
+            else:
+                if ccf.shape != (len(self.beta), len(self.r), len(mu)):
+                    raise OracleInputError("Unexpected real-space ccf shape")
+                self.real_multipoles = {f"{ell}": np.zeros((len(self.beta), len(self.r))) for ell in self.poles_r}
+                for i in range(len(self.beta)):
+                    tmp = legendre_moments(grid_interp(self.r, mu, ccf[i].T, 1), self.r, self.poles_r)
+                    for ell in self.poles_r:
+                        self.real_multipoles[f"{ell}"][i] = tmp[f"{ell}"]
+            return
         self.poles_r = np.atleast_1d([0, 2, 4][:len(keys) - 1])
         self.real_multipoles = {}
         for i, ell in enumerate(self.poles_r):
@@ -188,9 +205,27 @@ class OracleModel:
             self.integrated_delta = _ius(grid, enclosed)
 
     def _read_velocity_pdf(self, spec, raw):
-        # ccf_model.py:222-297 ('template' mean model = test-only option, not restated)
-        if spec["mean"].get("model", "linear") not in ("linear",):
-            raise NotImplementedError("oracle: only the 'linear' mean-velocity model")
+        # ccf_model.py:222-297
+        mean = spec["mean"]
+        self.has_velocity_template = False
+        if mean.get("model", "linear") == "template":     # :227-246
+            self.template_fsigma8 = mean.get("template_fsigma8")
+            if not self.template_fsigma8:
+                raise OracleInputError("template_fsigma8 must be provided")
+            self.z_sim = mean.get("z_sim", self.z_eff)
+            self.template_hubble_ratio = mean.get("template_hubble_ratio", 1)
+            vkeys = np.atleast_1d(mean.get("template_keys"))
+            if len(vkeys) != 2:
+                raise OracleInputError("need 2 velocity mean template keys")
+            for k in vkeys:
+                if k not in raw:
+                    raise OracleInputError(f"Key {k} not found in input model data file")
+            if len(raw[vkeys[0]]) != len(raw[vkeys[1]]):
+                raise OracleInputError("mean velocity template shape mismatch")
+            self.radial_velocity = _ius(raw[vkeys[0]], raw[vkeys[1]])
+            self.has_velocity_template = True
+        elif mean.get("model", "linear") != "linear":
+            raise NotImplementedError("oracle: only the 'linear' and 'template' mean-velocity models")
         disp = spec.get("dispersion", {})
         kind = disp.get("model", "constant")
         if kind != "template":
@@ -247,7 +282,7 @@ class OracleModel:
         raise NotImplementedError(f"oracle: matter_model {opts['matter_model']}")
 
     def velocity_terms(self, r, params, opts):
-        # ccf_model.py:385-492, linear mean model
+        # ccf_model.py:385-492, linear and template mean models
         if "epsilon" in params:
             apar = params.get("alpha", 1) * params["epsilon"] ** (-2 / 3)
         else:
@@ -260,7 +295,15 @@ class OracleModel:
             growth = params["beta"] * params.get("bias", opts["bias"])
         else:
             growth = params["fsigma8"] / self.template_sigma8
-        if not opts["empirical_corr"]:
+        if opts["mean_model"] == "template":              # :439-443, 483-488
+            if not self.has_velocity_template:
+                raise OracleInputError("velocity_terms: no velocity template has been supplied")
+            shift = (1 + self.z_sim) / (1 + self.z_eff)
+            growth = (params["fsigma8"] / self.template_fsigma8) * self.template_hubble_ratio * shift / apar
+            vr = self.radial_velocity(r) * growth
+            rg = np.linspace(0.1, self.r.max(), 100)
+            dvr = _ius(rg, np.gradient(self.radial_velocity(rg) * growth, rg))(r)
+        elif not opts["empirical_corr"]:
             vr = -growth * r * Delta(r) / (3 * iaH_true)
             dvr = -growth * (delta(r) - 2 * Delta(r) / 3) / iaH_true
         else:

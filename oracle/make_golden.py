@@ -392,6 +392,140 @@ def golden_fixed(victor):
     np.savez(os.path.join(OUT, "boss_fixed_everything.npz"), **out, **meta())
 
 
+def golden_rmu(victor):
+    """Real-space ccf given as xi(r, mu) ('rmu' format, ccf_model.py:154-181): converted to multipoles
+    0, 2, 4 at load through a linear interp2d.  No shipped file has that layout, so xi_0 + xi_2 L_2 of
+    the BOSS model (plus a small mu^4 term) is tabulated on a non-uniform mu grid, with and without
+    the reconstruction axis; inputs saved next to the outputs (tests/golden/model_rmu_inputs.npz)."""
+    import tempfile
+    from scipy.special import legendre
+    from victor_b200.io_hdf5 import read_hdf5
+    model, data = boss_blocks()
+    src = read_hdf5(os.path.join(REF, model["input_model_data_file"]))
+    rng = np.random.default_rng(SEED + 11)
+    mu = np.concatenate([[0.0], np.sort(rng.uniform(0.03, 0.97, 18)), [1.0]])
+    xi = (src["monopole"][:, :, None] + src["quadrupole"][:, :, None] * legendre(2)(mu)[None, None, :]
+          + 0.02 * src["monopole"][:, :, None] * legendre(4)(mu)[None, None, :])
+    inputs = dict(src)
+    inputs["mu_rmu"] = mu
+    inputs["xi_rmu"] = xi                     # (nbeta, nr, nmu)
+    inputs["xi_rmu_fixed"] = xi[12]           # (nr, nmu)
+    np.savez(os.path.join(OUT, "model_rmu_inputs.npz"), **inputs)
+    tmp = tempfile.mkdtemp()
+    np.save(os.path.join(tmp, "model_rmu.npy"), inputs, allow_pickle=True)
+    mm = copy.deepcopy(model)
+    mm["dir"] = tmp
+    mm["input_model_data_file"] = "model_rmu.npy"
+    mm["realspace_ccf"].update(format="rmu", ccf_keys=["r", "mu_rmu", "xi_rmu"])
+    ccf = victor.CCFFit(mm, copy.deepcopy(data))
+    P = np.vstack([synthetic_batch(65536)[:4], edge_rows(ccf.beta)[[0, 9]]])
+    out = dict(params=P, poles_r=ccf.poles_r)
+    for ell in ccf.poles_r:
+        out[f"real_multipole_{ell}"] = ccf.real_multipoles[f"{ell}"]
+    for name, kw in (("streaming", {}), ("aniso_streaming", {"assume_isotropic": False}),
+                     ("aniso_dispersion", {"assume_isotropic": False, "rsd_model": "dispersion"})):
+        th, c2, ll = run_points(ccf, P, **kw)
+        out[f"{name}_theory"], out[f"{name}_chi2"], out[f"{name}_lnl"] = th, c2, ll
+    # without the reconstruction axis (CCFModel only: the data still depend on beta)
+    mf = copy.deepcopy(mm)
+    mf["realspace_ccf"].update(reconstruction=False, ccf_keys=["r", "mu_rmu", "xi_rmu_fixed"])
+    cm = victor.CCFModel(mf)
+    for ell in cm.poles_r:
+        out[f"fixed_real_multipole_{ell}"] = cm.real_multipoles[f"{ell}"]
+    out["fixed_aniso_theory"] = np.array([cm.theory_multipole_vector(ccf.s, row_to_params(row), [0, 2, 4],
+                                                                     assume_isotropic=False) for row in P[:3]])
+    np.savez(os.path.join(OUT, "boss_rmu.npz"), **out, **meta())
+
+
+def golden_velocity(victor):
+    """Mean-velocity options of the velocity pdf (ccf_model.py:385-492): the empirical correction
+    (1 + Av delta(r)) with Av a parameter, a bias given with the parameters (linear_bias matter model),
+    and the 'template' mean model (a velocity profile read from file; none is shipped, so one is derived
+    from the BOSS matter template and saved in tests/golden/model_vtemplate_inputs.npz)."""
+    import tempfile
+    from victor_b200.io_hdf5 import read_hdf5
+    model, data = boss_blocks()
+    P = np.vstack([synthetic_batch(65536)[:4], edge_rows(np.linspace(0.16, 0.65, 31))[[0, 9]]])
+    Av = np.array([0.0, 0.8, -0.5, 1.5, 0.3, -1.0])
+    out = dict(params=P, Av=Av)
+
+    # (a) empirical correction, matter template
+    me = copy.deepcopy(model)
+    me["velocity_pdf"]["mean"]["empirical_corr"] = True
+    ccf = victor.CCFFit(me, copy.deepcopy(data))
+    for name, kw in (("emp_streaming", {}), ("emp_dispersion", {"rsd_model": "dispersion"}),
+                     ("emp_kaiser", {"rsd_model": "kaiser"})):
+        th, c2, ll = [], [], []
+        for row, av in zip(P, Av):
+            prm = row_to_params(row)
+            prm["Av"] = float(av)
+            th.append(ccf.theory_multipole_vector(ccf.s, dict(prm), ccf.poles_s, **kw))
+            a, b = ccf.log_likelihood(dict(prm), **kw)
+            ll.append(a)
+            c2.append(b)
+        out[f"{name}_theory"], out[f"{name}_chi2"], out[f"{name}_lnl"] = np.array(th), np.array(c2), np.array(ll)
+    # Av absent from the parameters: defaults to 0, but the slope still comes from the finite-difference branch
+    th, c2, ll = run_points(ccf, P[:3], rsd_model="dispersion")
+    out["emp_noAv_dispersion_theory"], out["emp_noAv_dispersion_chi2"], out["emp_noAv_dispersion_lnl"] = th, c2, ll
+
+    # (b) bias given with the parameters, linear_bias matter model (beta-dependent monopole)
+    mb = copy.deepcopy(model)
+    mb["matter_ccf"]["model"] = "linear_bias"
+    cb = victor.CCFFit(mb, copy.deepcopy(data))
+    bias = np.array([1.9, 2.3, 1.6, 2.0, 2.8, 1.2])
+    out["bias"] = bias
+    for name, kw in (("rowbias_streaming", {}), ("rowbias_dispersion", {"rsd_model": "dispersion"})):
+        th, c2, ll = [], [], []
+        for row, b_ in zip(P, bias):
+            prm = row_to_params(row)
+            prm["bias"] = float(b_)
+            th.append(cb.theory_multipole_vector(cb.s, dict(prm), cb.poles_s, **kw))
+            a, b = cb.log_likelihood(dict(prm), **kw)
+            ll.append(a)
+            c2.append(b)
+        out[f"{name}_theory"], out[f"{name}_chi2"], out[f"{name}_lnl"] = np.array(th), np.array(c2), np.array(ll)
+
+    # (c) empirical correction + linear_bias without reconstruction (fixed real-space input), with row bias
+    fx = np.load(os.path.join(OUT, "fixed_inputs_model.npz"))
+    tmp = tempfile.mkdtemp()
+    np.save(os.path.join(tmp, "m.npy"), {k: fx[k] for k in fx.files}, allow_pickle=True)
+    mf = copy.deepcopy(model)
+    mf["dir"] = tmp
+    mf["input_model_data_file"] = "m.npy"
+    mf["realspace_ccf"]["reconstruction"] = False
+    mf["matter_ccf"]["model"] = "linear_bias"
+    mf["velocity_pdf"]["mean"]["empirical_corr"] = True
+    cm = victor.CCFModel(mf)
+    s = read_hdf5(os.path.join(REF, data["redshift_space_ccf"]["data_file"]))["s"]
+    th = []
+    for row, av, b_ in zip(P, Av, bias):
+        prm = row_to_params(row)
+        prm.update(Av=float(av), bias=float(b_))
+        th.append(cm.theory_multipole_vector(s, dict(prm), [0, 2], rsd_model="dispersion"))
+    out["emp_linbias_fixed_dispersion_theory"] = np.array(th)
+
+    # (d) velocity template
+    src = read_hdf5(os.path.join(REF, model["input_model_data_file"]))
+    rv = np.linspace(0.5, 130.0, 40)
+    base = victor.CCFModel(copy.deepcopy(model))
+    vr_t = -0.52 * rv * base.integrated_delta(rv) / (3 * base.iaH) * (1 + 0.1 * np.sin(rv / 15.0))
+    inputs = dict(src)
+    inputs["rvel"], inputs["vr_template"] = rv, vr_t
+    np.savez(os.path.join(OUT, "model_vtemplate_inputs.npz"), **inputs)
+    np.save(os.path.join(tmp, "model_vt.npy"), inputs, allow_pickle=True)
+    mv = copy.deepcopy(model)
+    mv["dir"] = tmp
+    mv["input_model_data_file"] = "model_vt.npy"
+    mv["velocity_pdf"]["mean"].update(model="template", template_fsigma8=0.45, z_sim=0.5,
+                                      template_hubble_ratio=1.02, template_keys=["rvel", "vr_template"])
+    cv = victor.CCFFit(mv, copy.deepcopy(data))
+    for name, kw in (("vtemplate_streaming", {}), ("vtemplate_dispersion", {"rsd_model": "dispersion"}),
+                     ("vtemplate_kaiser", {"rsd_model": "kaiser"})):
+        th, c2, ll = run_points(cv, P, **kw)
+        out[f"{name}_theory"], out[f"{name}_chi2"], out[f"{name}_lnl"] = th, c2, ll
+    np.savez(os.path.join(OUT, "boss_velocity_options.npz"), **out, **meta())
+
+
 def golden_example(victor):
     with open(os.path.join(REF, "config/example_model_input.yaml")) as fh:
         model = yaml.full_load(fh)["model"]
@@ -419,7 +553,7 @@ def golden_example(victor):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     v = refshim.install(REF)
-    which = sys.argv[1:] or ["boss", "more", "sv2d", "linear_bias", "misc", "fixed", "example"]
+    which = sys.argv[1:] or ["boss", "more", "sv2d", "linear_bias", "misc", "fixed", "rmu", "velocity", "example"]
     if "boss" in which:
         golden_boss(v)
     if "more" in which:
@@ -432,6 +566,10 @@ if __name__ == "__main__":
         golden_misc(v)
     if "fixed" in which:
         golden_fixed(v)
+    if "rmu" in which:
+        golden_rmu(v)
+    if "velocity" in which:
+        golden_velocity(v)
     if "example" in which:
         golden_example(v)
     for fn in sorted(os.listdir(OUT)):

@@ -53,9 +53,17 @@ def point_scalars(mt, rows):
     else:
         y = apar[:, None] * np.sqrt(1 + (1 - mt.mu_resc[None, :] ** 2) * (eps[:, None] ** 2 - 1))
         f = (y * mt.w_resc[None, :]).sum(axis=1)
-    growth = beta * mt.bias if mt.growth_mode else fs8 / mt.template_sigma8
-    Av = -growth / (3 * iaHt)
-    return dict(eps=eps, iaHt=iaHt, f=f, Av=Av)
+    # a bias given with the row rescales the linear_bias profiles (tabulated with the model's bias)
+    brow = rows[:, 9] if rows.shape[1] > 9 else np.full(len(rows), np.nan)
+    has_b = bool(mt.linear_bias) & ~np.isnan(brow)
+    bs = np.where(has_b, mt.bias / np.where(has_b, brow, 1.0), 1.0)
+    if mt.growth_mode == T.GROWTH_VELOCITY_TEMPLATE:
+        Av = fs8 / mt.template_fsigma8 * mt.growth_scale / apar
+    else:
+        growth = beta * np.where(has_b, brow, mt.bias) if mt.growth_mode else fs8 / mt.template_sigma8
+        Av = -(growth * bs) / (3 * iaHt)
+    emp = (rows[:, 8] if rows.shape[1] > 8 else np.zeros(len(rows))) * bs
+    return dict(eps=eps, iaHt=iaHt, f=f, Av=Av, emp=emp)
 
 
 def xi_cells(mt, beta):
@@ -129,6 +137,9 @@ def theory_xi(mt, rows, s, mu, chunk=32):
         idx = np.arange(len(R))[:, None, None, None]
         if mt.vd_beta_dependent:
             v0c, d0c = _beta_cells(mt, mt.v0, beta), _beta_cells(mt, mt.d0, beta)
+        elif mt.v0b is not None:      # empirical correction (1 + Av delta) of the mean velocity
+            v0c = mt.v0[None] + sc["emp"][:, None, None] * mt.v0b[None]
+            d0c = mt.d0[None] + sc["emp"][:, None, None] * mt.d0b[None]
         else:
             v0c = np.broadcast_to(mt.v0, (len(R),) + mt.v0.shape)
             d0c = np.broadcast_to(mt.d0, (len(R),) + mt.d0.shape)

@@ -437,6 +437,114 @@ def test_linear_bias_from_data(boss_blocks, golden):
     fm.close()
 
 
+def _check_fit(fm, rows, g, name, **kw):
+    lnl, chi2, theory = fm.log_likelihood_batch(rows, return_theory=True, **kw)
+    assert_theory(theory, g[f"{name}_theory"], ns=len(fm.s))
+    np.testing.assert_allclose(chi2, g[f"{name}_chi2"], rtol=0, atol=CHI2_ATOL)
+    np.testing.assert_allclose(lnl, g[f"{name}_lnl"], rtol=0, atol=CHI2_ATOL)
+
+
+@pytest.mark.parametrize("name,kw", [("streaming", {}), ("aniso_streaming", {"assume_isotropic": False}),
+                                     ("aniso_dispersion", {"assume_isotropic": False, "rsd_model": "dispersion"})])
+def test_rmu_format_input(boss_blocks, golden, name, kw):
+    """Real-space ccf given as xi(r, mu) (ccf_model.py:154-181): converted at load, three real-space poles."""
+    from victor_b200 import CCFFit
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["input_model_data_file"] = "tests/golden/model_rmu_inputs.npz"
+    model["realspace_ccf"].update(format="rmu", ccf_keys=["r", "mu_rmu", "xi_rmu"])
+    fm = CCFFit(model, data)
+    g = golden("boss_rmu")
+    _check_fit(fm, g["params"], g, name, **kw)
+    fm.close()
+
+
+def test_rmu_format_input_without_reconstruction(boss_blocks, golden):
+    from victor_b200 import CCFModel
+    model = copy.deepcopy(boss_blocks[0])
+    model["input_model_data_file"] = "tests/golden/model_rmu_inputs.npz"
+    model["realspace_ccf"].update(format="rmu", ccf_keys=["r", "mu_rmu", "xi_rmu_fixed"], reconstruction=False)
+    cm = CCFModel(model)
+    g = golden("boss_rmu")
+    s = np.load("tests/golden/fixed_inputs_data.npz")["s"]
+    P = g["params"][:3]
+    prm = {"fsigma8": P[:, 0], "beta": P[:, 1], "sigma_v": P[:, 2], "aperp": P[:, 3], "apar": P[:, 4]}
+    th = cm.theory_multipole_vector_batch(s, prm, [0, 2, 4], assume_isotropic=False)
+    assert_theory(th, g["fixed_aniso_theory"], ns=len(s))
+    cm.close()
+
+
+def _velocity_params(g, av=False, bias=False, n=None):
+    P = g["params"][:n]
+    prm = {"fsigma8": P[:, 0], "beta": P[:, 1], "sigma_v": P[:, 2], "aperp": P[:, 3], "apar": P[:, 4]}
+    if av:
+        prm["Av"] = g["Av"][:n]
+    if bias:
+        prm["bias"] = g["bias"][:n]
+    return prm
+
+
+@pytest.mark.parametrize("name,kw", [("emp_streaming", {}), ("emp_dispersion", {"rsd_model": "dispersion"}),
+                                     ("emp_kaiser", {"rsd_model": "kaiser"})])
+def test_empirical_velocity_correction(boss_blocks, golden, name, kw):
+    """velocity_pdf.mean.empirical_corr with Av among the parameters (ccf_model.py:451-459)."""
+    from victor_b200 import CCFFit
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["velocity_pdf"]["mean"]["empirical_corr"] = True
+    fm = CCFFit(model, data)
+    g = golden("boss_velocity_options")
+    _check_fit(fm, _velocity_params(g, av=True), g, name, **kw)
+    if name == "emp_dispersion":
+        _check_fit(fm, _velocity_params(g, n=3), g, "emp_noAv_dispersion", **kw)
+        # single-point call, reference style
+        i = 3
+        prm = {k: float(v[i]) for k, v in _velocity_params(g, av=True).items()}
+        lnl, chi2 = fm.log_likelihood(prm, **kw)
+        assert abs(chi2 - g["emp_dispersion_chi2"][i]) < CHI2_ATOL and abs(lnl - g["emp_dispersion_lnl"][i]) < CHI2_ATOL
+    fm.close()
+
+
+@pytest.mark.parametrize("name,kw", [("rowbias_streaming", {}), ("rowbias_dispersion", {"rsd_model": "dispersion"})])
+def test_bias_given_with_the_parameters(boss_blocks, golden, name, kw):
+    from victor_b200 import CCFFit
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["matter_ccf"]["model"] = "linear_bias"
+    fm = CCFFit(model, data)
+    g = golden("boss_velocity_options")
+    _check_fit(fm, _velocity_params(g, bias=True), g, name, **kw)
+    fm.close()
+
+
+def test_empirical_correction_with_linear_bias(boss_blocks, golden):
+    from victor_b200 import CCFModel
+    model = copy.deepcopy(boss_blocks[0])
+    model["input_model_data_file"] = "tests/golden/fixed_inputs_model.npz"
+    model["realspace_ccf"]["reconstruction"] = False
+    model["matter_ccf"]["model"] = "linear_bias"
+    model["velocity_pdf"]["mean"]["empirical_corr"] = True
+    cm = CCFModel(model)
+    g = golden("boss_velocity_options")
+    s = np.load("tests/golden/fixed_inputs_data.npz")["s"]
+    th = cm.theory_multipole_vector_batch(s, _velocity_params(g, av=True, bias=True), [0, 2], rsd_model="dispersion")
+    assert_theory(th, g["emp_linbias_fixed_dispersion_theory"], ns=len(s))
+    cm.close()
+
+
+@pytest.mark.parametrize("name,kw", [("vtemplate_streaming", {}), ("vtemplate_dispersion", {"rsd_model": "dispersion"}),
+                                     ("vtemplate_kaiser", {"rsd_model": "kaiser"})])
+def test_velocity_template_mean_model(boss_blocks, golden, name, kw):
+    """velocity_pdf.mean.model 'template' (ccf_model.py:227-246, 439-443, 483-488); the streaming case runs
+    on the tuned kernel (only the per-row amplitude differs)."""
+    from victor_b200 import CCFFit
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["input_model_data_file"] = "tests/golden/model_vtemplate_inputs.npz"
+    model["velocity_pdf"]["mean"].update(model="template", template_fsigma8=0.45, z_sim=0.5,
+                                         template_hubble_ratio=1.02, template_keys=["rvel", "vr_template"])
+    fm = CCFFit(model, data)
+    g = golden("boss_velocity_options")
+    _check_fit(fm, _velocity_params(g), g, name, **kw)
+    fm.close()
+
+
 def test_direct_model_calls(fit, golden):
     """Notebook-style calls: odd poles, bare-integer poles, fine s grid, theory_xi on
     unsorted meshgrid input (sorted / uniqued like the reference) and at negative mu."""

@@ -176,12 +176,12 @@ def test_params_to_rows_conventions():
     from victor_b200.model import params_to_rows
     rows = params_to_rows({"fsigma8": 0.47, "beta": 0.37, "sigma_v": 380, "epsilon": 0.95, "alpha": 1.01})
     apar = 1.01 * 0.95 ** (-2 / 3)
-    assert rows.shape == (1, 8) and rows[0, 4] == apar and rows[0, 3] == 0.95 * apar   # ccf_model.py:589-592
+    assert rows.shape == (1, 10) and rows[0, 4] == apar and rows[0, 3] == 0.95 * apar   # ccf_model.py:589-592
     rows = params_to_rows({"fsigma8": [0.1, 0.2, 0.3], "beta": 0.4, "sigma_v": 300.0, "aperp": 1.0, "apar": 1.0,
                            "b": 1.9, "Av": 0, "chi2_unused": 7})                       # cobaya passes extras
-    assert rows.shape == (3, 8) and np.all(rows[:, 1] == 0.4) and np.all(rows[:, 5] == 1.0)
+    assert rows.shape == (3, 10) and np.all(rows[:, 1] == 0.4) and np.all(rows[:, 5] == 1.0)
     rows = params_to_rows(np.array([[0.47, 0.37, 380.0]]))
-    assert rows.shape == (1, 8) and rows[0, 3] == 1.0 and rows[0, 4] == 1.0
+    assert rows.shape == (1, 10) and rows[0, 3] == 1.0 and rows[0, 4] == 1.0
     with pytest.raises(InputError):
         params_to_rows(np.zeros((2, 2)))
 
@@ -423,3 +423,151 @@ def test_tables_no_reconstruction_anywhere(boss_blocks, golden, name, kw):
     chi2, lnl = E.chi2_lnl(ft, rows[:, 1], theory)
     np.testing.assert_allclose(chi2, g[f"{name}_chi2"], rtol=0, atol=C2_ATOL)
     np.testing.assert_allclose(lnl, g[f"{name}_lnl"], rtol=0, atol=C2_ATOL)
+
+
+# ---------------------------------------------------------------------------------------------
+# real-space input as xi(r, mu), the empirical velocity correction, a bias given with the
+# parameters, the velocity-template mean model
+# ---------------------------------------------------------------------------------------------
+def rmu_blocks(boss_blocks, fixed=False):
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["input_model_data_file"] = "tests/golden/model_rmu_inputs.npz"
+    model["realspace_ccf"].update(format="rmu", ccf_keys=["r", "mu_rmu", "xi_rmu_fixed" if fixed else "xi_rmu"])
+    if fixed:
+        model["realspace_ccf"]["reconstruction"] = False
+    return model, data
+
+
+def test_rmu_input_is_converted_like_the_reference(boss_blocks, golden):
+    """'rmu' format (ccf_model.py:154-181): multipoles 0, 2, 4 from a linear interp2d + 200-point trapezoid."""
+    from victor_b200 import CCFFit, CCFModel, InputError
+    g = golden("boss_rmu")
+    fm = CCFFit(*rmu_blocks(boss_blocks))
+    assert list(fm.poles_r) == [0, 2, 4]
+    for ell in (0, 2, 4):
+        assert fm.real_multipoles[f"{ell}"].shape == (31, 30)
+        np.testing.assert_allclose(fm.real_multipoles[f"{ell}"], g[f"real_multipole_{ell}"], rtol=1e-13, atol=1e-16)
+    cm = CCFModel(rmu_blocks(boss_blocks, fixed=True)[0])
+    for ell in (0, 2, 4):
+        np.testing.assert_allclose(cm.real_multipoles[f"{ell}"], g[f"fixed_real_multipole_{ell}"], rtol=1e-13,
+                                   atol=1e-16)
+    bad = rmu_blocks(boss_blocks)[0]
+    bad["realspace_ccf"]["ccf_keys"] = ["r", "xi_rmu"]
+    with pytest.raises(InputError):
+        CCFModel(bad)
+    bad = rmu_blocks(boss_blocks)[0]
+    bad["realspace_ccf"]["ccf_keys"] = ["r", "mu_rmu", "xi_rmu_fixed"]      # shape lacks the beta axis
+    with pytest.raises(InputError):
+        CCFModel(bad)
+
+
+@pytest.mark.parametrize("name,kw", [("streaming", {}), ("aniso_streaming", {"assume_isotropic": False}),
+                                     ("aniso_dispersion", {"assume_isotropic": False, "rsd_model": "dispersion"})])
+def test_tables_rmu_input(boss_blocks, golden, name, kw):
+    from victor_b200 import CCFFit
+    from victor_b200.model import params_to_rows
+    fm = CCFFit(*rmu_blocks(boss_blocks))
+    g = golden("boss_rmu")
+    _tables_vs_golden(fm, kw, params_to_rows(g["params"]), g[f"{name}_theory"], g[f"{name}_chi2"], g[f"{name}_lnl"])
+
+
+def test_tables_rmu_input_without_reconstruction(boss_blocks, golden):
+    from victor_b200 import CCFModel, tables as T
+    from victor_b200.model import params_to_rows
+    g = golden("boss_rmu")
+    cm = CCFModel(rmu_blocks(boss_blocks, fixed=True)[0])
+    mt = T.build_model_tables(cm, cm._merged_options({"assume_isotropic": False}))
+    assert mt.n_ell == 3 and not mt.beta_dependent
+    mu, W = T.mu_projection_weights([0, 2, 4])
+    s = np.load("tests/golden/fixed_inputs_data.npz")["s"]
+    mult, _ = E.theory_multipoles(mt, params_to_rows(g["params"][:3]), s, mu, W)
+    np.testing.assert_allclose(mult.reshape(3, -1), g["fixed_aniso_theory"], rtol=RTOL, atol=ATOL)
+
+
+def velocity_rows(g, av=False, bias=False):
+    from victor_b200.model import params_to_rows
+    rows = params_to_rows(g["params"])
+    if av:
+        rows[:, 8] = g["Av"]
+    if bias:
+        rows[:, 9] = g["bias"]
+    return rows
+
+
+EMP_CASES = [("emp_streaming", {}), ("emp_dispersion", {"rsd_model": "dispersion"}), ("emp_kaiser", {"rsd_model": "kaiser"})]
+
+
+@pytest.mark.parametrize("name,kw", EMP_CASES)
+def test_tables_empirical_velocity_correction(boss_blocks, golden, name, kw):
+    """velocity_pdf.mean.empirical_corr (ccf_model.py:451-459): v_r gains (1 + Av delta(r)), its slope comes
+    from a finite difference on a 100-point grid; both are linear in Av -> V0 = v0 + Av v0b, D0 = d0 + Av d0b."""
+    from victor_b200 import CCFFit
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["velocity_pdf"]["mean"]["empirical_corr"] = True
+    fm = CCFFit(model, data)
+    g = golden("boss_velocity_options")
+    _tables_vs_golden(fm, kw, velocity_rows(g, av=True), g[f"{name}_theory"], g[f"{name}_chi2"], g[f"{name}_lnl"])
+    if name == "emp_dispersion":     # no Av among the parameters: 0, but still the finite-difference slope
+        _tables_vs_golden(fm, kw, velocity_rows(g)[:3], g["emp_noAv_dispersion_theory"],
+                          g["emp_noAv_dispersion_chi2"], g["emp_noAv_dispersion_lnl"])
+
+
+@pytest.mark.parametrize("name,kw", [("rowbias_streaming", {}), ("rowbias_dispersion", {"rsd_model": "dispersion"})])
+def test_tables_bias_given_with_the_parameters(boss_blocks, golden, name, kw):
+    """params.get('bias', model['bias']) (ccf_model.py:359): delta and Delta scale as 1 / bias."""
+    from victor_b200 import CCFFit
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["matter_ccf"]["model"] = "linear_bias"
+    fm = CCFFit(model, data)
+    g = golden("boss_velocity_options")
+    _tables_vs_golden(fm, kw, velocity_rows(g, bias=True), g[f"{name}_theory"], g[f"{name}_chi2"], g[f"{name}_lnl"])
+
+
+def test_tables_empirical_correction_with_linear_bias(boss_blocks, golden):
+    from victor_b200 import CCFModel, tables as T
+    model = copy.deepcopy(boss_blocks[0])
+    model["input_model_data_file"] = "tests/golden/fixed_inputs_model.npz"
+    model["realspace_ccf"]["reconstruction"] = False
+    model["matter_ccf"]["model"] = "linear_bias"
+    model["velocity_pdf"]["mean"]["empirical_corr"] = True
+    cm = CCFModel(model)
+    g = golden("boss_velocity_options")
+    mt = T.build_model_tables(cm, cm._merged_options({"rsd_model": "dispersion"}))
+    assert mt.v0b is not None and mt.linear_bias and not mt.vd_beta_dependent
+    mu, W = T.mu_projection_weights([0, 2])
+    s = np.load("tests/golden/fixed_inputs_data.npz")["s"]
+    mult, _ = E.theory_multipoles(mt, velocity_rows(g, av=True, bias=True), s, mu, W)
+    np.testing.assert_allclose(mult.reshape(len(g["params"]), -1), g["emp_linbias_fixed_dispersion_theory"],
+                               rtol=RTOL, atol=ATOL)
+    # with a reconstruction-dependent monopole delta * Delta is no cubic in beta: refused, not approximated
+    model = copy.deepcopy(boss_blocks[0])
+    model["matter_ccf"]["model"] = "linear_bias"
+    model["velocity_pdf"]["mean"]["empirical_corr"] = True
+    cm = CCFModel(model)
+    with pytest.raises(NotImplementedError):
+        T.build_model_tables(cm, cm.model)
+
+
+def vtemplate_blocks(boss_blocks):
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["input_model_data_file"] = "tests/golden/model_vtemplate_inputs.npz"
+    model["velocity_pdf"]["mean"].update(model="template", template_fsigma8=0.45, z_sim=0.5,
+                                         template_hubble_ratio=1.02, template_keys=["rvel", "vr_template"])
+    return model, data
+
+
+@pytest.mark.parametrize("name,kw", [("vtemplate_streaming", {}), ("vtemplate_dispersion", {"rsd_model": "dispersion"}),
+                                     ("vtemplate_kaiser", {"rsd_model": "kaiser"})])
+def test_tables_velocity_template_mean_model(boss_blocks, golden, name, kw):
+    """velocity_pdf.mean.model 'template' (ccf_model.py:227-246, 439-443, 483-488)."""
+    from victor_b200 import CCFFit, InputError, tables as T
+    fm = CCFFit(*vtemplate_blocks(boss_blocks))
+    assert fm.has_velocity_template and fm.template_fsigma8 == 0.45
+    g = golden("boss_velocity_options")
+    _tables_vs_golden(fm, kw, velocity_rows(g), g[f"{name}_theory"], g[f"{name}_chi2"], g[f"{name}_lnl"])
+    mt = T.build_model_tables(fm, fm._merged_options(kw))
+    assert mt.growth_mode == T.GROWTH_VELOCITY_TEMPLATE and abs(mt.growth_scale - 1.02 * 1.5 / 1.57) < 1e-15
+    bad = vtemplate_blocks(boss_blocks)[0]
+    del bad["velocity_pdf"]["mean"]["template_fsigma8"]
+    with pytest.raises(InputError):
+        CCFFit(bad, vtemplate_blocks(boss_blocks)[1])

@@ -205,3 +205,50 @@ def test_linear_bias_matter_model(golden, boss_blocks):
     for name, kw in (("streaming", {}), ("kaiser", {"rsd_model": "kaiser"}), ("bias25", {"bias": 2.5})):
         check_rows(om, g["params"][[2, 7]], g[f"{name}_theory"][[2, 7]], g[f"{name}_chi2"][[2, 7]],
                    g[f"{name}_lnl"][[2, 7]], **kw)
+
+
+def test_rmu_format_input(golden, boss_blocks):
+    """Real-space ccf given as xi(r, mu) (ccf_model.py:154-181)."""
+    g = golden("boss_rmu")
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["input_model_data_file"] = "tests/golden/model_rmu_inputs.npz"
+    model["realspace_ccf"].update(format="rmu", ccf_keys=["r", "mu_rmu", "xi_rmu"])
+    om = OracleFit(model, data)
+    for ell in (0, 2, 4):
+        np.testing.assert_allclose(om.real_multipoles[f"{ell}"], g[f"real_multipole_{ell}"], rtol=1e-13, atol=1e-16)
+    check_rows(om, g["params"][[1, 5]], g["aniso_streaming_theory"][[1, 5]], g["aniso_streaming_chi2"][[1, 5]],
+               g["aniso_streaming_lnl"][[1, 5]], assume_isotropic=False)
+
+
+def test_velocity_options(golden, boss_blocks):
+    """Empirical correction with Av, bias among the parameters, velocity-template mean model
+    (ccf_model.py:227-246, 359, 439-459, 483-488)."""
+    g = golden("boss_velocity_options")
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["velocity_pdf"]["mean"]["empirical_corr"] = True
+    om = OracleFit(model, data)
+    for i in (1, 3):
+        prm = as_params(g["params"][i])
+        prm["Av"] = float(g["Av"][i])
+        th = om.theory_multipole_vector(om.s, dict(prm), om.poles_s, rsd_model="dispersion")
+        np.testing.assert_allclose(th, g["emp_dispersion_theory"][i], rtol=TH_RTOL, atol=TH_ATOL)
+        l, c = om.log_likelihood(dict(prm))
+        assert abs(c - g["emp_streaming_chi2"][i]) < C2_ATOL and abs(l - g["emp_streaming_lnl"][i]) < C2_ATOL
+
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["matter_ccf"]["model"] = "linear_bias"
+    om = OracleFit(model, data)
+    prm = as_params(g["params"][4])
+    prm["bias"] = float(g["bias"][4])
+    l, c = om.log_likelihood(dict(prm))
+    assert abs(c - g["rowbias_streaming_chi2"][4]) < C2_ATOL and abs(l - g["rowbias_streaming_lnl"][4]) < C2_ATOL
+
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["input_model_data_file"] = "tests/golden/model_vtemplate_inputs.npz"
+    model["velocity_pdf"]["mean"].update(model="template", template_fsigma8=0.45, z_sim=0.5,
+                                         template_hubble_ratio=1.02, template_keys=["rvel", "vr_template"])
+    om = OracleFit(model, data)
+    check_rows(om, g["params"][[2]], g["vtemplate_streaming_theory"][[2]], g["vtemplate_streaming_chi2"][[2]],
+               g["vtemplate_streaming_lnl"][[2]])
+    check_rows(om, g["params"][[5]], g["vtemplate_dispersion_theory"][[5]], g["vtemplate_dispersion_chi2"][[5]],
+               g["vtemplate_dispersion_lnl"][[5]], rsd_model="dispersion")

@@ -29,7 +29,7 @@ def test_shard_bounds():
 
 def test_unsharded_call_is_a_passthrough():
     from victor_b200.batch import evaluate_sharded
-    rows = np.arange(24.0).reshape(3, 8)
+    rows = np.arange(30.0).reshape(3, 10)
     lnl, chi2, (lo, hi) = evaluate_sharded(lambda r: (-r[:, 0], r[:, 1] ** 2), rows)
     assert (lo, hi) == (0, 3) and np.array_equal(lnl, -rows[:, 0]) and np.array_equal(chi2, rows[:, 1] ** 2)
 

@@ -31,10 +31,11 @@ class ModelTablesC(ctypes.Structure):
         ("nbeta", c_int32), ("nx", c_int32), ("nresc", c_int32),
         ("realspace_from_data", c_int32), ("kaiser_approximation", c_int32), ("kaiser_coord_shift", c_int32),
         ("niter", c_int32), ("sv_ny", c_int32), ("vd_beta_dependent", c_int32), ("growth_mode", c_int32),
-        ("bias", c_double),
+        ("linear_bias", c_int32),
+        ("bias", c_double), ("template_fsigma8", c_double), ("growth_scale", c_double),
         ("origin", c_double_p), ("upper", c_double_p), ("bucket_base", c_int32_p),
         ("beta_grid", c_double_p), ("xi_tab", c_double_p),
-        ("v0", c_double_p), ("d0", c_double_p), ("sv", c_double_p),
+        ("v0", c_double_p), ("d0", c_double_p), ("v0b", c_double_p), ("d0b", c_double_p), ("sv", c_double_p),
         ("sv2d", c_double_p), ("sv_ybreaks", c_double_p),
         ("x", c_double_p), ("wx", c_double_p), ("mu_resc", c_double_p), ("w_resc", c_double_p),
     ]
@@ -134,6 +135,10 @@ def pack_model(mt):
     c.beta_grid, c.xi_tab = f64("beta_grid", mt.beta_grid), f64("xi_tab", mt.xi_tab)
     c.v0, c.d0, c.sv = f64("v0", mt.v0), f64("d0", mt.d0), f64("sv", mt.sv)
     c.vd_beta_dependent, c.growth_mode, c.bias = int(mt.vd_beta_dependent), int(mt.growth_mode), float(mt.bias)
+    c.linear_bias = int(mt.linear_bias)
+    c.template_fsigma8, c.growth_scale = float(mt.template_fsigma8), float(mt.growth_scale)
+    if mt.v0b is not None:
+        c.v0b, c.d0b = f64("v0b", mt.v0b), f64("d0b", mt.d0b)
     if mt.sv2d is not None:
         c.sv_ny = int(mt.sv2d.shape[1])
         c.sv2d, c.sv_ybreaks = f64("sv2d", mt.sv2d), f64("sv_ybreaks", mt.sv_ybreaks)

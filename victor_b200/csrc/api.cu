@@ -17,6 +17,8 @@
 
 using namespace vb200;
 
+static_assert(kNPar == VB200_NPAR, "kernel row stride and VB200_NPAR differ");
+
 namespace {
 
 thread_local std::string g_err;
@@ -138,6 +140,11 @@ int check_model(const vb200_model_tables *m) {
         return fail(VB200_EINVAL, "model tables: bad sigma_v(r, mu) template");
     if (!(m->inv_h > 0.0) || !(m->iaH > 0.0) || !(m->template_sigma8 > 0.0))
         return fail(VB200_EINVAL, "model tables: bad scalars");
+    if (m->growth_mode < 0 || m->growth_mode > 2) return fail(VB200_EINVAL, "model tables: unknown growth_mode");
+    if (m->growth_mode == 2 && !(m->template_fsigma8 > 0.0))
+        return fail(VB200_EINVAL, "model tables: velocity template needs template_fsigma8");
+    if ((m->v0b == nullptr) != (m->d0b == nullptr) || (m->v0b && m->vd_beta_dependent))
+        return fail(VB200_EINVAL, "model tables: bad empirical-correction tables");
     return VB200_OK;
 }
 
@@ -332,7 +339,7 @@ int vb200_create(const vb200_model_tables *m, const vb200_fit_tables *f, int dev
     d.niter = m->niter;
     for (int i = 0; i < kMaxPoles; ++i) d.ells[i] = m->ells[i];
     c->tuned = (m->rsd_model == VB200_RSD_STREAMING && m->n_ell == 1 && !m->realspace_from_data && m->sv_ny == 0 &&
-                !m->vd_beta_dependent);
+                !m->vd_beta_dependent && !m->v0b);
     const size_t nc4 = (size_t)m->ncell * 4;
     if ((rc = upload(c, m->origin, (size_t)m->ncell, &d.origin))) return bail(rc);
     if ((rc = upload(c, m->upper, (size_t)m->ncell, &d.upper))) return bail(rc);
@@ -342,6 +349,14 @@ int vb200_create(const vb200_model_tables *m, const vb200_fit_tables *f, int dev
     d.vd_beta_dep = m->vd_beta_dependent;
     d.growth_mode = m->growth_mode;
     d.bias = m->bias;
+    d.lin_bias = m->linear_bias;
+    d.fs8t = m->template_fsigma8;
+    d.growth_scale = m->growth_scale;
+    d.v0b = d.d0b = nullptr;
+    if (m->v0b) {
+        if ((rc = upload(c, m->v0b, nc4, &d.v0b))) return bail(rc);
+        if ((rc = upload(c, m->d0b, nc4, &d.d0b))) return bail(rc);
+    }
     const size_t nvd = m->vd_beta_dependent ? (size_t)(m->nbeta - 1) * 4 * nc4 : nc4;
     if ((rc = upload(c, m->v0, nvd, &d.v0))) return bail(rc);
     if ((rc = upload(c, m->d0, nvd, &d.d0))) return bail(rc);

@@ -11,6 +11,8 @@ constexpr int kMaxPoles = 3;
 constexpr int kExpTab = 32;
 constexpr int kMaxNx = 128;       // velocity nodes that fit in the kernel-parameter table
 constexpr int kBucketFlag = (int)0x80000000;
+constexpr int kNPar = 10;         // doubles per parameter row (VB200_NPAR)
+constexpr int kNScal = 10;        // per-row scalars in shared memory (row_scalars_to_shared)
 
 enum { kRsdStreaming = 0, kRsdDispersion = 1, kRsdKaiser = 2, kRsdEuclid = 3 };
 
@@ -29,6 +31,9 @@ struct ModelDev {
     int sv_ny;
     int vd_beta_dep, growth_mode;   // matter model linear_bias: v0 / d0 beta power tables; growth = beta * bias
     double bias;
+    int lin_bias;           // v0 / d0 carry 1 / bias (matter model linear_bias): a per-row bias rescales them
+    double fs8t, growth_scale;      // growth_mode 2 (velocity template): A_v = fsigma8 / fs8t * growth_scale / apar
+    const double *v0b, *d0b;        // [ncell][4] empirical-correction parts: V0 = v0 + Av v0b (null if unused)
 };
 
 struct K1Args {
@@ -236,14 +241,17 @@ __device__ __forceinline__ double pin_f64(double v) {
 // ---------------------------------------------------------------------------------------
 // pieces shared by both K1 kernels
 // ---------------------------------------------------------------------------------------
-// per-row scalars, scal[8] in shared memory:
+// per-row scalars, scal[kNScal] in shared memory:
 //   [0] f        template rescaling factor (ccf_model.py:606-613)
 //   [1] aperp/f  [2] apar/f
 //   [3] kappa    sigma_v iaH apar / f : displacement in u-units per unit x
 //   [4] B        A_v / sigma_v, A_v = -growth / (3 iaH apar)               (:419, 435, 449)
-//   [5] G        iaH apar A_v / f = -growth / (3 f)   (dispersion / kaiser terms)
+//                (velocity template, growth_mode 2: A_v = fsigma8 / fs8t * growth_scale / apar, :439-443)
+//   [5] G        iaH apar A_v / f   (dispersion / kaiser terms)
 //   [6] apar     [7] aperp
-// warp 0 of the block computes the scalars of parameter row `pr` into shared `scal[8]`
+//   [8] Av       empirical correction amplitude of the mean velocity (:453), times model bias / row bias
+//                for the linear_bias matter model (delta carries 1 / bias, :367)
+// warp 0 of the block computes the scalars of parameter row `pr` into shared `scal[kNScal]`
 __device__ __forceinline__ void row_scalars_to_shared(const ModelDev &m, const double *pr, double *scal, int tid) {
     const double fs8 = pr[0], sigv = pr[2], aperp = pr[3], apar = pr[4], astar = pr[5];
     if (tid < 32) {
@@ -261,16 +269,30 @@ __device__ __forceinline__ void row_scalars_to_shared(const ModelDev &m, const d
         }
         if (tid == 0) {
             const double iaHt = m.iaH * apar;
-            const double g = m.growth_mode ? pr[1] * m.bias : fs8 / m.s8t;   // ccf_model.py:425-435
-            const double Av = -g / (3.0 * iaHt);
+            // a bias given with the row (params.get('bias', model['bias']), :359, :430) rescales the
+            // linear_bias profiles, which were tabulated with the model's bias; NaN = not given
+            const double brow = pr[9];
+            const bool has_b = m.lin_bias && (brow == brow);
+            const double bs = has_b ? m.bias / brow : 1.0;
+            double Av, G;
+            if (m.growth_mode == 2) {
+                Av = fs8 / m.fs8t * m.growth_scale / apar;                        // :439-443, :484
+                G = iaHt * Av / f;
+            } else {
+                const double g = (m.growth_mode ? pr[1] * (has_b ? brow : m.bias) : fs8 / m.s8t) * bs;   // :425-435
+                Av = -g / (3.0 * iaHt);
+                G = -g / (3.0 * f);
+            }
             scal[0] = f;
             scal[1] = aperp / f;
             scal[2] = apar / f;
             scal[3] = sigv * iaHt / f;
             scal[4] = Av / sigv;
-            scal[5] = -g / (3.0 * f);
+            scal[5] = G;
             scal[6] = apar;
             scal[7] = aperp;
+            scal[8] = pr[8] * bs;
+            scal[9] = 0.0;
         }
     }
 }

@@ -4,6 +4,7 @@
 //   anisotropic real-space input                victor/ccf_model.py:684-687  (assume_isotropic: False)
 //   real-space ccf measured from data           victor/ccf_model.py:675-679  (realspace_ccf.from_data)
 //   sigma_v(r, mu) dispersion templates         victor/ccf_model.py:654-655, 667-668 (3 template keys)
+//   empirical correction of the mean velocity   victor/ccf_model.py:451-459  (velocity_pdf.mean.empirical_corr)
 // and the streaming model combined with the last two.  Same tiling as the tuned kernel (one block
 // per parameter row x s-range, one thread per (s_j, mu_k) pair, velocity nodes in registers), plain
 // the same hand-rolled rsqrt / reciprocal / exp as the tuned kernel (kFast) or CUDA libm (a test
@@ -19,7 +20,7 @@ constexpr int kRecG = 26;
 constexpr int kGXi = 0, kGV0 = 12, kGD0 = 16, kGSV = 20, kGOrg = 24;
 
 __host__ __device__ inline size_t k1g_smem_bytes(int ncell, int jper, int nmu, int nbucket) {
-    size_t d = (size_t)ncell * (kRecG + 1) + kExpTab + (size_t)jper * nmu + 8;
+    size_t d = (size_t)ncell * (kRecG + 1) + kExpTab + (size_t)jper * nmu + kNScal;
     return d * sizeof(double) + (size_t)nbucket * sizeof(int);
 }
 
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
     double *etab = rec + (size_t)ncell * kRecG;
     double *stage = etab + kExpTab;
     double *scal = stage + (size_t)a.jper * a.nmu;
-    double *upper = scal + 8;
+    double *upper = scal + kNScal;
     int *bbase = reinterpret_cast<int *>(upper + ncell);
 
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
     const int jn = min(a.jper, a.ns - j0);
     if (jn <= 0) return;
 
-    const double *pr = a.params + row * 8;
+    const double *pr = a.params + row * kNPar;
     const double beta = m.beta_dependent ? pr[1] : m.beta_fixed;
     const double Mk = pr[6], Qk = pr[7];
 
@@ -134,7 +135,9 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
     for (int i = tid; i < m.nbucket; i += nthr) bbase[i] = m.bucket_base[i];
     if (tid < kExpTab) etab[tid] = m.exp_tab[tid];
     const unsigned etab_s = (unsigned)__cvta_generic_to_shared(etab);
+    if (m.v0b) __syncthreads();   // the cell records below need this row's empirical-correction amplitude
     {
+        const double Ae = m.v0b ? scal[8] : 0.0;
         int kb = 0;
         double tb = 0.0;
         if (m.beta_dependent) {
@@ -158,6 +161,9 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
                 const double *tv = m.v0 + (size_t)kb * 4 * per, *td = m.d0 + (size_t)kb * 4 * per;
                 r[kGV0 + c] = fma(fma(fma(tv[3 * per + i], tb, tv[2 * per + i]), tb, tv[per + i]), tb, tv[i]);
                 r[kGD0 + c] = fma(fma(fma(td[3 * per + i], tb, td[2 * per + i]), tb, td[per + i]), tb, td[i]);
+            } else if (m.v0b) {    // empirical correction (1 + Av delta(r)) of the mean velocity, ccf_model.py:451-459
+                r[kGV0 + c] = fma(Ae, m.v0b[i], m.v0[i]);
+                r[kGD0 + c] = fma(Ae, m.d0b[i], m.d0[i]);
             } else {
                 r[kGV0 + c] = m.v0[i];
                 r[kGD0 + c] = m.d0[i];

@@ -19,13 +19,13 @@ namespace vb200 {
 //                   stride 112 B = 28 banks, so 8 consecutive cells tile the 32 banks exactly)
 //   etab[32]        2^(j/32)
 //   stage[jper*nmu] xi(s_j, mu_k) of this block
-//   scal[8]         per-row scalars
+//   scal[kNScal]    per-row scalars
 //   upper[ncell]    upper knot of each cell (slow path of the cell search only)
 //   int bbase[nbucket]  bucket -> first cell; bit 31 set when a knot lies strictly inside the bucket
 constexpr int kRec = 14;
 
 __host__ __device__ inline size_t k1_smem_bytes(int ncell, int jper, int nmu, int nbucket) {
-    size_t d = (size_t)ncell * (kRec + 1) + kExpTab + (size_t)jper * nmu + 8;
+    size_t d = (size_t)ncell * (kRec + 1) + kExpTab + (size_t)jper * nmu + kNScal;
     return d * sizeof(double) + (size_t)nbucket * sizeof(int);
 }
 
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(256, 4) k_multipoles(const __grid_constant__ K
     double *etab = rec + (size_t)ncell * kRec;
     double *stage = etab + kExpTab;
     double *scal = stage + (size_t)a.jper * a.nmu;
-    double *upper = scal + 8;
+    double *upper = scal + kNScal;
     int *bbase = reinterpret_cast<int *>(upper + ncell);
 
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256, 4) k_multipoles(const __grid_constant__ K
     const int jn = min(a.jper, a.ns - j0);
     if (jn <= 0) return;
 
-    const double *pr = a.params + row * 8;
+    const double *pr = a.params + row * kNPar;
     const double beta = m.beta_dependent ? pr[1] : m.beta_fixed;
 
     // ---- per-row scalars (ccf_model.py:589-613; velocity amplitude :419, :435, :449) ----

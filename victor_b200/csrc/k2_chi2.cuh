@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(kK2Warps * 32) k_chi2(const __grid_constant__ 
     double *res = reinterpret_cast<double *>(smem_raw) + (size_t)warp * p;
     const long long row = (long long)blockIdx.x * kK2Warps + warp;
     if (row >= a.n) return;
-    const double beta = a.params[row * 8 + 1];
+    const double beta = a.params[row * kNPar + 1];
     const double *th = a.theory + (size_t)row * p;
 
     // residual against the PCHIP-in-beta data vector (ccf_fit.py:193, 322-323, 350)

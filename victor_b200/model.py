@@ -26,6 +26,20 @@ def _ext3_spline(x, y):
     return InterpolatedUnivariateSpline(x, y, ext=3)
 
 
+def _grid_multipoles(r, mu, f_rmu, ells, npts=200):
+    """Legendre multipoles at ``r`` of a function tabulated as f_rmu[len(r)][len(mu)], even in mu.
+
+    The reference's ``utils.multipoles_from_fn(interp2d(r, mu, f.T), r, ell)`` (utils.py:9-58): bilinear
+    interpolation (interp2d's default kind) to 200 mu values in [0, 1] -- arguments outside the table are
+    moved to its edge -- then (2l+1) x trapezoid of f L_l."""
+    r, mu = np.asarray(r, float), np.asarray(mu, float)
+    lin = RectBivariateSpline(r, mu, np.asarray(f_rmu, float), kx=1, ky=1, s=0)
+    fine = np.linspace(0.0, 1.0, npts)
+    rows = lin(r, np.clip(fine, mu.min(), mu.max()))            # [len(r)][npts]
+    return {f"{ell}": np.array([(2 * ell + 1) * trapezoid(row * legendre(ell)(fine), fine) for row in rows])
+            for ell in np.atleast_1d(ells)}
+
+
 def hubble_ratio(cosmology, z):
     """E(z) for LambdaCDM with Om, Ok, OL = 1 - Om - Ok and no radiation.
 
@@ -50,7 +64,7 @@ def params_to_rows(params, n_hint=None):
     (ccf_model.py:589-596): apar = alpha * epsilon^(-2/3), aperp = epsilon * apar.
     """
     defaults = {"fsigma8": np.nan, "beta": np.nan, "sigma_v": 380.0, "aperp": 1.0, "apar": 1.0,
-                "astar": 1.0, "M": 1.0, "Q": 1.0}
+                "astar": 1.0, "M": 1.0, "Q": 1.0, "Av": 0.0, "bias": np.nan}   # bias NaN: the model's own (:359)
     if isinstance(params, dict):
         # fast path for one parameter point given as plain numbers (the MCMC step): no array work
         get = params.get
@@ -62,7 +76,8 @@ def params_to_rows(params, n_hint=None):
                 aperp = eps * apar
             else:
                 aperp, apar = float(get("aperp", 1.0)), float(get("apar", 1.0))
-            row = [fs8, beta, sig, aperp, apar, float(get("astar", 1.0)), float(get("M", 1.0)), float(get("Q", 1.0))]
+            row = [fs8, beta, sig, aperp, apar, float(get("astar", 1.0)), float(get("M", 1.0)), float(get("Q", 1.0)),
+                   float(get("Av", 0.0)), float(get("bias", np.nan))]
             if not n_hint or n_hint == 1:
                 return np.array([row], dtype=np.float64)
         except TypeError:      # some value is an array: general path below
@@ -175,10 +190,28 @@ class CCFModel:
         isim = realspace_ccf.get("simulation_number", None)
         if isim is not None and not isinstance(isim, int):
             raise InputError("If provided, simulation_number must be an integer")
-        if fmt != "multipoles":
-            raise NotImplementedError("real-space ccf input in 'rmu' format has no B200 path; convert it to "
-                                      "multipoles first")
+        if fmt not in ("multipoles", "rmu"):
+            raise InputError(f"Unrecognised real-space ccf format {fmt}: options are 'multipoles' or 'rmu'")
         self.r = input_data[ccf_keys[0]]
+        if fmt == "rmu":
+            # xi(r, mu) on a grid -> multipoles 0, 2, 4 by bilinear interpolation and a 200-point trapezoid
+            # over mu in [0, 1] (ccf_model.py:154-181: interp2d(r, mu, xi.T) with its default kind='linear',
+            # then utils.multipoles_from_fn, utils.py:45-56)
+            mu = np.asarray(input_data[ccf_keys[1]], float)
+            real_ccf = input_data[ccf_keys[2]]
+            real_ccf = real_ccf if isim is None else real_ccf[isim]
+            self.poles_r = np.array([0, 2, 4])
+            if self.fixed_real_input:
+                if real_ccf.shape != (len(self.r), len(mu)):
+                    raise InputError(f"Shape of real ccf is {real_ccf.shape}, expected ({len(self.r)}, {len(mu)})")
+                self.real_multipoles = _grid_multipoles(self.r, mu, real_ccf, self.poles_r)
+            else:
+                want = (len(self.beta), len(self.r), len(mu))
+                if real_ccf.shape != want:
+                    raise InputError(f"Shape of real ccf is {real_ccf.shape}, expected {want}")
+                per_beta = [_grid_multipoles(self.r, mu, real_ccf[i], self.poles_r) for i in range(len(self.beta))]
+                self.real_multipoles = {f"{ell}": np.array([pb[f"{ell}"] for pb in per_beta]) for ell in self.poles_r}
+            return
         npole = len(ccf_keys) - 1
         self.poles_r = np.atleast_1d([0, 2, 4][:npole])
         self.real_multipoles = {}
@@ -222,9 +255,25 @@ class CCFModel:
         # reference: ccf_model.py:222-297
         mean_model = velocity_pdf["mean"].get("model", "linear")
         self.has_velocity_template = False
-        if mean_model == "template":
-            raise NotImplementedError("velocity mean model 'template' (a testing option of the reference) "
-                                      "has no B200 path")
+        if mean_model == "template":  # a testing option of the reference (ccf_model.py:227-246)
+            mean = velocity_pdf["mean"]
+            self.template_fsigma8 = mean.get("template_fsigma8")
+            if not self.template_fsigma8:
+                raise InputError("When using template model for the mean of the velocity pdf, a value for "
+                                 "template_fsigma8 must be provided")
+            self.z_sim = mean.get("z_sim", self.z_eff)
+            self.template_hubble_ratio = mean.get("template_hubble_ratio", 1)
+            template_keys = np.atleast_1d(mean.get("template_keys"))
+            if len(template_keys) != 2:
+                raise InputError(f"{len(template_keys)} velocity mean template keys provided, require 2")
+            for key in template_keys:
+                if key not in input_data:
+                    raise InputError(f"Key {key} not found in input model data file")
+            r_for_v, vr = input_data[template_keys[0]], input_data[template_keys[1]]
+            if len(r_for_v) != len(vr):
+                raise InputError(f"Shape of mean velocity template is {len(vr)}, expected {len(r_for_v)}")
+            self.radial_velocity = _ext3_spline(r_for_v, vr)
+            self.has_velocity_template = True
         if mean_model == "nonlinear" and self.matter_model != "excursion_set":
             raise InputError("Cannot have nonlinear mean velocity model unless using excursion_set matter model")
         dispersion = velocity_pdf.get("dispersion", {})

@@ -32,8 +32,9 @@ from .utils import InputError, trapezoid
 RSD_STREAMING, RSD_DISPERSION, RSD_KAISER, RSD_EUCLID = 0, 1, 2, 3
 LIKE_LINEAR, LIKE_LOG = 0, 1          # lnL = -a/2 chi2 + norm   |   lnL = -m/2 log(1 + chi2/(nm-1)) + norm
 MAX_POLES = 3
-NPAR = 8                               # fsigma8, beta, sigma_v, aperp, apar, astar, M, Q
-PARAM_ORDER = ("fsigma8", "beta", "sigma_v", "aperp", "apar", "astar", "M", "Q")
+NPAR = 10                              # fsigma8, beta, sigma_v, aperp, apar, astar, M, Q, Av, bias
+PARAM_ORDER = ("fsigma8", "beta", "sigma_v", "aperp", "apar", "astar", "M", "Q", "Av", "bias")
+GROWTH_FSIGMA8, GROWTH_BETA_BIAS, GROWTH_VELOCITY_TEMPLATE = 0, 1, 2
 
 
 # --------------------------------------------------------------------------------------------
@@ -259,8 +260,13 @@ class ModelTables:
     mu_resc: np.ndarray             # [50] nodes of the AP rescaling trapezoid
     w_resc: np.ndarray              # [50] its weights
     vd_beta_dependent: bool = False # v0 / d0 are [nbint][4][ncell][4] power tables in beta (linear_bias)
-    growth_mode: int = 0            # 0: fsigma8 / template_sigma8;  1: beta * bias (:429-430)
+    growth_mode: int = 0            # 0: fsigma8 / template_sigma8;  1: beta * bias (:429-430);  2: velocity template
     bias: float = 1.9
+    linear_bias: bool = False       # v0 / d0 carry 1 / bias: a bias given with the parameter row rescales them
+    template_fsigma8: float = 0.0   # growth_mode 2: v_r = V0(r) fsigma8 / template_fsigma8 growth_scale / apar (:439-443)
+    growth_scale: float = 1.0       # template_hubble_ratio (1 + z_sim) / (1 + z_eff)
+    v0b: np.ndarray = None          # [ncell][4] empirical correction: V0 = v0 + Av v0b, D0 = d0 + Av d0b (:451-459)
+    d0b: np.ndarray = None
     sv2d: np.ndarray = None         # [ncell][nyc][4][4] bicubic sigma_v(u, mu) patches, or None (isotropic)
     sv_ybreaks: np.ndarray = None   # [nyc + 1] mu breakpoints of sv2d
     from_data: bool = False         # real-space ccf measured from data: xi at (r_par/apar, s_perp/aperp)
@@ -325,9 +331,9 @@ def build_model_tables(state, options, nx=50):
     if options["matter_model"] not in ("template", "linear_bias"):
         raise NotImplementedError(
             f"matter_model '{options['matter_model']}' has no B200 path (only 'template' and 'linear_bias')")
-    if options["mean_model"] != "linear" or options["empirical_corr"]:
-        raise NotImplementedError("only the 'linear' mean-velocity model without empirical correction "
-                                  "has a B200 path")
+    if options["mean_model"] not in ("linear", "template"):
+        raise NotImplementedError(f"mean-velocity model '{options['mean_model']}' has no B200 path "
+                                  "(only 'linear' and 'template')")
     rsd = {"streaming": RSD_STREAMING, "dispersion": RSD_DISPERSION, "kaiser": RSD_KAISER,
            "euclid_special": RSD_EUCLID}.get(options["rsd_model"])
     if rsd is None:
@@ -342,24 +348,56 @@ def build_model_tables(state, options, nx=50):
     inv_h, base, maxscan = bucket_map(knots)
 
     beta_dep = not state.fixed_real_input
-    vd_beta_dep, growth_mode, bias = False, 0, float(options.get("bias", 1.9))
-    if options["matter_model"] == "template":
+    vd_beta_dep, growth_mode, bias = False, GROWTH_FSIGMA8, float(options.get("bias", 1.9))
+    linear_bias = options["matter_model"] == "linear_bias"
+    empirical = bool(options["empirical_corr"]) and options["mean_model"] == "linear"
+    template_fsigma8, growth_scale = 0.0, 1.0
+    v0b = d0b = None
+    r_fine = np.linspace(0.1, r.max(), 100)      # "finer grid to better estimate derivative numerically" (:456, :486)
+
+    def slope_at_r31(values_on_fine_grid):
+        # dvr_interp = _spline(rgrid, np.gradient(vr_grid, rgrid), ext=3); dvr = dvr_interp(r)   (:457-459, 487-488)
+        return InterpolatedUnivariateSpline(r_fine, np.gradient(values_on_fine_grid, r_fine), ext=3)(r31)
+
+    def velocity_cells(d31, D31):
+        """(v0, d0, v0b, d0b) cell cubics from delta(r31), Delta(r31): v_r = A_v (v0 + Av v0b)(r),
+        dv_r/dr = A_v (d0 + Av d0b)(r) with A_v = -growth / (3 iaH)   (ccf_model.py:446-459)."""
+        if not empirical:
+            # velocity_terms() re-splines the profiles at their own abscissae before use (:422-423);
+            # an interpolating spline evaluated at its knots returns the data, so V0/D0 data are:
+            return (spline_cells(r31, r31 * D31, knots),
+                    spline_cells(r31, 3.0 * (d31 - 2.0 * D31 / 3.0), knots), None, None)
+        dS = InterpolatedUnivariateSpline(r31, d31, ext=3)          # :422-423
+        DS = InterpolatedUnivariateSpline(r31, D31, ext=3)
+        base, corr = r_fine * DS(r_fine), r_fine * DS(r_fine) * dS(r_fine)
+        return (spline_cells(r31, r31 * D31, knots), spline_cells(r31, slope_at_r31(base), knots),
+                spline_cells(r31, r31 * D31 * d31, knots), spline_cells(r31, slope_at_r31(corr), knots))
+
+    if options["mean_model"] == "template":
+        # velocity template (a testing option of the reference, ccf_model.py:227-246, 439-443, 483-488):
+        # v_r = radial_velocity(r) * growth', growth' = fsigma8 / template_fsigma8 * hubble ratio * (1+z_sim)/(1+z_eff) / apar
+        if not getattr(state, "has_velocity_template", False):
+            raise InputError("velocity_terms: Cannot use template option as no template has been supplied.")
+        growth_mode = GROWTH_VELOCITY_TEMPLATE
+        template_fsigma8 = float(state.template_fsigma8)
+        growth_scale = float(state.template_hubble_ratio) * (1 + state.z_sim) / (1 + state.z_eff)
+        v0 = spline_cells(r31, state.radial_velocity(r31), knots)
+        d0 = spline_cells(r31, slope_at_r31(state.radial_velocity(r_fine)), knots)
+    elif options["matter_model"] == "template":
         # velocity templates (ccf_model.py:421-423, 449-450, 635-636): data at r31, knots r31
-        D31 = state.integrated_delta(r31)
-        d31 = state.delta(r31)
-        # velocity_terms() re-splines the profiles at their own abscissae before use (:422-423);
-        # an interpolating spline evaluated at its knots returns the data, so V0/D0 data are:
-        v0 = spline_cells(r31, r31 * D31, knots)
-        d0 = spline_cells(r31, 3.0 * (d31 - 2.0 * D31 / 3.0), knots)
+        v0, d0, v0b, d0b = velocity_cells(state.delta(r31), state.integrated_delta(r31))
     else:
         # linear_bias (ccf_model.py:358-370): delta = xi_0 / b, Delta(r) = 3 / (b r^3) times a 100-point
         # trapezoid of xi_0 r'^2 -- both linear in the monopole values, which are PCHIP cubics in beta:
         # the V0 / D0 cell cubics are therefore, per beta interval, cubics in (beta - beta_k) too
         Ld, LD = linear_bias_maps(r, r31)
         if options["realspace_ccf_from_data"]:
-            growth_mode = 1                       # growth term beta * bias (:429-430)
+            growth_mode = GROWTH_BETA_BIAS        # growth term beta * bias (:429-430)
         mono = np.asarray(state.real_multipoles["0"], float)
         if beta_dep:
+            if empirical:
+                raise NotImplementedError("empirical_corr with a beta-dependent linear_bias matter model has no "
+                                          "B200 path (delta * Delta is not a cubic in beta)")
             vd_beta_dep = True
             pw = pchip_power_table(np.asarray(state.beta, float), mono)      # (nbint, 4, nr)
             v0 = np.zeros((pw.shape[0], 4, ncell, 4))
@@ -370,9 +408,7 @@ def build_model_tables(state, options, nx=50):
                     v0[k, q] = spline_cells(r31, r31 * D31, knots)
                     d0[k, q] = spline_cells(r31, 3.0 * (d31 - 2.0 * D31 / 3.0), knots)
         else:
-            D31, d31 = LD @ mono / bias, Ld @ mono / bias
-            v0 = spline_cells(r31, r31 * D31, knots)
-            d0 = spline_cells(r31, 3.0 * (d31 - 2.0 * D31 / 3.0), knots)
+            v0, d0, v0b, d0b = velocity_cells(Ld @ mono / bias, LD @ mono / bias)
 
     # sigma_v template: all mu rows identical -> 1-D cubic spline in u (FITPACK tensor spline of a
     # function constant in mu is that 1-D spline)
@@ -416,7 +452,8 @@ def build_model_tables(state, options, nx=50):
         bucket_base=base, maxscan=maxscan, beta_grid=beta_grid,
         xi_tab=np.ascontiguousarray(xi_tab), v0=v0, d0=d0, sv=sv,
         x=x, wx=w / np.sqrt(2 * np.pi), mu_resc=mu_resc, w_resc=w_resc,
-        vd_beta_dependent=vd_beta_dep, growth_mode=growth_mode, bias=bias,
+        vd_beta_dependent=vd_beta_dep, growth_mode=growth_mode, bias=bias, linear_bias=linear_bias,
+        template_fsigma8=template_fsigma8, growth_scale=growth_scale, v0b=v0b, d0b=d0b,
         sv2d=sv2d, sv_ybreaks=sv_ybreaks, from_data=bool(options["realspace_ccf_from_data"]),
         kaiser_approximation=bool(options.get("kaiser_approximation", False)),
         kaiser_coord_shift=bool(options.get("kaiser_coord_shift", True)), niter=5)
