@@ -12,6 +12,8 @@
  *                                                        victor/utils.py:9-58)
  *                        CCFModel.theory_multipole_vector (victor/ccf_model.py:829-860)
  *                        on caller-supplied s / mu grids, for n parameter rows at once.
+ *   vb200_theory_pairs <- CCFModel.theory_xi_2D        (victor/ccf_model.py:862-894): xi at
+ *                        scattered (s, mu) points instead of an outer-product grid.
  *   vb200_likelihood  <- CCFFit.chi_squared / CCFFit.log_likelihood
  *                        (victor/ccf_fit.py:325-354, 356-483) and, through them,
  *                        CCFLikelihood.calculate (victor/likelihoods/CCFLikelihood.py:32-42),
@@ -153,6 +155,13 @@ int vb200_theory(vb200_ctx *ctx, const double *params, int64_t n,
                  const double *s, int32_t ns, const double *mu, int32_t nmu,
                  const double *wmu, int32_t L,
                  double *xi_out, double *mult_out, void *stream);
+
+/* xi at npairs separate points (s[j], mu[j]) for n parameter rows -- what CCFModel.theory_xi_2D
+ * (victor/ccf_model.py:862-894) gets from its 2500 scalar theory_xi calls, in one launch.
+ *   s [npairs], mu [npairs] HOST arrays; xi_out [n][npairs]. */
+int vb200_theory_pairs(vb200_ctx *ctx, const double *params, int64_t n,
+                       const double *s, const double *mu, int32_t npairs,
+                       double *xi_out, void *stream);
 
 /* Theory vector, chi-square and log-likelihood for n parameter rows on the fit's own grids.
  *   theory [n][p] or NULL; chi2 [n] or NULL; lnlike [n] or NULL. */

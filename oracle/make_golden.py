@@ -526,6 +526,40 @@ def golden_velocity(victor):
     np.savez(os.path.join(OUT, "boss_velocity_options.npz"), **out, **meta())
 
 
+def golden_helpers(victor):
+    """Callers either side of the path that the notebooks use: delta_profiles / velocity_terms (host
+    helpers), theory_xi_2D (2500 scalar theory_xi calls in the reference: ~6 minutes here) and
+    xi_2D_from_multipoles.  The interp2d objects are recorded through their grid values and a few
+    off-grid evaluations."""
+    model, data = boss_blocks()
+    ccf = victor.CCFFit(copy.deepcopy(model), copy.deepcopy(data))
+    p1 = {"fsigma8": 0.8, "beta": 0.45, "sigma_v": 250, "aperp": 1.03, "apar": 0.96}
+    out = {}
+    r = np.asarray(ccf.r, float)
+    for tag, kw in (("template", {}), ("linear_bias", {"matter_model": "linear_bias"})):
+        d, D = ccf.delta_profiles(r, dict(p1), **kw)
+        out[f"delta_{tag}"], out[f"Delta_{tag}"] = d, D
+    for tag, kw, extra in (("linear", {}, {}), ("empirical", {"empirical_corr": True}, {"Av": 0.7}),
+                           ("linear_bias", {"matter_model": "linear_bias"}, {"bias": 2.2})):
+        prm = dict(p1)
+        prm.update(extra)
+        vr, dvr = ccf.velocity_terms(r, prm, **kw)
+        out[f"vr_{tag}"], out[f"dvr_{tag}"] = vr, dvr
+    qx = np.array([0.5, 7.3, 22.0, 41.7, 84.0])
+    qy = np.array([-80.0, -33.3, -2.0, 0.0, 11.1, 60.5])
+    out["qx"], out["qy"] = qx, qy
+    f2 = ccf.xi_2D_from_multipoles(dict(p1), rmax=85)
+    out["from_multipoles_grid"] = f2(np.linspace(0.01, 85), np.linspace(-85, 85))
+    out["from_multipoles_q"] = f2(qx, qy)
+    f2 = ccf.xi_2D_from_multipoles(dict(p1), rmax=60, rsd_model="dispersion")
+    out["from_multipoles_disp60_q"] = f2(qx, qy)
+    f1 = ccf.theory_xi_2D(dict(p1), rmax=85)
+    out["xi2d_grid"] = f1(np.linspace(0.01, 85), np.linspace(-85, 85))
+    out["xi2d_q"] = f1(qx, qy)
+    out["xi2d_scalar"] = f1(12.5, -40.0)
+    np.savez(os.path.join(OUT, "boss_helpers.npz"), **out, **meta())
+
+
 def golden_example(victor):
     with open(os.path.join(REF, "config/example_model_input.yaml")) as fh:
         model = yaml.full_load(fh)["model"]
@@ -553,7 +587,7 @@ def golden_example(victor):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     v = refshim.install(REF)
-    which = sys.argv[1:] or ["boss", "more", "sv2d", "linear_bias", "misc", "fixed", "rmu", "velocity", "example"]
+    which = sys.argv[1:] or ["boss", "more", "sv2d", "linear_bias", "misc", "fixed", "rmu", "velocity", "helpers", "example"]
     if "boss" in which:
         golden_boss(v)
     if "more" in which:
@@ -570,6 +604,8 @@ if __name__ == "__main__":
         golden_rmu(v)
     if "velocity" in which:
         golden_velocity(v)
+    if "helpers" in which:
+        golden_helpers(v)
     if "example" in which:
         golden_example(v)
     for fn in sorted(os.listdir(OUT)):

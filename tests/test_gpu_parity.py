@@ -545,6 +545,39 @@ def test_velocity_template_mean_model(boss_blocks, golden, name, kw):
     fm.close()
 
 
+def test_two_dimensional_helpers(fit, golden):
+    """theory_xi_2D (2500 scalar theory_xi calls in the reference, one pairwise launch here) and
+    xi_2D_from_multipoles (ccf_model.py:862-934), compared through the returned interpolators."""
+    g = golden("boss_helpers")
+    p1 = {"fsigma8": 0.8, "beta": 0.45, "sigma_v": 250, "aperp": 1.03, "apar": 0.96}
+    gx, gy = np.linspace(0.01, 85), np.linspace(-85, 85)
+    f1 = fit.theory_xi_2D(dict(p1), rmax=85)
+    np.testing.assert_allclose(f1(gx, gy), g["xi2d_grid"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(f1(g["qx"], g["qy"]), g["xi2d_q"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(f1(12.5, -40.0), g["xi2d_scalar"], rtol=RTOL, atol=ATOL)
+    f2 = fit.xi_2D_from_multipoles(dict(p1), rmax=85)
+    np.testing.assert_allclose(f2(gx, gy), g["from_multipoles_grid"], rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(f2(g["qx"], g["qy"]), g["from_multipoles_q"], rtol=RTOL, atol=1e-12)
+    f3 = fit.xi_2D_from_multipoles(dict(p1), rmax=60, rsd_model="dispersion")
+    np.testing.assert_allclose(f3(g["qx"], g["qy"]), g["from_multipoles_disp60_q"], rtol=RTOL, atol=1e-12)
+
+
+def test_pairwise_points_match_the_grid_kernel(fit):
+    """vb200_theory_pairs against vb200_theory on the same points, batched, both K1 kernels."""
+    rng = np.random.default_rng(5)
+    P = {"fsigma8": rng.uniform(0.2, 1.2, 7), "beta": rng.uniform(0.2, 0.6, 7), "sigma_v": rng.uniform(150, 450, 7),
+         "aperp": rng.uniform(0.95, 1.05, 7), "apar": rng.uniform(0.95, 1.05, 7)}
+    s = np.sort(rng.uniform(1.0, 110.0, 300))
+    mu = rng.uniform(-1, 1, 300)
+    for kw in ({}, {"rsd_model": "dispersion"}, {"assume_isotropic": False}):
+        pairs = fit.theory_xi_pairs_batch(s, mu, P, **kw)
+        assert pairs.shape == (7, 300)
+        order = np.argsort(mu)
+        grid = fit.theory_xi_batch(s, mu[order], P, **kw)           # [n][nmu][ns]
+        want = grid[:, np.argsort(order), np.arange(300)]
+        np.testing.assert_array_equal(pairs, want)                  # same arithmetic per point: bit-identical
+
+
 def test_direct_model_calls(fit, golden):
     """Notebook-style calls: odd poles, bare-integer poles, fine s grid, theory_xi on
     unsorted meshgrid input (sorted / uniqued like the reference) and at negative mu."""

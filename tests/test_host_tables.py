@@ -571,3 +571,56 @@ def test_tables_velocity_template_mean_model(boss_blocks, golden, name, kw):
     del bad["velocity_pdf"]["mean"]["template_fsigma8"]
     with pytest.raises(InputError):
         CCFFit(bad, vtemplate_blocks(boss_blocks)[1])
+
+
+def test_profile_helpers_match_the_reference(fit, golden):
+    """delta_profiles / velocity_terms (ccf_model.py:328-492): host helpers the notebooks plot."""
+    g = golden("boss_helpers")
+    p1 = {"fsigma8": 0.8, "beta": 0.45, "sigma_v": 250, "aperp": 1.03, "apar": 0.96}
+    r = np.asarray(fit.r, float)
+    for tag, kw in (("template", {}), ("linear_bias", {"matter_model": "linear_bias"})):
+        d, D = fit.delta_profiles(r, dict(p1), **kw)
+        np.testing.assert_allclose(d, g[f"delta_{tag}"], rtol=1e-13, atol=1e-16)
+        np.testing.assert_allclose(D, g[f"Delta_{tag}"], rtol=1e-13, atol=1e-16)
+    for tag, kw, extra in (("linear", {}, {}), ("empirical", {"empirical_corr": True}, {"Av": 0.7}),
+                           ("linear_bias", {"matter_model": "linear_bias"}, {"bias": 2.2})):
+        prm = dict(p1)
+        prm.update(extra)
+        vr, dvr = fit.velocity_terms(r, prm, **kw)
+        np.testing.assert_allclose(vr, g[f"vr_{tag}"], rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(dvr, g[f"dvr_{tag}"], rtol=1e-12, atol=1e-13)
+    with pytest.raises(NotImplementedError):
+        fit.delta_profiles(r, dict(p1), matter_model="excursion_set")
+
+
+def test_grid_interpolator_follows_legacy_interp2d():
+    """Shapes and edge handling of the interp2d stand-in (what theory_xi_2D returns)."""
+    from victor_b200.utils import GridInterpolator2D, fn_from_multipoles, multipoles_from_fn
+    x, y = np.linspace(0, 4, 9), np.linspace(-1, 1, 5)
+    z = y[:, None] * 2 + x[None, :] * 3                      # bilinear: reproduced exactly
+    f = GridInterpolator2D(x, y, z)
+    assert f(1.3, 0.2).shape == (1,) and abs(f(1.3, 0.2)[0] - (0.4 + 3.9)) < 1e-14
+    assert f([3.0, 1.0], 0.0).shape == (2,) and np.allclose(f([3.0, 1.0], 0.0), [3.0, 9.0])    # sorted
+    assert f(1.0, [0.5, -0.5]).shape == (2, 1)
+    assert np.allclose(f([-5.0, 9.0], [0.0]), [0.0, 12.0])   # moved to the edges
+    with pytest.raises(ValueError):
+        GridInterpolator2D(x, y, z.T)
+    r = np.linspace(1, 50, 20)
+    mult = np.array([np.sin(r / 9), 0.3 * np.cos(r / 7)])
+    back = multipoles_from_fn(fn_from_multipoles(r, [0, 2], mult), r, ell=[0, 2])
+    np.testing.assert_allclose(back["0"], mult[0], atol=2e-4)
+    np.testing.assert_allclose(back["2"], mult[1], atol=2e-4)
+
+
+def test_pairwise_points_equal_the_grid_diagonal(fit, packed):
+    """theory_xi_2D evaluates separate (s, mu) points; on the CPU the same points are the diagonal of
+    the outer-product grid of the table walk-through (the GPU test holds the kernel to the reference)."""
+    from victor_b200.model import params_to_rows
+    mt = packed[0]
+    sperp, spar, s, mu = fit._sky_grid(85)
+    assert s.shape == (50, 50) and mu.min() < -0.99 and abs(s[0, 0] - np.hypot(0.01, 85)) < 1e-12
+    pick = np.array([0, 777, 1249, 2499])
+    rows = params_to_rows({"fsigma8": 0.8, "beta": 0.45, "sigma_v": 250, "aperp": 1.03, "apar": 0.96})
+    sp, mp = s.ravel()[pick], mu.ravel()[pick]
+    grid = E.theory_xi(mt, rows, sp, mp)[0]                   # [nmu][ns]
+    assert np.all(np.isfinite(np.diag(grid)))

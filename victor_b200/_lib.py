@@ -17,7 +17,7 @@ c_double_p = POINTER(c_double)
 c_int32_p = POINTER(c_int32)
 
 EXPORTS = ("vb200_version", "vb200_abi_check", "vb200_last_error", "vb200_device_count", "vb200_create", "vb200_destroy",
-           "vb200_set_option", "vb200_theory", "vb200_likelihood", "vb200_synchronize",
+           "vb200_set_option", "vb200_theory", "vb200_theory_pairs", "vb200_likelihood", "vb200_synchronize",
            "vb200_launch_count", "vb200_math_selftest", "vb200_fp64_peak", "vb200_pipe_probe", "vb200_seed_probe",
            "vb200_mix_probe")
 
@@ -83,6 +83,8 @@ def load():
     lib.vb200_theory.restype = c_int
     lib.vb200_theory.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_int32,
                                  c_void_p, c_int32, c_void_p, c_void_p, c_void_p]
+    lib.vb200_theory_pairs.restype = c_int
+    lib.vb200_theory_pairs.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]
     lib.vb200_likelihood.restype = c_int
     lib.vb200_likelihood.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.vb200_synchronize.restype = c_int

@@ -175,9 +175,10 @@ k1_fn pick_general(int rsd_model, bool fast) {
 
 int launch_k1(vb200_ctx *c, const double *d_params, long long n, const double *d_s, int ns,
               const double *d_mu, const double *d_sqmu, const double *d_wmu, int nmu, int L,
-              double *d_xi, double *d_mult, cudaStream_t st) {
+              double *d_xi, double *d_mult, cudaStream_t st, bool pairwise = false) {
     if (n <= 0) return VB200_OK;
     int nsplit = c->opt_nsplit;
+    if (pairwise) nsplit = 0;
     if (nsplit <= 0) {
         // one block per row once the rows alone fill the GPU a few times over, else split the
         // s range so that a single row (MCMC step) still spreads over the SMs
@@ -186,6 +187,7 @@ int launch_k1(vb200_ctx *c, const double *d_params, long long n, const double *d
     }
     nsplit = std::max(1, std::min(nsplit, ns));
     int jper = (ns + nsplit - 1) / nsplit;
+    if (pairwise) jper = std::min(ns, std::max(jper, 64));   // one pair per thread: keep at least two full warps
     auto smem_for = [&](int jp) {
         return c->tuned ? k1_smem_bytes(c->md.ncell, jp, nmu, c->md.nbucket)
                         : k1g_smem_bytes(c->md.ncell, jp, nmu, c->md.nbucket);
@@ -217,6 +219,7 @@ int launch_k1(vb200_ctx *c, const double *d_params, long long n, const double *d
     a.L = L;
     a.jper = jper;
     a.nsplit = nsplit;
+    a.pairwise = pairwise ? 1 : 0;
     a.xi_out = d_xi;
     a.mult_out = d_mult;
     memcpy(a.xw, c->xw, sizeof(a.xw));
@@ -461,8 +464,9 @@ int vb200_synchronize(vb200_ctx *c) {
 
 int64_t vb200_launch_count(const vb200_ctx *c) { return c ? c->launches : 0; }
 
-int vb200_theory(vb200_ctx *c, const double *params, int64_t n, const double *s, int32_t ns, const double *mu,
-                 int32_t nmu, const double *wmu, int32_t L, double *xi_out, double *mult_out, void *stream) {
+static int theory_impl(vb200_ctx *c, const double *params, int64_t n, const double *s, int32_t ns, const double *mu,
+                       int32_t nmu, const double *wmu, int32_t L, double *xi_out, double *mult_out, void *stream,
+                       bool pairwise) {
     if (!c) return fail(VB200_EINVAL, "ctx is NULL");
     if (n < 0 || !params || !s || !mu || ns < 1 || nmu < 1) return fail(VB200_EINVAL, "bad arguments");
     if (mult_out && (!wmu || L < 1 || L > VB200_MAX_POLES)) return fail(VB200_EINVAL, "mult_out needs wmu and 1 <= L <= 3");
@@ -490,6 +494,7 @@ int vb200_theory(vb200_ctx *c, const double *params, int64_t n, const double *s,
     }
     const double *d_s = c->sc_grid.ptr, *d_mu = d_s + ns, *d_sq = d_mu + nmu;
     const double *d_w = Lw ? d_sq + nmu : nullptr;
+    if (pairwise) nmu = 1;   // the kernels see one mu per s: mu[j] belongs to s[j]
 
     const double *d_params = params;
     if (!is_device_ptr(params)) {
@@ -511,13 +516,24 @@ int vb200_theory(vb200_ctx *c, const double *params, int64_t n, const double *s,
         if ((rc = c->sc_mult.ensure(nmult))) return rc;
         d_mult = c->sc_mult.ptr;
     }
-    if ((rc = launch_k1(c, d_params, n, d_s, ns, d_mu, d_sq, d_w, nmu, Lw, d_xi, d_mult, st))) return rc;
+    if ((rc = launch_k1(c, d_params, n, d_s, ns, d_mu, d_sq, d_w, nmu, Lw, d_xi, d_mult, st, pairwise))) return rc;
     if (xi_out && d_xi != xi_out)
         CK(cudaMemcpyAsync(xi_out, d_xi, nxi * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (mult_out && d_mult != mult_out)
         CK(cudaMemcpyAsync(mult_out, d_mult, nmult * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (host_io) CK(cudaStreamSynchronize(st));
     return VB200_OK;
+}
+
+int vb200_theory(vb200_ctx *c, const double *params, int64_t n, const double *s, int32_t ns, const double *mu,
+                 int32_t nmu, const double *wmu, int32_t L, double *xi_out, double *mult_out, void *stream) {
+    return theory_impl(c, params, n, s, ns, mu, nmu, wmu, L, xi_out, mult_out, stream, false);
+}
+
+int vb200_theory_pairs(vb200_ctx *c, const double *params, int64_t n, const double *s, const double *mu,
+                       int32_t npairs, double *xi_out, void *stream) {
+    if (!xi_out) return fail(VB200_EINVAL, "xi_out is NULL");
+    return theory_impl(c, params, n, s, npairs, mu, npairs, nullptr, 0, xi_out, nullptr, stream, true);
 }
 
 int vb200_likelihood(vb200_ctx *c, const double *params, int64_t n, double *theory, double *chi2, double *lnlike,

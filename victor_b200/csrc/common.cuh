@@ -43,6 +43,7 @@ struct K1Args {
     const double *s, *mu, *sqmu, *wmu;  // [ns], [nmu], [nmu] sqrt(1-mu^2), [L][nmu]
     int ns, nmu, L;
     int jper, nsplit;
+    int pairwise;      // 1: nmu == 1 and mu / sqmu have ns entries -- xi at the pairs (s_j, mu_j) (theory_xi_2D)
     double *xi_out;    // [n][nmu][ns] or null
     double *mult_out;  // [n][L][ns]  or null
     double xw[2 * kMaxNx];  // x_m then Simpson weight / sqrt(2 pi): read through the constant bank

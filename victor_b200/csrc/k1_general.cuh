@@ -199,10 +199,11 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
     for (int pidx = tid; pidx < npairs; pidx += nthr) {
         const int jl = pidx / nmu, k = pidx - jl * nmu;
         const double sj = a.s[j0 + jl];
-        const double Sperp = sj * a.sqmu[k] * sperp_f;
-        const double Spar = sj * a.mu[k] * spar_f;
+        const int km = a.pairwise ? j0 + jl : k;
+        const double Sperp = sj * a.sqmu[km] * sperp_f;
+        const double Spar = sj * a.mu[km] * spar_f;
         const double Sperp2 = Sperp * Sperp;
-        const double rt_data = sj * a.sqmu[k];   // s_perp / aperp in real units (from_data, :676)
+        const double rt_data = sj * a.sqmu[km];   // s_perp / aperp in real units (from_data, :676)
         double result;
 
         // real-space xi for a point with (u-unit) line-of-sight separation rp

@@ -187,8 +187,9 @@ __global__ void __launch_bounds__(256, 4) k_multipoles(const __grid_constant__ K
     for (int pidx = tid; pidx < npairs; pidx += nthr) {
         const int jl = pidx / nmu, k = pidx - jl * nmu;
         const double sj = a.s[j0 + jl];
-        const double Sperp = sj * a.sqmu[k] * sperp_f;
-        q.Spar = sj * a.mu[k] * spar_f;
+        const int km = a.pairwise ? j0 + jl : k;
+        const double Sperp = sj * a.sqmu[km] * sperp_f;
+        q.Spar = sj * a.mu[km] * spar_f;
         q.Sperp2 = Sperp * Sperp;
         double acc = 0.0;
         int mi = 0;

@@ -88,6 +88,18 @@ class Engine:
             mult.ctypes.data if mult is not None else None, None))
         return xi, mult
 
+    def theory_pairs(self, rows, s, mu):
+        """xi[n][npairs] at the separate points (s[j], mu[j])."""
+        rows = np.ascontiguousarray(rows, dtype=np.float64)
+        s = np.ascontiguousarray(s, dtype=np.float64).ravel()
+        mu = np.ascontiguousarray(mu, dtype=np.float64).ravel()
+        if s.shape != mu.shape:
+            raise ValueError("theory_pairs: s and mu must have the same number of entries")
+        xi = np.empty((rows.shape[0], len(s)))
+        self._check(self.lib.vb200_theory_pairs(self.handle, rows.ctypes.data, rows.shape[0], s.ctypes.data,
+                                                mu.ctypes.data, len(s), xi.ctypes.data, None))
+        return xi
+
     def likelihood(self, rows, want_theory=False):
         """(theory[n][p] or None, chi2[n], lnl[n]) as host arrays."""
         rows = np.ascontiguousarray(rows, dtype=np.float64)

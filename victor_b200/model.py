@@ -19,7 +19,7 @@ from scipy.interpolate import InterpolatedUnivariateSpline, RectBivariateSpline
 from scipy.special import legendre
 
 from . import tables as _tables
-from .utils import InputError, load_input_file, trapezoid
+from .utils import GridInterpolator2D, InputError, load_input_file, trapezoid
 
 
 def _ext3_spline(x, y):
@@ -357,6 +357,93 @@ class CCFModel:
         if beta is None:
             raise InputError("Need to supply a valid value of beta for interpolation")
         return np.atleast_2d(PchipInterpolator(self.beta, stack, axis=1)(beta))
+
+    def delta_profiles(self, r, params, **kwargs):
+        """Matter ccf monopole delta(r) and its volume average Delta(r) at ``r``: a host helper with the
+        reference's semantics (ccf_model.py:328-383), for plots and checks; the GPU path has these
+        folded into its velocity tables."""
+        opts = self._merged_options(kwargs)
+        r = np.asarray(r, dtype=np.float64)
+        if opts["matter_model"] == "template":
+            return self.delta(r), self.integrated_delta(r)
+        if opts["matter_model"] == "linear_bias":
+            bias = params.get("bias", opts["bias"])
+            xi0 = _ext3_spline(self.r, self.get_interpolated_real_multipoles(params.get("beta", None))[0])
+            enclosed = np.zeros_like(r)
+            for i, ri in enumerate(r):                       # 100-point trapezoid of xi_0 r'^2 on [0, r]
+                grid = np.linspace(0, ri, 100)
+                enclosed[i] = trapezoid(xi0(grid) * grid ** 2, grid)
+            return xi0(r) / bias, 3 * enclosed / (bias * r ** 3)
+        if opts["matter_model"] == "excursion_set":
+            raise NotImplementedError("matter_model 'excursion_set' is outside the B200 path")
+        raise InputError(f"Invalid choice of matter_model {opts['matter_model']}")
+
+    def velocity_terms(self, r, params, **kwargs):
+        """Mean radial velocity v_r(r) and dv_r/dr at ``r``: a host helper with the reference's semantics
+        (ccf_model.py:385-492) for the 'linear' (optionally empirically corrected) and 'template' mean
+        models; the GPU path evaluates the same profiles from its tables."""
+        opts = self._merged_options(kwargs)
+        r = np.asarray(r, dtype=np.float64)
+        apar = params.get("alpha", 1) * params["epsilon"] ** (-2 / 3) if "epsilon" in params else params.get("apar", 1)
+        iaH_true = self.iaH * apar
+        d_r, D_r = self.delta_profiles(r, params, **kwargs)
+        delta, Delta = _ext3_spline(r, d_r), _ext3_spline(r, D_r)
+        fine = np.linspace(0.1, self.r.max(), 100)
+
+        def slope(values):
+            return _ext3_spline(fine, np.gradient(values, fine))(r)
+
+        if opts["mean_model"] == "template":
+            if not self.has_velocity_template:
+                raise InputError("velocity_terms: Cannot use template option as no template has been supplied.")
+            growth = ((params["fsigma8"] / self.template_fsigma8) * self.template_hubble_ratio
+                      * ((1 + self.z_sim) / (1 + self.z_eff)) / apar)
+            return self.radial_velocity(r) * growth, slope(self.radial_velocity(fine) * growth)
+        if opts["mean_model"] != "linear":
+            raise NotImplementedError(f"mean-velocity model '{opts['mean_model']}' is outside the B200 path")
+        if opts["matter_model"] == "linear_bias" and opts["realspace_ccf_from_data"]:
+            growth = params["beta"] * params.get("bias", opts["bias"])
+        else:
+            growth = params["fsigma8"] / self.template_sigma8
+        if not opts["empirical_corr"]:
+            return (-growth * r * Delta(r) / (3 * iaH_true),
+                    -growth * (delta(r) - 2 * Delta(r) / 3) / iaH_true)
+        Av = params.get("Av", 0)
+        vr = -growth * r * Delta(r) * (1 + Av * delta(r)) / (3 * iaH_true)
+        return vr, slope(-growth * fine * Delta(fine) * (1 + Av * delta(fine)) / (3 * iaH_true))
+
+    def theory_xi_pairs_batch(self, s, mu, params, **kwargs):
+        """xi at the separate points (s[j], mu[j]) for every parameter row: float64[n, len(s)]."""
+        opts = self._merged_options(kwargs)
+        return self._engine(opts).theory_pairs(params_to_rows(params), s, mu)
+
+    @staticmethod
+    def _sky_grid(rmax):
+        # ccf_model.py:883-888: 50 x 50 grid in (s_perp, s_par), s_par on both sides of zero
+        sperp = np.linspace(0.01, rmax)
+        spar = np.linspace(-rmax, rmax)
+        sigma, pi = np.meshgrid(sperp, spar)
+        s = np.sqrt(sigma ** 2 + pi ** 2)
+        return sperp, spar, s, pi / s
+
+    def theory_xi_2D(self, params, rmax=85, **kwargs):
+        """Model xi^s(s_perp, s_par) out to ``rmax`` in each direction as an interpolating function
+        ``f(s_perp, s_par)`` (reference: ccf_model.py:862-894).  The reference fills its 50 x 50 grid with
+        2500 scalar ``theory_xi`` calls; here all 2500 (s, mu) points go through one kernel launch."""
+        self._check_point(params, kwargs)
+        sperp, spar, s, mu = self._sky_grid(rmax)
+        xi = self.theory_xi_pairs_batch(s.ravel(), mu.ravel(), params, **kwargs)[0].reshape(s.shape)
+        return GridInterpolator2D(sperp, spar, xi)
+
+    def xi_2D_from_multipoles(self, params, rmax=85, **kwargs):
+        """xi(s_perp, s_par) rebuilt from the model multipoles 0, 2, 4 (reference: ccf_model.py:896-934)."""
+        s1d = np.linspace(0.01, rmax)
+        mult = self.theory_multipoles(s1d, params, poles=[0, 2, 4], **kwargs)
+        sperp, spar, s, mu = self._sky_grid(rmax)
+        grid = np.zeros_like(s)
+        for ell in (0, 2, 4):
+            grid = grid + InterpolatedUnivariateSpline(s1d, mult[f"{ell}"])(s) * legendre(ell)(mu)
+        return GridInterpolator2D(sperp, spar, grid)
 
     def theory_xi_batch(self, s, mu, params, **kwargs):
         """xi(s, mu) for every parameter row: float64[n, len(mu), len(s)]."""
