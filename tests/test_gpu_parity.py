@@ -209,6 +209,30 @@ def test_batch_invariances(fit, golden):
     eng.set_option("nsplit", 0)
 
 
+def test_fused_likelihood_epilogue_is_bit_identical(fit):
+    """Batch mode: chi2 / lnL from the epilogue of K1 (one block per row) equal the separate K2 launch bit
+    for bit, for the general kernel (default) and the tuned one (option fuse = 2)."""
+    rng = np.random.default_rng(11)
+    n = 2048                                                   # >= 6 blocks per SM: one block per row
+    P = np.column_stack([rng.uniform(0.05, 1.5, n), rng.uniform(0.1, 0.7, n), rng.uniform(100, 500, n),
+                         rng.uniform(0.9, 1.1, n), rng.uniform(0.9, 1.1, n)])
+    P[7, 1] = np.nan                                           # a failing row goes through the same guard
+    for kw in ({}, {"rsd_model": "dispersion"}, {"rsd_model": "kaiser", "assume_isotropic": False}):
+        eng, _ = fit._fit_engine(kw)
+        out = {}
+        for fuse in (0, 2):
+            eng.set_option("fuse", fuse)
+            before = eng.launch_count()
+            out[fuse] = fit.log_likelihood_batch(P, **kw)
+            launches = eng.launch_count() - before
+            assert launches == (1 if fuse else 2)
+        eng.set_option("fuse", 1)
+        assert np.array_equal(out[0][0], out[2][0]) and np.array_equal(out[0][1], out[2][1])
+        assert out[0][0][7] == -np.inf and out[0][1][7] == np.inf
+        lnl_t, chi2_t, _ = fit.log_likelihood_batch(P, return_theory=True, **kw)
+        assert np.array_equal(lnl_t, out[0][0]) and np.array_equal(chi2_t, out[0][1])
+
+
 def test_against_oracle_fresh_points(fit, boss_blocks):
     """Seeded rows that are not in the golden files, checked against the CPU oracle."""
     from oracle.ccf_oracle import OracleFit

@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--ilp", type=int, default=4)
     ap.add_argument("--expdeg", type=int, default=5)
     ap.add_argument("--newton", type=int, default=3)
+    ap.add_argument("--fuse", type=int, default=1, help="1: chi2 / lnL in the K1 epilogue; 0: separate K2 launch")
+    ap.add_argument("--theory", type=int, default=1, help="0: do not ask for the theory vectors (chi2 / lnL only)")
     ap.add_argument("--sigma-v", type=float, default=None, help="override the sigma_v column (access-pattern probe)")
     ap.add_argument("--rsd", default="streaming", help="rsd_model (general kernel for anything but streaming)")
     ap.add_argument("--aniso", type=int, default=0, help="1: assume_isotropic False (general kernel)")
@@ -45,6 +47,7 @@ def main():
     eng.set_option("ilp", args.ilp)
     eng.set_option("exp_degree", args.expdeg)
     eng.set_option("newton", args.newton)
+    eng.set_option("fuse", args.fuse)
     n = args.batch
     dev = torch.device("cuda", 0)
     rows = params_to_rows(synthetic_batch(n))
@@ -58,11 +61,12 @@ def main():
     for _ in range(args.passes):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        eng.likelihood_ptr(d_params.data_ptr(), n, d_theory.data_ptr(), d_chi2.data_ptr(), d_lnl.data_ptr())
+        eng.likelihood_ptr(d_params.data_ptr(), n, d_theory.data_ptr() if args.theory else None, d_chi2.data_ptr(),
+                           d_lnl.data_ptr())
         b.record()
         torch.cuda.synchronize()
         times.append(a.elapsed_time(b))
-    print(f"batch={n} fast={args.fast} threads={args.threads} nsplit={args.nsplit} ilp={args.ilp} expdeg={args.expdeg} newton={args.newton} sigma_v={args.sigma_v} rsd={args.rsd} aniso={args.aniso} "
+    print(f"batch={n} fast={args.fast} threads={args.threads} nsplit={args.nsplit} ilp={args.ilp} expdeg={args.expdeg} newton={args.newton} fuse={args.fuse} theory={args.theory} sigma_v={args.sigma_v} rsd={args.rsd} aniso={args.aniso} "
           f"ms={['%.3f' % t for t in times]} evals/s={n / (min(times) * 1e-3):.4g} "
           f"chi2[0]={float(d_chi2[0]):.10f}")
     fit.close()

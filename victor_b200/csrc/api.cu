@@ -104,6 +104,7 @@ struct vb200_ctx {
     Scratch sc_params, sc_theory, sc_chi2, sc_lnl, sc_xi, sc_mult, sc_grid;
     // options
     int opt_fast = 1, opt_nsplit = 0, opt_threads = 256, opt_ilp = 4, opt_expdeg = 5, opt_newton = 3;
+    int opt_fuse = 1;             // batch mode: chi2 / lnL in the epilogue of K1 instead of a K2 launch
     bool tuned = false;           // streaming + isotropic xi + model coordinates: the tuned kernel applies
     // small-call path (MCMC steps): page-locked staging for the rows in and (chi2 | lnL) out
     double *pin = nullptr, *d_small = nullptr;
@@ -152,6 +153,13 @@ typedef void (*k1_fn)(const K1Args);
 
 // Tuned streaming kernel variants in this build.  The default is <fast, U = 4, degree-5 exp>; the
 // others exist for parity tests (libm math) and for measurement (ILP, exp degree).
+// Variants with the fused likelihood epilogue exist for the default tuned configuration only
+// (nullptr otherwise: the caller then launches K2 after the plain kernel).
+k1_fn pick_k1_fused(bool fast, bool flags, int ilp, int expdeg, int newton) {
+    if (!fast || ilp < 4 || expdeg != 5 || newton != 3) return nullptr;
+    return flags ? k_multipoles<K1Cfg<true, true, 4, 5>, true> : k_multipoles<K1Cfg<true, false, 4, 5>, true>;
+}
+
 k1_fn pick_k1(bool fast, bool flags, int ilp, int expdeg, int newton = 3) {
     if (fast && newton == 2 && ilp >= 4 && expdeg == 5)
         return flags ? k_multipoles<K1Cfg<true, true, 4, 5, 2>> : k_multipoles<K1Cfg<true, false, 4, 5, 2>>;
@@ -165,6 +173,13 @@ k1_fn pick_k1(bool fast, bool flags, int ilp, int expdeg, int newton = 3) {
     return expdeg == 5 ? k_multipoles<K1Cfg<true, false, 4, 5>> : k_multipoles<K1Cfg<true, false, 4, 6>>;
 }
 
+k1_fn pick_general_fused(int rsd_model, bool fast) {
+    if (!fast) return nullptr;
+    if (rsd_model == kRsdStreaming) return k_multipoles_general<kRsdStreaming, true, true>;
+    if (rsd_model == kRsdDispersion) return k_multipoles_general<kRsdDispersion, true, true>;
+    return k_multipoles_general<kRsdKaiser, true, true>;
+}
+
 k1_fn pick_general(int rsd_model, bool fast) {
     if (rsd_model == kRsdStreaming)
         return fast ? k_multipoles_general<kRsdStreaming, true> : k_multipoles_general<kRsdStreaming, false>;
@@ -173,24 +188,45 @@ k1_fn pick_general(int rsd_model, bool fast) {
     return fast ? k_multipoles_general<kRsdKaiser, true> : k_multipoles_general<kRsdKaiser, false>;
 }
 
-int launch_k1(vb200_ctx *c, const double *d_params, long long n, const double *d_s, int ns,
-              const double *d_mu, const double *d_sqmu, const double *d_wmu, int nmu, int L,
-              double *d_xi, double *d_mult, cudaStream_t st, bool pairwise = false) {
-    if (n <= 0) return VB200_OK;
-    int nsplit = c->opt_nsplit;
-    if (pairwise) nsplit = 0;
+// blocks per parameter row: one once the rows alone fill the GPU a few times over, else the s range
+// is split so that a single row (MCMC step) still spreads over the SMs
+int pick_nsplit(const vb200_ctx *c, long long n, int ns, bool pairwise) {
+    int nsplit = pairwise ? 0 : c->opt_nsplit;
     if (nsplit <= 0) {
-        // one block per row once the rows alone fill the GPU a few times over, else split the
-        // s range so that a single row (MCMC step) still spreads over the SMs
         const long long target = (long long)c->sm_count * 6;
         nsplit = (n >= target) ? 1 : (int)std::min<long long>(ns, (target + n - 1) / n);
     }
-    nsplit = std::max(1, std::min(nsplit, ns));
+    return std::max(1, std::min(nsplit, ns));
+}
+
+// opt_fuse: 0 never, 1 where it pays (general kernels), 2 always.  The tuned kernel is excluded by
+// default: with the epilogue compiled in, ptxas reads x_m / w_m through LDC into vector registers instead
+// of LDCU into uniform ones (+2.5 register reads per node), and the step gets 6 % slower instead of
+// 2.5 % faster (profiles/r01n_variants_fuse.log).
+k1_fn fused_variant(const vb200_ctx *c) {
+    if (!c->opt_fuse || !c->has_fit) return nullptr;
+    if (c->tuned)
+        return c->opt_fuse >= 2 ? pick_k1_fused(c->opt_fast != 0, c->has_flags, c->opt_ilp, c->opt_expdeg, c->opt_newton)
+                                : nullptr;
+    return pick_general_fused(c->md.rsd_model, c->opt_fast != 0);
+}
+
+int launch_k1(vb200_ctx *c, const double *d_params, long long n, const double *d_s, int ns,
+              const double *d_mu, const double *d_sqmu, const double *d_wmu, int nmu, int L,
+              double *d_xi, double *d_mult, cudaStream_t st, bool pairwise = false, double *d_chi2 = nullptr,
+              double *d_lnl = nullptr, bool *fused = nullptr) {
+    if (fused) *fused = false;
+    if (n <= 0) return VB200_OK;
+    int nsplit = pick_nsplit(c, n, ns, pairwise);
     int jper = (ns + nsplit - 1) / nsplit;
     if (pairwise) jper = std::min(ns, std::max(jper, 64));   // one pair per thread: keep at least two full warps
+    // the likelihood epilogue needs the whole theory vector in one block
+    k1_fn fused_fn = ((d_chi2 || d_lnl) && nsplit == 1 && !pairwise) ? fused_variant(c) : nullptr;
+    const bool want_fuse = fused_fn != nullptr;
+    const int fitd = want_fuse ? fused_fit_doubles(c->fd.p) : 0;
     auto smem_for = [&](int jp) {
-        return c->tuned ? k1_smem_bytes(c->md.ncell, jp, nmu, c->md.nbucket)
-                        : k1g_smem_bytes(c->md.ncell, jp, nmu, c->md.nbucket);
+        return c->tuned ? k1_smem_bytes(c->md.ncell, jp, nmu, c->md.nbucket, fitd)
+                        : k1g_smem_bytes(c->md.ncell, jp, nmu, c->md.nbucket, fitd);
     };
     // long s grids: split further until a block's xi(s, mu) stage leaves room for 4 blocks per SM
     // (or, failing that, at least fits)
@@ -220,6 +256,13 @@ int launch_k1(vb200_ctx *c, const double *d_params, long long n, const double *d
     a.jper = jper;
     a.nsplit = nsplit;
     a.pairwise = pairwise ? 1 : 0;
+    if (want_fuse && nsplit == 1) {   // (a long s grid may have been split further above)
+        a.fuse = 1;
+        a.f = c->fd;
+        a.chi2 = d_chi2;
+        a.lnl = d_lnl;
+        if (fused) *fused = true;
+    }
     a.xi_out = d_xi;
     a.mult_out = d_mult;
     memcpy(a.xw, c->xw, sizeof(a.xw));
@@ -227,6 +270,7 @@ int launch_k1(vb200_ctx *c, const double *d_params, long long n, const double *d
         for (int i = 0; i < c->md.nx; ++i) a.xw[kMaxNx + i] = c->xw[kMaxNx + i] / kGaussScale;
     auto fn = c->tuned ? pick_k1(c->opt_fast != 0, c->has_flags, c->opt_ilp, c->opt_expdeg, c->opt_newton)
                        : pick_general(c->md.rsd_model, c->opt_fast != 0);
+    if (a.fuse) fn = fused_fn;
     void *kargs[] = {(void *)&a};
     CK(cudaLaunchKernel((const void *)fn, dim3((unsigned)blocks), dim3(threads), kargs, smem, st));
     CK(cudaGetLastError());
@@ -427,6 +471,8 @@ int vb200_create(const vb200_model_tables *m, const vb200_fit_tables *f, int dev
     for (int v = 0; v < 32; ++v) fns.push_back((const void *)pick_k1(v & 1, v & 2, 1 << ((v >> 2) & 3), (v & 16) ? 5 : 6));
     for (int r = 0; r < 6; ++r) fns.push_back((const void *)pick_general(r >> 1, r & 1));
     for (int fl = 0; fl < 2; ++fl) fns.push_back((const void *)pick_k1(true, fl, 4, 5, 2));
+    for (int fl = 0; fl < 2; ++fl) fns.push_back((const void *)pick_k1_fused(true, fl, 4, 5, 3));
+    for (int r = 0; r < 3; ++r) fns.push_back((const void *)pick_general_fused(r, true));
     for (const void *fn : fns) {
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k1_smem_limit);
         if (e != cudaSuccess)
@@ -440,6 +486,7 @@ int vb200_set_option(vb200_ctx *c, const char *key, int64_t value) {
     if (!c || !key) return fail(VB200_EINVAL, "null argument");
     if (!strcmp(key, "fast_math")) c->opt_fast = value ? 1 : 0;
     else if (!strcmp(key, "nsplit")) c->opt_nsplit = (int)value;
+    else if (!strcmp(key, "fuse")) c->opt_fuse = (int)std::max<int64_t>(0, std::min<int64_t>(value, 2));
     else if (!strcmp(key, "newton")) {
         if (value != 2 && value != 3) return fail(VB200_EINVAL, "newton must be 2 (one Newton step) or 3 (cubic step)");
         c->opt_newton = (int)value;
@@ -562,10 +609,11 @@ int vb200_likelihood(vb200_ctx *c, const double *params, int64_t n, double *theo
         double *h_out = c->pin + (size_t)kSmallCall * VB200_NPAR, *d_out = c->d_small + (size_t)kSmallCall * VB200_NPAR;
         memcpy(c->pin, params, (size_t)n * VB200_NPAR * sizeof(double));
         CK(cudaMemcpyAsync(c->d_small, c->pin, (size_t)n * VB200_NPAR * sizeof(double), cudaMemcpyHostToDevice, st));
+        bool fused = false;
         if ((rc = launch_k1(c, c->d_small, n, c->fit_s, c->fit_ns, c->fit_mu, c->fit_sqmu, c->fit_wmu, c->fit_nmu,
-                            c->fit_L, nullptr, c->sc_theory.ptr, st)))
+                            c->fit_L, nullptr, c->sc_theory.ptr, st, false, d_out, d_out + n, &fused)))
             return rc;
-        if ((rc = launch_k2(c, c->d_small, c->sc_theory.ptr, n, d_out, d_out + n, st))) return rc;
+        if (!fused && (rc = launch_k2(c, c->d_small, c->sc_theory.ptr, n, d_out, d_out + n, st))) return rc;
         CK(cudaMemcpyAsync(h_out, d_out, (size_t)2 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         memcpy(chi2, h_out, (size_t)n * sizeof(double));
@@ -582,7 +630,14 @@ int vb200_likelihood(vb200_ctx *c, const double *params, int64_t n, double *theo
         d_params = c->sc_params.ptr;
     }
     double *d_theory = theory;
-    if (!theory || !is_device_ptr(theory)) {
+    // chi2 / lnL from the epilogue of K1: the theory vectors only leave the SM if the caller wants them
+    const bool will_fuse = (chi2 || lnlike) && pick_nsplit(c, n, c->fit_ns, false) == 1 && fused_variant(c) &&
+                           (c->tuned ? k1_smem_bytes(c->md.ncell, c->fit_ns, c->fit_nmu, c->md.nbucket, fused_fit_doubles(p))
+                                     : k1g_smem_bytes(c->md.ncell, c->fit_ns, c->fit_nmu, c->md.nbucket, fused_fit_doubles(p))) <=
+                               std::min<size_t>(c->k1_smem_limit, (size_t)56 * 1024);
+    if (!theory && will_fuse) {
+        d_theory = nullptr;
+    } else if (!theory || !is_device_ptr(theory)) {
         if ((rc = c->sc_theory.ensure((size_t)n * p))) return rc;
         d_theory = c->sc_theory.ptr;
         if (theory) host_io = true;
@@ -598,11 +653,14 @@ int vb200_likelihood(vb200_ctx *c, const double *params, int64_t n, double *theo
         if ((rc = c->sc_lnl.ensure((size_t)n))) return rc;
         d_lnl = c->sc_lnl.ptr;
     }
+    bool fused = false;
     if ((rc = launch_k1(c, d_params, n, c->fit_s, c->fit_ns, c->fit_mu, c->fit_sqmu, c->fit_wmu, c->fit_nmu,
-                        c->fit_L, nullptr, d_theory, st)))
+                        c->fit_L, nullptr, d_theory, st, false, d_chi2, d_lnl, &fused)))
         return rc;
-    if (chi2 || lnlike)
+    if ((chi2 || lnlike) && !fused) {
+        if (!d_theory) return fail(VB200_ECUDA, "internal: likelihood epilogue was expected to be fused");
         if ((rc = launch_k2(c, d_params, d_theory, n, d_chi2, d_lnl, st))) return rc;
+    }
     if (theory && d_theory != theory)
         CK(cudaMemcpyAsync(theory, d_theory, (size_t)n * p * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (chi2 && d_chi2 != chi2) CK(cudaMemcpyAsync(chi2, d_chi2, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -36,6 +36,12 @@ struct ModelDev {
     const double *v0b, *d0b;        // [ncell][4] empirical-correction parts: V0 = v0 + Av v0b (null if unused)
 };
 
+struct FitDev {
+    int p, data_beta_dependent, nbeta_ccf, cov_fixed, nbeta_cov, like_kind, use_logdet;
+    double like_a, like_nm1;
+    const double *beta_ccf, *data_tab, *beta_cov, *icov, *logdet, *lam;
+};
+
 struct K1Args {
     ModelDev m;
     const double *params;
@@ -47,12 +53,12 @@ struct K1Args {
     double *xi_out;    // [n][nmu][ns] or null
     double *mult_out;  // [n][L][ns]  or null
     double xw[2 * kMaxNx];  // x_m then Simpson weight / sqrt(2 pi): read through the constant bank
-};
-
-struct FitDev {
-    int p, data_beta_dependent, nbeta_ccf, cov_fixed, nbeta_cov, like_kind, use_logdet;
-    double like_a, like_nm1;
-    const double *beta_ccf, *data_tab, *beta_cov, *icov, *logdet, *lam;
+    // fused likelihood epilogue (nsplit == 1 only): the block that produced a row's theory vector also
+    // contracts it with the precision matrices (k2_chi2.cuh: block_chi2), so K2 is not launched and the
+    // theory vector need not leave the SM
+    int fuse;
+    FitDev f;
+    double *chi2, *lnl;   // [n] each, either may be null
 };
 
 struct K2Args {
@@ -302,7 +308,7 @@ __device__ __forceinline__ void row_scalars_to_shared(const ModelDev &m, const d
 // onto L <= 3 multipoles (one warp per s_j, lane-strided FMAs + shuffle reduction).
 // ccf_model.py:824-825, utils.py:45-56, ccf_model.py:856-858.
 __device__ __forceinline__ void write_outputs(const K1Args &a, const double *stage, long long row, int j0, int jn,
-                                              int tid, int nthr) {
+                                              int tid, int nthr, double *th = nullptr) {
     const int nmu = a.nmu;
     const int npairs = jn * nmu;
     if (a.xi_out) {
@@ -312,9 +318,9 @@ __device__ __forceinline__ void write_outputs(const K1Args &a, const double *sta
             xo[(size_t)k * a.ns + j0 + jl] = stage[pidx];
         }
     }
-    if (a.mult_out) {
+    if (a.mult_out || th) {
         const int warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
-        double *mo = a.mult_out + (size_t)row * a.L * a.ns;
+        double *mo = a.mult_out ? a.mult_out + (size_t)row * a.L * a.ns : nullptr;
         for (int jl = warp; jl < jn; jl += nwarp) {
             double s0 = 0.0, s1 = 0.0, s2 = 0.0;
             for (int k = lane; k < nmu; k += 32) {
@@ -326,10 +332,15 @@ __device__ __forceinline__ void write_outputs(const K1Args &a, const double *sta
             s0 = warp_sum(s0);
             if (a.L > 1) s1 = warp_sum(s1);
             if (a.L > 2) s2 = warp_sum(s2);
-            if (lane == 0) {
+            if (lane == 0 && mo) {
                 mo[j0 + jl] = s0;
                 if (a.L > 1) mo[a.ns + j0 + jl] = s1;
                 if (a.L > 2) mo[2 * a.ns + j0 + jl] = s2;
+            }
+            if (lane == 0 && th) {   // theory vector of this row, l-major (ccf_model.py:856-858)
+                th[j0 + jl] = s0;
+                if (a.L > 1) th[a.ns + j0 + jl] = s1;
+                if (a.L > 2) th[2 * a.ns + j0 + jl] = s2;
             }
         }
     }

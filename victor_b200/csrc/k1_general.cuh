@@ -11,6 +11,7 @@
 // variant: both must pass parity).  No instruction-level tuning beyond that.
 #pragma once
 #include "common.cuh"
+#include "k2_chi2.cuh"
 
 namespace vb200 {
 
@@ -19,8 +20,8 @@ namespace vb200 {
 constexpr int kRecG = 26;
 constexpr int kGXi = 0, kGV0 = 12, kGD0 = 16, kGSV = 20, kGOrg = 24;
 
-__host__ __device__ inline size_t k1g_smem_bytes(int ncell, int jper, int nmu, int nbucket) {
-    size_t d = (size_t)ncell * (kRecG + 1) + kExpTab + (size_t)jper * nmu + kNScal;
+__host__ __device__ inline size_t k1g_smem_bytes(int ncell, int jper, int nmu, int nbucket, int fitd = 0) {
+    size_t d = (size_t)ncell * (kRecG + 1) + kExpTab + (size_t)jper * nmu + kNScal + fitd;
     return d * sizeof(double) + (size_t)nbucket * sizeof(int);
 }
 
@@ -106,7 +107,7 @@ struct GMath {
     }
 };
 
-template <int kModel, bool kFast>
+template <int kModel, bool kFast, bool kFuse = false>
 __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constant__ K1Args a) {
     using M = GMath<kFast>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -116,7 +117,9 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
     double *etab = rec + (size_t)ncell * kRecG;
     double *stage = etab + kExpTab;
     double *scal = stage + (size_t)a.jper * a.nmu;
-    double *upper = scal + kNScal;
+    double *th = scal + kNScal;
+    const int fitd = kFuse ? fused_fit_doubles(a.f.p) : 0;
+    double *upper = th + fitd;
     int *bbase = reinterpret_cast<int *>(upper + ncell);
 
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -310,7 +313,11 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
         stage[pidx] = result;
     }
     __syncthreads();
-    write_outputs(a, stage, row, j0, jn, tid, nthr);
+    write_outputs(a, stage, row, j0, jn, tid, nthr, kFuse ? th : nullptr);
+    if (kFuse) {   // one block per row: finish with chi2 and lnL (ccf_fit.py:349-354, 441-483)
+        __syncthreads();
+        block_chi2(a.f, pr[1], th, th + ((a.f.p + 1) & ~1), row, a.chi2, a.lnl, tid, nthr);
+    }
 }
 
 }  // namespace vb200

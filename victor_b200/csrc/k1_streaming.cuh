@@ -11,6 +11,7 @@
 // is staged in shared memory and projected onto the multipoles with warp shuffles.
 #pragma once
 #include "common.cuh"
+#include "k2_chi2.cuh"
 
 namespace vb200 {
 
@@ -20,12 +21,13 @@ namespace vb200 {
 //   etab[32]        2^(j/32)
 //   stage[jper*nmu] xi(s_j, mu_k) of this block
 //   scal[kNScal]    per-row scalars
+//   th[fitd]        fused likelihood epilogue only: theory / residual vector and per-warp partial sums
 //   upper[ncell]    upper knot of each cell (slow path of the cell search only)
 //   int bbase[nbucket]  bucket -> first cell; bit 31 set when a knot lies strictly inside the bucket
 constexpr int kRec = 14;
 
-__host__ __device__ inline size_t k1_smem_bytes(int ncell, int jper, int nmu, int nbucket) {
-    size_t d = (size_t)ncell * (kRec + 1) + kExpTab + (size_t)jper * nmu + kNScal;
+__host__ __device__ inline size_t k1_smem_bytes(int ncell, int jper, int nmu, int nbucket, int fitd = 0) {
+    size_t d = (size_t)ncell * (kRec + 1) + kExpTab + (size_t)jper * nmu + kNScal + fitd;
     return d * sizeof(double) + (size_t)nbucket * sizeof(int);
 }
 
@@ -112,7 +114,9 @@ __device__ __forceinline__ double quad_nodes(const K1Args &a, const QuadCtx &q, 
 }
 
 // 64 registers per thread -> 4 resident blocks of 256 threads per SM
-template <class C>
+// kFuse: the block also turns its row's theory vector into chi2 / lnL (k2_chi2.cuh: block_chi2); a
+// separate instantiation, so the plain kernel's schedule is untouched by the epilogue
+template <class C, bool kFuse = false>
 __global__ void __launch_bounds__(256, 4) k_multipoles(const __grid_constant__ K1Args a) {
     constexpr int kU = C::kU;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -122,7 +126,8 @@ __global__ void __launch_bounds__(256, 4) k_multipoles(const __grid_constant__ K
     double *etab = rec + (size_t)ncell * kRec;
     double *stage = etab + kExpTab;
     double *scal = stage + (size_t)a.jper * a.nmu;
-    double *upper = scal + kNScal;
+    const int fitd = kFuse ? fused_fit_doubles(a.f.p) : 0;
+    double *upper = scal + kNScal + fitd;
     int *bbase = reinterpret_cast<int *>(upper + ncell);
 
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -198,7 +203,16 @@ __global__ void __launch_bounds__(256, 4) k_multipoles(const __grid_constant__ K
         stage[pidx] = acc - 1.0;  // ccf_model.py:690
     }
     __syncthreads();
-    write_outputs(a, stage, row, j0, jn, tid, nthr);
+    // (everything the epilogue needs is re-derived from the kernel arguments here, so that nothing
+    // extra stays live in registers across the quadrature loop)
+    double *th2 = reinterpret_cast<double *>(smem_raw) + (size_t)a.m.ncell * kRec + kExpTab + (size_t)a.jper * a.nmu + kNScal;
+    write_outputs(a, stage, row, j0, jn, tid, nthr, kFuse ? th2 : nullptr);
+    if (kFuse) {   // one block per row: finish with chi2 and lnL (ccf_fit.py:349-354, 441-483)
+        __syncthreads();
+        const long long r2 = blockIdx.x;   // nsplit == 1
+        block_chi2(a.f, a.params[r2 * kNPar + 1], th2, th2 + ((a.f.p + 1) & ~1), r2, a.chi2, a.lnl, threadIdx.x,
+                   blockDim.x);
+    }
 }
 
 }  // namespace vb200

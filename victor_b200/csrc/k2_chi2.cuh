@@ -1,8 +1,14 @@
-// K2: chi-square and log-likelihood, one warp per parameter row.  Replaces
+// K2: chi-square and log-likelihood.  Replaces
 //   CCFFit.multipole_datavector / get_interpolated_{covariance,precision}
 //                                         victor/ccf_fit.py:166-260, 306-323
 //   CCFFit.chi_squared                    victor/ccf_fit.py:349-354
 //   CCFFit.log_likelihood                 victor/ccf_fit.py:441-483
+// Two forms of the same arithmetic:
+//   k_chi2      one warp per parameter row, theory vectors read from global memory (after a K1 launch
+//               that split rows over several blocks, or when the caller asked for the theory vectors);
+//   block_chi2  epilogue of the K1 kernels when one block owns a whole row (batch mode): the theory
+//               vector is still in shared memory, the block's warps split the rows of the precision
+//               matrices, and neither a second launch nor the theory round trip through HBM is needed.
 #pragma once
 #include "common.cuh"
 
@@ -11,13 +17,16 @@ namespace vb200 {
 constexpr int kK2Warps = 8;
 constexpr int kK2MaxChunks = 8;  // p <= 256
 
-__device__ __forceinline__ double quad_form(const double *M, const double *res, int p, int lane) {
-    // y_j = sum_i M[i][j] res_i with lanes over columns j (coalesced rows; M symmetric in exact
-    // arithmetic, and res^T M res does not depend on which index is contracted first)
+// res^T M res as kK2Warps partial sums, partial `part` taking the matrix rows i = part, part + kK2Warps, ...:
+//   sum_i sum_j M[i][j] res_i res_j  with lanes over columns j (coalesced rows; M symmetric in exact
+// arithmetic, and res^T M res does not depend on which index is contracted first).  The partition is
+// the same whether one warp walks through all the partials (k_chi2) or the warps of a block take one
+// each (block_chi2), so both give bit-identical chi-squares.
+__device__ __forceinline__ double quad_partial(const double *M, const double *res, int p, int lane, int part) {
     double y[kK2MaxChunks];
 #pragma unroll
     for (int c = 0; c < kK2MaxChunks; ++c) y[c] = 0.0;
-    for (int i = 0; i < p; ++i) {
+    for (int i = part; i < p; i += kK2Warps) {
         const double ri = res[i];
         const double *rowp = M + (size_t)i * p;
 #pragma unroll
@@ -35,6 +44,93 @@ __device__ __forceinline__ double quad_form(const double *M, const double *res, 
     return warp_sum(q);
 }
 
+__device__ __forceinline__ double quad_form(const double *M, const double *res, int p, int lane) {
+    double q = 0.0;
+    for (int part = 0; part < kK2Warps; ++part) q += quad_partial(M, res, p, lane, part);
+    return q;
+}
+
+// data vector at beta: PCHIP power table (ccf_fit.py:193, 322-323, 350)
+struct DataAt {
+    const double *dt;
+    double td;
+    int p;
+    __device__ __forceinline__ DataAt(const FitDev &f, double beta) : p(f.p) {
+        int kd = 0;
+        td = 0.0;
+        if (f.data_beta_dependent) {
+            kd = beta_interval(f.beta_ccf, f.nbeta_ccf, beta);
+            td = beta - f.beta_ccf[kd];
+        }
+        dt = f.data_tab + (size_t)kd * 4 * p;
+    }
+    __device__ __forceinline__ double operator()(int j) const {
+        return fma(fma(fma(dt[3 * p + j], td, dt[2 * p + j]), td, dt[p + j]), td, dt[j]);
+    }
+};
+
+// matrix bracket with the reference's conventions (ccf_fit.py:218-227, 250-259): lower neighbour and
+// the LAST grid index; end matrices outside the grid; the grid matrix itself on a grid value.
+// A NaN beta comes back as w = NaN with lo == hi.
+__device__ __forceinline__ void cov_bracket(const FitDev &f, double beta, int &lo, int &hi, double &w) {
+    lo = hi = 0;
+    w = 0.0;
+    if (f.cov_fixed) return;
+    const int nb = f.nbeta_cov;
+    const double *g = f.beta_cov;
+    if (beta < g[0]) return;
+    if (beta > g[nb - 1]) {
+        lo = hi = nb - 1;
+        return;
+    }
+    int below = 0, exact = -1;
+    for (int i = 0; i < nb; ++i) {
+        below += (g[i] < beta) ? 1 : 0;
+        if (g[i] == beta) exact = i;
+    }
+    if (exact >= 0) {
+        lo = hi = exact;
+    } else if (below == 0) {  // beta is NaN: every comparison false
+        w = beta;
+    } else {
+        lo = below - 1;
+        hi = nb - 1;  // sic: last index with grid >= beta
+        w = (beta - g[lo]) / (g[hi] - g[lo]);
+    }
+}
+
+__device__ __forceinline__ double blend_chi2(double qlo, double qhi, int lo, int hi, double w) {
+    if (hi != lo) return (1.0 - w) * qlo + w * qhi;
+    return (w != w) ? w : qlo;
+}
+
+// log det of the blended covariance from the generalised eigenvalues (tables.py: lam), one warp
+__device__ __forceinline__ double norm_term(const FitDev &f, int lo, int hi, double w, int lane) {
+    if (!f.use_logdet) return 0.0;
+    double ld = 0.0;
+    if (hi != lo) {
+        const double *lam = f.lam + (size_t)lo * f.p;
+        for (int j = lane; j < f.p; j += 32) ld += log1p(w * (lam[j] - 1.0));
+        ld = warp_sum(ld);
+    }
+    return -0.5 * (f.logdet[lo] + ld);
+}
+
+__device__ __forceinline__ void store_likelihood(const FitDev &f, double chi2, double norm, long long row,
+                                                 double *chi2_out, double *lnl_out) {
+    double lnl;
+    if (f.like_kind == 1)
+        lnl = -f.like_a * log(1.0 + chi2 / f.like_nm1) / 2.0 + norm;  // ccf_fit.py:457, 469
+    else
+        lnl = -0.5 * chi2 * f.like_a + norm;                          // ccf_fit.py:462, 471
+    if (lnl != lnl) {  // ccf_fit.py:477-481
+        lnl = -INFINITY;
+        chi2 = INFINITY;
+    }
+    if (chi2_out) chi2_out[row] = chi2;
+    if (lnl_out) lnl_out[row] = lnl;
+}
+
 __global__ void __launch_bounds__(kK2Warps * 32) k_chi2(const __grid_constant__ K2Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const FitDev &f = a.f;
@@ -46,79 +142,54 @@ __global__ void __launch_bounds__(kK2Warps * 32) k_chi2(const __grid_constant__ 
     const double beta = a.params[row * kNPar + 1];
     const double *th = a.theory + (size_t)row * p;
 
-    // residual against the PCHIP-in-beta data vector (ccf_fit.py:193, 322-323, 350)
-    int kd = 0;
-    double td = 0.0;
-    if (f.data_beta_dependent) {
-        kd = beta_interval(f.beta_ccf, f.nbeta_ccf, beta);
-        td = beta - f.beta_ccf[kd];
-    }
-    const double *dt = f.data_tab + (size_t)kd * 4 * p;
-    for (int j = lane; j < p; j += 32) {
-        const double d = fma(fma(fma(dt[3 * p + j], td, dt[2 * p + j]), td, dt[p + j]), td, dt[j]);
-        res[j] = th[j] - d;
-    }
+    const DataAt data(f, beta);
+    for (int j = lane; j < p; j += 32) res[j] = th[j] - data(j);
     __syncwarp();
 
-    // matrix bracket with the reference's conventions (ccf_fit.py:218-227, 250-259)
-    int lo = 0, hi = 0;
-    double w = 0.0;
-    if (!f.cov_fixed) {
-        const int nb = f.nbeta_cov;
-        const double *g = f.beta_cov;
-        if (beta < g[0]) {
-            lo = hi = 0;
-        } else if (beta > g[nb - 1]) {
-            lo = hi = nb - 1;
-        } else {
-            int below = 0, exact = -1;
-            for (int i = 0; i < nb; ++i) {
-                below += (g[i] < beta) ? 1 : 0;
-                if (g[i] == beta) exact = i;
-            }
-            if (exact >= 0) {
-                lo = hi = exact;
-            } else if (below == 0) {  // beta is NaN: every comparison false
-                lo = hi = 0;
-                w = beta;
-            } else {
-                lo = below - 1;
-                hi = nb - 1;  // sic: last index with grid >= beta
-                w = (beta - g[lo]) / (g[hi] - g[lo]);
-            }
-        }
-    }
+    int lo, hi;
+    double w;
+    cov_bracket(f, beta, lo, hi, w);
     const double qlo = quad_form(f.icov + (size_t)lo * p * p, res, p, lane);
-    double chi2 = qlo;
-    if (hi != lo) {
-        const double qhi = quad_form(f.icov + (size_t)hi * p * p, res, p, lane);
-        chi2 = (1.0 - w) * qlo + w * qhi;
-    } else if (w != w) {
-        chi2 = w;
-    }
+    const double qhi = (hi != lo) ? quad_form(f.icov + (size_t)hi * p * p, res, p, lane) : 0.0;
+    const double chi2 = blend_chi2(qlo, qhi, lo, hi, w);
+    const double norm = norm_term(f, lo, hi, w, lane);
+    if (lane == 0) store_likelihood(f, chi2, norm, row, a.chi2, a.lnl);
+}
 
-    double norm = 0.0;
-    if (f.use_logdet) {
-        double ld = 0.0;
-        if (hi != lo) {
-            const double *lam = f.lam + (size_t)lo * p;
-            for (int j = lane; j < p; j += 32) ld += log1p(w * (lam[j] - 1.0));
-            ld = warp_sum(ld);
+// doubles of shared memory the fused epilogue needs: the theory / residual vector and the per-warp
+// partial quadratic forms
+__host__ __device__ inline int fused_fit_doubles(int p) { return ((p + 1) & ~1) + 2 * kK2Warps; }
+
+// Fused epilogue: `th` [p] holds this row's theory vector in shared memory (written by
+// write_outputs, visible after a __syncthreads); `red` has room for 2 * kK2Warps doubles.
+__device__ __forceinline__ void block_chi2(const FitDev &f, double beta, double *th, double *red, long long row,
+                                           double *chi2_out, double *lnl_out, int tid, int nthr) {
+    const int p = f.p;
+    const int warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
+    const DataAt data(f, beta);
+    for (int j = tid; j < p; j += nthr) th[j] -= data(j);
+    __syncthreads();
+    int lo, hi;
+    double w;
+    cov_bracket(f, beta, lo, hi, w);
+    for (int part = warp; part < kK2Warps; part += nwarp) {   // (blocks of fewer than 8 warps take several)
+        const double qlo = quad_partial(f.icov + (size_t)lo * p * p, th, p, lane, part);
+        const double qhi = (hi != lo) ? quad_partial(f.icov + (size_t)hi * p * p, th, p, lane, part) : 0.0;
+        if (lane == 0) {
+            red[part] = qlo;
+            red[kK2Warps + part] = qhi;
         }
-        norm = -0.5 * (f.logdet[lo] + ld);
     }
-    if (lane == 0) {
-        double lnl;
-        if (f.like_kind == 1)
-            lnl = -f.like_a * log(1.0 + chi2 / f.like_nm1) / 2.0 + norm;  // ccf_fit.py:457, 469
-        else
-            lnl = -0.5 * chi2 * f.like_a + norm;                          // ccf_fit.py:462, 471
-        if (lnl != lnl) {  // ccf_fit.py:477-481
-            lnl = -INFINITY;
-            chi2 = INFINITY;
+    __syncthreads();
+    if (warp == 0) {
+        double a = 0.0, b = 0.0;
+        for (int i = 0; i < kK2Warps; ++i) {   // same order as quad_form
+            a += red[i];
+            b += red[kK2Warps + i];
         }
-        if (a.chi2) a.chi2[row] = chi2;
-        if (a.lnl) a.lnl[row] = lnl;
+        const double chi2 = blend_chi2(a, b, lo, hi, w);
+        const double norm = norm_term(f, lo, hi, w, lane);
+        if (lane == 0) store_likelihood(f, chi2, norm, row, chi2_out, lnl_out);
     }
 }
 }  // namespace vb200
