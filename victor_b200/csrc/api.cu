@@ -199,15 +199,18 @@ int pick_nsplit(const vb200_ctx *c, long long n, int ns, bool pairwise) {
     return std::max(1, std::min(nsplit, ns));
 }
 
-// opt_fuse: 0 never, 1 where it pays (general kernels), 2 always.  The tuned kernel is excluded by
-// default: with the epilogue compiled in, ptxas reads x_m / w_m through LDC into vector registers instead
-// of LDCU into uniform ones (+2.5 register reads per node), and the step gets 6 % slower instead of
-// 2.5 % faster (profiles/r01n_variants_fuse.log).
+// opt_fuse: 0 never, 1 where it pays, 2 always.  Measured (profiles/r01n_variants_fuse.log):
+//   general kernel, velocity-integral models: +0.5 % and no theory scratch -> fused by default;
+//   general kernel, kaiser / euclid_special (3000 points per row, short blocks): the epilogue's L2 reads sit
+//     exposed at the end of every block, 4.54 ms instead of 4.00 ms per 65 536 rows -> not fused;
+//   tuned kernel: with the epilogue compiled in, ptxas reads x_m / w_m through LDC into vector registers
+//     instead of LDCU into uniform ones (+2.5 register reads per node), 31.6 ms instead of 29.7 -> not fused.
 k1_fn fused_variant(const vb200_ctx *c) {
     if (!c->opt_fuse || !c->has_fit) return nullptr;
+    const bool always = c->opt_fuse >= 2;
     if (c->tuned)
-        return c->opt_fuse >= 2 ? pick_k1_fused(c->opt_fast != 0, c->has_flags, c->opt_ilp, c->opt_expdeg, c->opt_newton)
-                                : nullptr;
+        return always ? pick_k1_fused(c->opt_fast != 0, c->has_flags, c->opt_ilp, c->opt_expdeg, c->opt_newton) : nullptr;
+    if (c->md.rsd_model >= kRsdKaiser && !always) return nullptr;
     return pick_general_fused(c->md.rsd_model, c->opt_fast != 0);
 }
 
@@ -256,6 +259,7 @@ int launch_k1(vb200_ctx *c, const double *d_params, long long n, const double *d
     a.jper = jper;
     a.nsplit = nsplit;
     a.pairwise = pairwise ? 1 : 0;
+    a.has_flags = c->has_flags ? 1 : 0;
     if (want_fuse && nsplit == 1) {   // (a long s grid may have been split further above)
         a.fuse = 1;
         a.f = c->fd;

@@ -49,6 +49,7 @@ struct K1Args {
     const double *s, *mu, *sqmu, *wmu;  // [ns], [nmu], [nmu] sqrt(1-mu^2), [L][nmu]
     int ns, nmu, L;
     int jper, nsplit;
+    int has_flags;     // some bucket entry carries the interior-knot flag (general kernel: comparison scan needed)
     int pairwise;      // 1: nmu == 1 and mu / sqmu have ns entries -- xi at the pairs (s_j, mu_j) (theory_xi_2D)
     double *xi_out;    // [n][nmu][ns] or null
     double *mult_out;  // [n][L][ns]  or null

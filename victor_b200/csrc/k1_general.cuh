@@ -26,38 +26,48 @@ __host__ __device__ inline size_t k1g_smem_bytes(int ncell, int jper, int nmu, i
 }
 
 struct GenCtx {
-    const double *rec, *upper;
-    const int *bbase;
-    int nbucket, maxscan, n_ell;
+    unsigned rec_s, bb_s;   // 32-bit shared-window addresses of the cell records and of the bucket table
+    unsigned nbm1;
+    const double *upper;
+    int maxscan, has_flags, n_ell;
     int ell1, ell2;
     double inv_h;
     const double *sv2d, *sv_yb;
     int sv_ny;
 };
 
-// cell of coordinate u and the local coordinate inside it; below the first knot t = 0 (every
-// spline is its boundary value there, FITPACK ext=3)
-__device__ __forceinline__ const double *locate(const GenCtx &g, double u, double &t) {
-    const double bf = floor(u * g.inv_h);
-    int b = 0;
-    if (bf >= 0.0) b = (bf < (double)(g.nbucket - 1)) ? (int)bf : g.nbucket - 1;   // NaN -> bucket 0
-    int cell = g.bbase[b];
-    if (cell < 0) {
-        cell &= ~kBucketFlag;
-        for (int sc = 0; sc < g.maxscan; ++sc) cell += (u >= g.upper[cell]) ? 1 : 0;
-    }
-    const double *r = g.rec + cell * kRecG;
-    const double tt = u - r[kGOrg];
-    t = (tt < 0.0) ? 0.0 : tt;      // NaN stays NaN
-    return r;
+// cubic c0 + c1 t + c2 t^2 + c3 t^3 whose coefficients sit at 32-bit shared address `addr` (two LDS.128)
+__device__ __forceinline__ double cubic_s(unsigned addr, double t) {
+    const double2 c01 = lds_f64x2(addr), c23 = lds_f64x2(addr + 16);
+    return fma(fma(fma(c23.y, t, c23.x), t, c01.y), t, c01.x);
 }
 
-// normalised dispersion template at (cell record r, local coordinate t, mu_r): the 1-D cubic, or
+// cell of coordinate u (shared address of its record) and the local coordinate inside it; below the
+// first knot t = 0 (every spline is its boundary value there, FITPACK ext=3).  Same branch-free search as
+// the tuned kernel: bucket = floor(u inv_h) through a round-down FMA onto 1.5 * 2^52 (u >= 0; NaN -> 0),
+// one LDS.32 for the cell, a comparison scan only when some bucket holds a knot in its interior.
+__device__ __forceinline__ unsigned locate(const GenCtx &g, double u, double &t) {
+    const unsigned b = min((unsigned)__double2loint(__fma_rd(u, g.inv_h, 6755399441055744.0)), g.nbm1);
+    int cell = lds_s32(g.bb_s + (b << 2));
+    if (g.has_flags) {
+        if (cell < 0) {
+            cell &= ~kBucketFlag;
+            for (int sc = 0; sc < g.maxscan; ++sc) cell += (u >= g.upper[cell]) ? 1 : 0;
+        }
+    }
+    const unsigned ra = g.rec_s + cell * (kRecG * 8);
+    const double tt = u - lds_f64(ra + kGOrg * 8);
+    // t = max(t, 0) on the high word: a negative t becomes a denormal-sized positive number, 0 for the cubics
+    t = __hiloint2double(max(__double2hiint(tt), 0), __double2loint(tt));
+    return ra;
+}
+
+// normalised dispersion template at (cell record ra, local coordinate t, mu_r): the 1-D cubic, or
 // for a sigma_v(r, mu) template the bicubic patch with mu clamped to the template's range
 // (RectBivariateSpline.ev -> FITPACK bispeu clamps both arguments)
-__device__ __forceinline__ double sv_at(const GenCtx &g, const double *r, double t, double mur) {
-    if (g.sv_ny == 0) return horner3(r + kGSV, t);
-    const int cell = (int)((r - g.rec) / kRecG);
+__device__ __forceinline__ double sv_at(const GenCtx &g, unsigned ra, double t, double mur) {
+    if (g.sv_ny == 0) return cubic_s(ra + kGSV * 8, t);
+    const int cell = (int)((ra - g.rec_s) / (kRecG * 8));
     const double *yb = g.sv_yb;
     double mc = mur;
     if (mc < yb[0]) mc = yb[0];
@@ -81,10 +91,10 @@ __device__ __forceinline__ double legendre_even(int ell, double x) {
 }
 
 // real-space xi at (u, mu_r): sum_l xi_l(u) L_l(mu_r)                 ccf_model.py:681-687
-__device__ __forceinline__ double xi_real(const GenCtx &g, const double *r, double t, double mur) {
-    double xi = horner3(r + kGXi, t);
-    if (g.n_ell > 1) xi += horner3(r + kGXi + 4, t) * legendre_even(g.ell1, mur);
-    if (g.n_ell > 2) xi += horner3(r + kGXi + 8, t) * legendre_even(g.ell2, mur);
+__device__ __forceinline__ double xi_real(const GenCtx &g, unsigned ra, double t, double mur) {
+    double xi = cubic_s(ra + kGXi * 8, t);
+    if (g.n_ell > 1) xi += cubic_s(ra + (kGXi + 4) * 8, t) * legendre_even(g.ell1, mur);
+    if (g.n_ell > 2) xi += cubic_s(ra + (kGXi + 8) * 8, t) * legendre_even(g.ell2, mur);
     return xi;
 }
 
@@ -183,11 +193,12 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
     const double f = scal[0], sperp_f = scal[1], spar_f = scal[2], kappa = scal[3], B = scal[4], G = scal[5];
     const double apar = scal[6];
     GenCtx g;
-    g.rec = rec;
+    g.rec_s = (unsigned)__cvta_generic_to_shared(rec);
+    g.bb_s = (unsigned)__cvta_generic_to_shared(bbase);
+    g.nbm1 = (unsigned)(m.nbucket - 1);
     g.upper = upper;
-    g.bbase = bbase;
-    g.nbucket = m.nbucket;
     g.maxscan = m.maxscan;
+    g.has_flags = a.has_flags;
     g.n_ell = m.n_ell;
     g.ell1 = m.ells[1];
     g.ell2 = m.ells[2];
@@ -210,13 +221,13 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
         double result;
 
         // real-space xi for a point with (u-unit) line-of-sight separation rp
-        auto xi_at = [&](double rp, double u, double mur, const double *rcell, double t) {
+        auto xi_at = [&](double rp, double u, double mur, unsigned rcell, double t) {
             if (!m.from_data) return xi_real(g, rcell, t, mur);
             const double rpd = rp * f_over_apar;                       // r_par / apar      (:675)
             double rd, ird;
             M::root(rpd * rpd + rt_data * rt_data, rd, ird);           // (:677)
             double td;
-            const double *rc = locate(g, rd, td);
+            const unsigned rc = locate(g, rd, td);
             return xi_real(g, rc, td, kFast ? rpd * ird : rpd / rd);   // (:678-687)
         };
 
@@ -229,10 +240,10 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
                 M::root(Sperp2 + rp * rp, u, iu);                      // :651
                 const double mur = kFast ? rp * iu : rp / u;           // :652
                 double t;
-                const double *rc = locate(g, u, t);
+                const unsigned rc = locate(g, u, t);
                 const double sv = sv_at(g, rc, t, mur);                // :654-655
                 const double isv = kFast ? rcp_cubic(sv) : 1.0 / sv;
-                const double d = xm - B * horner3(rc + kGV0, t) * mur;
+                const double d = xm - B * cubic_s(rc + kGV0 * 8, t) * mur;
                 const double z = kFast ? d * isv : d / sv;             // :656
                 const double xi = xi_at(rp, u, mur, rc, t);
                 const double pdf = M::gauss(z * z, etab_s);
@@ -244,9 +255,9 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
             double Strue, iS;
             M::root(Sperp2 + Spar * Spar, Strue, iS);
             double t0;
-            const double *r0 = locate(g, Strue, t0);
-            const double first = kFast ? fma(G * horner3(r0 + kGV0, t0), iS, 1.0)
-                                       : 1.0 + G * horner3(r0 + kGV0, t0) / Strue;
+            const unsigned r0 = locate(g, Strue, t0);
+            const double first = kFast ? fma(G * cubic_s(r0 + kGV0 * 8, t0), iS, 1.0)
+                                       : 1.0 + G * cubic_s(r0 + kGV0 * 8, t0) / Strue;
             const double ifirst = kFast ? rcp_cubic(first) : 0.0;
             double acc = 0.0;
             for (int mi = 0; mi < nx; ++mi) {
@@ -254,19 +265,19 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
                 const double num = Spar - xm * kappa;
                 double rp = kFast ? num * ifirst : num / first;
                 double u, iu, t;
-                const double *rc;
+                unsigned rc;
                 for (int it = 0; it < m.niter; ++it) {
                     M::root(Sperp2 + rp * rp, u, iu);
                     rc = locate(g, u, t);
-                    rp = kFast ? num * rcp_cubic(fma(G * horner3(rc + kGV0, t), iu, 1.0))
-                               : num / (1.0 + G * horner3(rc + kGV0, t) / u);
+                    rp = kFast ? num * rcp_cubic(fma(G * cubic_s(rc + kGV0 * 8, t), iu, 1.0))
+                               : num / (1.0 + G * cubic_s(rc + kGV0 * 8, t) / u);
                 }
                 M::root(Sperp2 + rp * rp, u, iu);
                 const double mur = kFast ? rp * iu : rp / u;
                 rc = locate(g, u, t);
                 const double sv = sv_at(g, rc, t, mur);                // :667-668
-                const double v0u = kFast ? horner3(rc + kGV0, t) * iu : horner3(rc + kGV0, t) / u;
-                const double jd = 1.0 + G * v0u + G * mur * mur * (horner3(rc + kGD0, t) - v0u);
+                const double v0u = kFast ? cubic_s(rc + kGV0 * 8, t) * iu : cubic_s(rc + kGV0 * 8, t) / u;
+                const double jd = 1.0 + G * v0u + G * mur * mur * (cubic_s(rc + kGD0 * 8, t) - v0u);
                 const double xi = xi_at(rp, u, mur, rc, t);
                 if (kFast) {
                     const double isv = rcp_cubic(sv);
@@ -283,27 +294,27 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
             const double MG = Mk * G;
             double rp = Spar;
             double u, t;
-            const double *rc;
+            unsigned rc;
             double iu;
             if (m.kaiser_shift) {
                 double Strue;
                 M::root(Sperp2 + Spar * Spar, Strue, iu);
                 rc = locate(g, Strue, t);
-                rp = kFast ? Spar * rcp_cubic(fma(MG * horner3(rc + kGV0, t), iu, 1.0))
-                           : Spar / (1.0 + MG * horner3(rc + kGV0, t) / Strue);
+                rp = kFast ? Spar * rcp_cubic(fma(MG * cubic_s(rc + kGV0 * 8, t), iu, 1.0))
+                           : Spar / (1.0 + MG * cubic_s(rc + kGV0 * 8, t) / Strue);
                 for (int it = 0; it < m.niter; ++it) {
                     M::root(Sperp2 + rp * rp, u, iu);
                     rc = locate(g, u, t);
-                    rp = kFast ? Spar * rcp_cubic(fma(MG * horner3(rc + kGV0, t), iu, 1.0))
-                               : Spar / (1.0 + MG * horner3(rc + kGV0, t) / u);
+                    rp = kFast ? Spar * rcp_cubic(fma(MG * cubic_s(rc + kGV0 * 8, t), iu, 1.0))
+                               : Spar / (1.0 + MG * cubic_s(rc + kGV0 * 8, t) / u);
                 }
             }
             M::root(Sperp2 + rp * rp, u, iu);
             const double mur = kFast ? rp * iu : rp / u;
             rc = locate(g, u, t);
-            const double v0u = kFast ? horner3(rc + kGV0, t) * iu : horner3(rc + kGV0, t) / u;
+            const double v0u = kFast ? cubic_s(rc + kGV0 * 8, t) * iu : cubic_s(rc + kGV0 * 8, t) / u;
             const double ca = (m.rsd_model == kRsdEuclid) ? 3.0 : 1.0, cb = (m.rsd_model == kRsdEuclid) ? 2.0 : 1.0;
-            const double J = ca * MG * v0u + cb * MG * Qk * mur * mur * (horner3(rc + kGD0, t) - v0u);
+            const double J = ca * MG * v0u + cb * MG * Qk * mur * mur * (cubic_s(rc + kGD0 * 8, t) - v0u);
             const double xi = xi_at(rp, u, mur, rc, t);
             if (m.rsd_model == kRsdEuclid || m.kaiser_approx)
                 result = Mk * xi - J;
