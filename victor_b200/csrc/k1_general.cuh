@@ -18,6 +18,11 @@ namespace vb200 {
 // per-cell record of the general kernel:
 //   xi_l cubics (3 x 4, unused ones zero) | V0 (4) | D0 (4) | SV (4) | origin | pad
 constexpr int kRecG = 26;
+constexpr int kGU = 2;   // velocity nodes in flight per thread (general kernel)
+template <int U>
+struct NodeCount {
+    static constexpr int value = U;
+};
 constexpr int kGXi = 0, kGV0 = 12, kGD0 = 16, kGSV = 20, kGOrg = 24;
 
 __host__ __device__ inline size_t k1g_smem_bytes(int ncell, int jper, int nmu, int nbucket, int fitd = 0) {
@@ -231,24 +236,96 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
             return xi_real(g, rc, td, kFast ? rpd * ird : rpd / rd);   // (:678-687)
         };
 
+        // U consecutive velocity nodes of this (s_j, mu_k) pair, stage by stage, so that U independent
+        // dependency chains are in flight per warp (the fixed-point iteration of the dispersion model is one
+        // long chain per node: rsqrt -> cell -> cubic -> reciprocal, six times over)
+        auto stream_nodes = [&](auto Uc, int mi, double acc) {
+            constexpr int U = decltype(Uc)::value;
+            double xm[U], rp[U], u[U], iu[U], mur[U], t[U], isv[U], sv[U], z[U], xi[U];
+            unsigned rc[U];
+#pragma unroll
+            for (int i = 0; i < U; ++i) {
+                xm[i] = a.xw[mi + i];
+                rp[i] = Spar - xm[i] * kappa;                          // :648
+                M::root(Sperp2 + rp[i] * rp[i], u[i], iu[i]);         // :651
+                mur[i] = kFast ? rp[i] * iu[i] : rp[i] / u[i];         // :652
+            }
+#pragma unroll
+            for (int i = 0; i < U; ++i) rc[i] = locate(g, u[i], t[i]);
+#pragma unroll
+            for (int i = 0; i < U; ++i) {
+                sv[i] = sv_at(g, rc[i], t[i], mur[i]);                 // :654-655
+                isv[i] = kFast ? rcp_cubic(sv[i]) : 1.0 / sv[i];
+            }
+#pragma unroll
+            for (int i = 0; i < U; ++i) {
+                const double d = xm[i] - B * cubic_s(rc[i] + kGV0 * 8, t[i]) * mur[i];
+                z[i] = kFast ? d * isv[i] : d / sv[i];                 // :656
+            }
+#pragma unroll
+            for (int i = 0; i < U; ++i) xi[i] = xi_at(rp[i], u[i], mur[i], rc[i], t[i]);
+#pragma unroll
+            for (int i = 0; i < U; ++i) {
+                const double wm = a.xw[kMaxNx + mi + i];
+                const double pdf = M::gauss(z[i] * z[i], etab_s);
+                acc += kFast ? wm * (1.0 + xi[i]) * pdf * isv[i] : wm * (1.0 + xi[i]) * pdf / sv[i];   // :690
+            }
+            return acc;
+        };
+
+        auto disp_nodes = [&](auto Uc, int mi, double acc, double first, double ifirst) {
+            constexpr int U = decltype(Uc)::value;
+            double xm[U], num[U], rp[U], u[U], iu[U], t[U];
+            unsigned rc[U];
+#pragma unroll
+            for (int i = 0; i < U; ++i) {
+                xm[i] = a.xw[mi + i];
+                num[i] = Spar - xm[i] * kappa;
+                rp[i] = kFast ? num[i] * ifirst : num[i] / first;
+            }
+            for (int it = 0; it < m.niter; ++it) {
+#pragma unroll
+                for (int i = 0; i < U; ++i) M::root(Sperp2 + rp[i] * rp[i], u[i], iu[i]);
+#pragma unroll
+                for (int i = 0; i < U; ++i) rc[i] = locate(g, u[i], t[i]);
+#pragma unroll
+                for (int i = 0; i < U; ++i)
+                    rp[i] = kFast ? num[i] * rcp_cubic(fma(G * cubic_s(rc[i] + kGV0 * 8, t[i]), iu[i], 1.0))
+                                  : num[i] / (1.0 + G * cubic_s(rc[i] + kGV0 * 8, t[i]) / u[i]);
+            }
+            double mur[U];
+#pragma unroll
+            for (int i = 0; i < U; ++i) {
+                M::root(Sperp2 + rp[i] * rp[i], u[i], iu[i]);
+                mur[i] = kFast ? rp[i] * iu[i] : rp[i] / u[i];
+            }
+#pragma unroll
+            for (int i = 0; i < U; ++i) rc[i] = locate(g, u[i], t[i]);
+#pragma unroll
+            for (int i = 0; i < U; ++i) {
+                const double sv = sv_at(g, rc[i], t[i], mur[i]);       // :667-668
+                const double v0 = cubic_s(rc[i] + kGV0 * 8, t[i]);
+                const double v0u = kFast ? v0 * iu[i] : v0 / u[i];
+                const double jd = 1.0 + G * v0u + G * mur[i] * mur[i] * (cubic_s(rc[i] + kGD0 * 8, t[i]) - v0u);
+                const double xi = xi_at(rp[i], u[i], mur[i], rc[i], t[i]);
+                const double wm = a.xw[kMaxNx + mi + i];
+                if (kFast) {
+                    const double isv = rcp_cubic(sv);
+                    const double z = xm[i] * isv;
+                    acc += wm * (1.0 + xi) * rcp_cubic(jd) * M::gauss(z * z, etab_s) * isv;
+                } else {
+                    const double z = xm[i] / sv;
+                    acc += wm * (1.0 + xi) * (1.0 / jd) * exp(-0.5 * z * z) / sv;
+                }
+            }
+            return acc;
+        };
+
         if (kModel == kRsdStreaming) {
             double acc = 0.0;
-            for (int mi = 0; mi < nx; ++mi) {
-                const double xm = a.xw[mi], wm = a.xw[kMaxNx + mi];
-                const double rp = Spar - xm * kappa;                   // :648
-                double u, iu;
-                M::root(Sperp2 + rp * rp, u, iu);                      // :651
-                const double mur = kFast ? rp * iu : rp / u;           // :652
-                double t;
-                const unsigned rc = locate(g, u, t);
-                const double sv = sv_at(g, rc, t, mur);                // :654-655
-                const double isv = kFast ? rcp_cubic(sv) : 1.0 / sv;
-                const double d = xm - B * cubic_s(rc + kGV0 * 8, t) * mur;
-                const double z = kFast ? d * isv : d / sv;             // :656
-                const double xi = xi_at(rp, u, mur, rc, t);
-                const double pdf = M::gauss(z * z, etab_s);
-                acc += kFast ? wm * (1.0 + xi) * pdf * isv : wm * (1.0 + xi) * pdf / sv;   // :690
-            }
+            int mi = 0;
+            for (; mi + kGU <= nx; mi += kGU) acc = stream_nodes(NodeCount<kGU>{}, mi, acc);
+            for (; mi < nx; ++mi) acc = stream_nodes(NodeCount<1>{}, mi, acc);
             result = acc - 1.0;
         } else if (kModel == kRsdDispersion) {
             // ccf_model.py:659-671
@@ -260,34 +337,9 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
                                        : 1.0 + G * cubic_s(r0 + kGV0 * 8, t0) / Strue;
             const double ifirst = kFast ? rcp_cubic(first) : 0.0;
             double acc = 0.0;
-            for (int mi = 0; mi < nx; ++mi) {
-                const double xm = a.xw[mi], wm = a.xw[kMaxNx + mi];
-                const double num = Spar - xm * kappa;
-                double rp = kFast ? num * ifirst : num / first;
-                double u, iu, t;
-                unsigned rc;
-                for (int it = 0; it < m.niter; ++it) {
-                    M::root(Sperp2 + rp * rp, u, iu);
-                    rc = locate(g, u, t);
-                    rp = kFast ? num * rcp_cubic(fma(G * cubic_s(rc + kGV0 * 8, t), iu, 1.0))
-                               : num / (1.0 + G * cubic_s(rc + kGV0 * 8, t) / u);
-                }
-                M::root(Sperp2 + rp * rp, u, iu);
-                const double mur = kFast ? rp * iu : rp / u;
-                rc = locate(g, u, t);
-                const double sv = sv_at(g, rc, t, mur);                // :667-668
-                const double v0u = kFast ? cubic_s(rc + kGV0 * 8, t) * iu : cubic_s(rc + kGV0 * 8, t) / u;
-                const double jd = 1.0 + G * v0u + G * mur * mur * (cubic_s(rc + kGD0 * 8, t) - v0u);
-                const double xi = xi_at(rp, u, mur, rc, t);
-                if (kFast) {
-                    const double isv = rcp_cubic(sv);
-                    const double z = xm * isv;
-                    acc += wm * (1.0 + xi) * rcp_cubic(jd) * M::gauss(z * z, etab_s) * isv;
-                } else {
-                    const double z = xm / sv;
-                    acc += wm * (1.0 + xi) * (1.0 / jd) * exp(-0.5 * z * z) / sv;
-                }
-            }
+            int mi = 0;
+            for (; mi + kGU <= nx; mi += kGU) acc = disp_nodes(NodeCount<kGU>{}, mi, acc, first, ifirst);
+            for (; mi < nx; ++mi) acc = disp_nodes(NodeCount<1>{}, mi, acc, first, ifirst);
             result = acc - 1.0;
         } else {
             // kaiser / euclid_special: ccf_model.py:692-741
