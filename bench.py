@@ -526,7 +526,7 @@ def run_mcmc(args):
                            "calls_per_step": calls_per_step, "parallelism": f"{world} independent chain(s), replicas only"},
                 "latency_us": {"median": float(np.median(lat_us)), "p95": float(np.percentile(lat_us, 95)),
                                "min": float(lat_us.min())},
-                "e2e": {"value": calls / wall, "unit": "calls/s", "h2d_bytes_per_step": calls_per_step * 64,
+                "e2e": {"value": calls / wall, "unit": "calls/s", "h2d_bytes_per_step": calls_per_step * 80,
                         "d2h_bytes_per_step": calls_per_step * 16, "api": "CCFLikelihood.calculate"},
                 "gpu_launches": int(2 * calls_per_step * args.steps), "final_logp": float(cur)}
         print(json.dumps(line))

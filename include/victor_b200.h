@@ -143,9 +143,12 @@ void vb200_destroy(vb200_ctx *ctx);
 
 /* Kernel variant switches (integers): "fast_math" (1 = hand-rolled rsqrt / rcp / exp, default;
  * 0 = CUDA libm), "nsplit" (blocks per parameter row; 0 = automatic), "threads" (block size),
- * "ilp" (velocity nodes per loop trip: 1, 2, 4), "exp_degree" (5, default, or 6).  They select
- * among the tuned streaming kernels; the general kernel (dispersion, kaiser, anisotropic or
- * from-data real-space input) has one variant per rsd_model. */
+ * "ilp" (velocity nodes per loop trip: 1, 2, 4), "exp_degree" (5, default, or 6), "newton" (3 = cubic
+ * refinement of the MUFU seeds, default; 2 = one Newton step).  They select among the tuned streaming
+ * kernels; the general kernel (dispersion, kaiser, anisotropic or from-data real-space input) has one
+ * variant per rsd_model.  "fuse": chi2 / lnL in the epilogue of the theory kernel when one block owns a
+ * row (0 never, 1 where measured faster = default, 2 always).  "graph": replay calls of up to 256 host
+ * rows (MCMC steps) as one CUDA graph (1 = default, 0 = plain stream submissions). */
 int vb200_set_option(vb200_ctx *ctx, const char *key, int64_t value);
 
 /* xi(s, mu) and / or its projections for n parameter rows.

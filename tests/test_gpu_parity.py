@@ -233,6 +233,32 @@ def test_fused_likelihood_epilogue_is_bit_identical(fit):
         assert np.array_equal(lnl_t, out[0][0]) and np.array_equal(chi2_t, out[0][1])
 
 
+def test_small_calls_replayed_as_graph(fit, golden):
+    """MCMC-sized calls (host rows, n <= 256) go through a captured CUDA graph; changing n or an option
+    rebuilds it; results equal the plain submissions bit for bit and the golden values."""
+    g = golden("boss_streaming_points")
+    P = g["params"]
+    eng, _ = fit._fit_engine({})
+    ref_l, ref_c = fit.log_likelihood_batch(P)                 # 80 rows: still the small path
+    np.testing.assert_allclose(ref_c, g["chi2"], rtol=0, atol=CHI2_ATOL)
+    for graph in (1, 0, 1):
+        eng.set_option("graph", graph)
+        for sl in (slice(0, 1), slice(3, 6), slice(0, 1), slice(0, 1), slice(0, 80), slice(79, 80)):
+            l, c = fit.log_likelihood_batch(P[sl])
+            assert np.array_equal(l, ref_l[sl]) and np.array_equal(c, ref_c[sl])
+        before = eng.launch_count()
+        for i in range(5):
+            lnl, chi2 = fit.log_likelihood({"fsigma8": float(P[i, 0]), "beta": float(P[i, 1]), "sigma_v": float(P[i, 2]),
+                                            "aperp": float(P[i, 3]), "apar": float(P[i, 4])})
+            assert chi2 == ref_c[i] and lnl == ref_l[i]
+        assert eng.launch_count() - before == 10               # K1 + K2 per call, graph or not
+    eng.set_option("fast_math", 0)                             # a different kernel variant: the graph is rebuilt
+    l0, c0 = fit.log_likelihood_batch(P[:2])
+    eng.set_option("fast_math", 1)
+    l1, c1 = fit.log_likelihood_batch(P[:2])
+    assert np.array_equal(c1, ref_c[:2]) and np.allclose(c0, c1, rtol=0, atol=1e-8) and not np.array_equal(c0, c1)
+
+
 def test_against_oracle_fresh_points(fit, boss_blocks):
     """Seeded rows that are not in the golden files, checked against the CPU oracle."""
     from oracle.ccf_oracle import OracleFit

@@ -107,7 +107,14 @@ struct vb200_ctx {
     int opt_fuse = 1;             // batch mode: chi2 / lnL in the epilogue of K1 instead of a K2 launch
     bool tuned = false;           // streaming + isotropic xi + model coordinates: the tuned kernel applies
     // small-call path (MCMC steps): page-locked staging for the rows in and (chi2 | lnL) out
-    double *pin = nullptr, *d_small = nullptr;
+    double *pin = nullptr, *d_small = nullptr, *d_small_theory = nullptr;
+    // the small-call sequence (H2D, K1, K2, D2H) as an instantiated CUDA graph, rebuilt when n or an option changes
+    cudaGraphExec_t small_exec = nullptr;
+    int64_t small_n = -1;
+    long long small_launches = 0;
+    cudaStream_t cap_stream = nullptr;
+    bool graphs_ok = true;
+    int opt_graph = 1;
     long long launches = 0;
     size_t k1_smem_limit = 0;
     double xw[2 * kMaxNx] = {0};  // host copy of x_m | w_m for the kernel-parameter table
@@ -292,12 +299,71 @@ int launch_k2(vb200_ctx *c, const double *d_params, const double *d_theory, long
     a.n = n;
     a.chi2 = d_chi2;
     a.lnl = d_lnl;
-    const long long blocks = (n + kK2Warps - 1) / kK2Warps;
-    const size_t smem = (size_t)kK2Warps * c->fd.p * sizeof(double);
-    k_chi2<<<(unsigned)blocks, kK2Warps * 32, smem, st>>>(a);
+    if (n <= (long long)c->sm_count * 4) {
+        // few rows: a block per row, so that one row's matrix reads are spread over eight warps
+        k_chi2_block<<<(unsigned)n, kK2Warps * 32, (size_t)fused_fit_doubles(c->fd.p) * sizeof(double), st>>>(a);
+    } else {
+        const long long blocks = (n + kK2Warps - 1) / kK2Warps;
+        const size_t smem = (size_t)kK2Warps * c->fd.p * sizeof(double);
+        k_chi2<<<(unsigned)blocks, kK2Warps * 32, smem, st>>>(a);
+    }
     CK(cudaGetLastError());
     c->launches++;
     return VB200_OK;
+}
+
+// H2D of the staged rows, K1, K2 (unless fused), D2H of (chi2 | lnL) -- the whole small call on one stream
+int small_sequence(vb200_ctx *c, int64_t n, cudaStream_t st) {
+    int rc;
+    double *h_out = c->pin + (size_t)kSmallCall * VB200_NPAR, *d_out = c->d_small + (size_t)kSmallCall * VB200_NPAR;
+    CK(cudaMemcpyAsync(c->d_small, c->pin, (size_t)n * VB200_NPAR * sizeof(double), cudaMemcpyHostToDevice, st));
+    bool fused = false;
+    if ((rc = launch_k1(c, c->d_small, n, c->fit_s, c->fit_ns, c->fit_mu, c->fit_sqmu, c->fit_wmu, c->fit_nmu,
+                        c->fit_L, nullptr, c->d_small_theory, st, false, d_out, d_out + n, &fused)))
+        return rc;
+    if (!fused && (rc = launch_k2(c, c->d_small, c->d_small_theory, n, d_out, d_out + n, st))) return rc;
+    CK(cudaMemcpyAsync(h_out, d_out, (size_t)2 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    return VB200_OK;
+}
+
+void drop_small_graph(vb200_ctx *c) {
+    if (c->small_exec) cudaGraphExecDestroy(c->small_exec);
+    c->small_exec = nullptr;
+    c->small_n = -1;
+}
+
+// capture small_sequence for n rows into an executable graph; on any failure graphs are switched off for
+// this context and the caller uses the plain sequence
+bool build_small_graph(vb200_ctx *c, int64_t n) {
+    drop_small_graph(c);
+    if (!c->cap_stream && cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        return c->graphs_ok = false;
+    }
+    const long long before = c->launches;
+    if (cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        return c->graphs_ok = false;
+    }
+    const int rc = small_sequence(c, n, c->cap_stream);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(c->cap_stream, &graph);
+    c->small_launches = c->launches - before;
+    c->launches = before;
+    if (rc != VB200_OK || e != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        return c->graphs_ok = false;
+    }
+    const cudaError_t ei = cudaGraphInstantiate(&c->small_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) {
+        c->small_exec = nullptr;
+        cudaGetLastError();
+        return c->graphs_ok = false;
+    }
+    c->small_n = n;
+    return true;
 }
 
 void fill_exp_table(double *t) {
@@ -341,8 +407,11 @@ void vb200_destroy(vb200_ctx *c) {
     c->sc_xi.release();
     c->sc_mult.release();
     c->sc_grid.release();
+    if (c->small_exec) cudaGraphExecDestroy(c->small_exec);
+    if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
     if (c->pin) cudaFreeHost(c->pin);
     if (c->d_small) cudaFree(c->d_small);
+    if (c->d_small_theory) cudaFree(c->d_small_theory);
     delete c;
 }
 
@@ -488,7 +557,9 @@ int vb200_create(const vb200_model_tables *m, const vb200_fit_tables *f, int dev
 
 int vb200_set_option(vb200_ctx *c, const char *key, int64_t value) {
     if (!c || !key) return fail(VB200_EINVAL, "null argument");
-    if (!strcmp(key, "fast_math")) c->opt_fast = value ? 1 : 0;
+    drop_small_graph(c);   // the captured small-call sequence bakes the kernel variant in
+    if (!strcmp(key, "graph")) c->opt_graph = value ? 1 : 0;
+    else if (!strcmp(key, "fast_math")) c->opt_fast = value ? 1 : 0;
     else if (!strcmp(key, "nsplit")) c->opt_nsplit = (int)value;
     else if (!strcmp(key, "fuse")) c->opt_fuse = (int)std::max<int64_t>(0, std::min<int64_t>(value, 2));
     else if (!strcmp(key, "newton")) {
@@ -604,21 +675,26 @@ int vb200_likelihood(vb200_ctx *c, const double *params, int64_t n, double *theo
     const bool params_on_host = !is_device_ptr(params);
     if (n <= kSmallCall && !theory && chi2 && lnlike && params_on_host && !is_device_ptr(chi2) &&
         !is_device_ptr(lnlike)) {
-        // one pinned H2D of the rows, two launches, one pinned D2H of (chi2 | lnL), one sync
+        // one pinned H2D of the rows, two launches, one pinned D2H of (chi2 | lnL), one sync -- replayed as a
+        // CUDA graph (one submission instead of four) while n and the options stay the same
         if (!c->pin) {
             CK(cudaMallocHost(&c->pin, (size_t)kSmallCall * (VB200_NPAR + 2) * sizeof(double)));
             CK(cudaMalloc(&c->d_small, (size_t)kSmallCall * (VB200_NPAR + 2) * sizeof(double)));
+            CK(cudaMalloc(&c->d_small_theory, (size_t)kSmallCall * p * sizeof(double)));
         }
-        if ((rc = c->sc_theory.ensure((size_t)n * p))) return rc;
-        double *h_out = c->pin + (size_t)kSmallCall * VB200_NPAR, *d_out = c->d_small + (size_t)kSmallCall * VB200_NPAR;
+        double *h_out = c->pin + (size_t)kSmallCall * VB200_NPAR;
         memcpy(c->pin, params, (size_t)n * VB200_NPAR * sizeof(double));
-        CK(cudaMemcpyAsync(c->d_small, c->pin, (size_t)n * VB200_NPAR * sizeof(double), cudaMemcpyHostToDevice, st));
-        bool fused = false;
-        if ((rc = launch_k1(c, c->d_small, n, c->fit_s, c->fit_ns, c->fit_mu, c->fit_sqmu, c->fit_wmu, c->fit_nmu,
-                            c->fit_L, nullptr, c->sc_theory.ptr, st, false, d_out, d_out + n, &fused)))
-            return rc;
-        if (!fused && (rc = launch_k2(c, c->d_small, c->sc_theory.ptr, n, d_out, d_out + n, st))) return rc;
-        CK(cudaMemcpyAsync(h_out, d_out, (size_t)2 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        bool replayed = false;
+        if (c->opt_graph && c->graphs_ok && (c->small_n == n || build_small_graph(c, n))) {
+            if (cudaGraphLaunch(c->small_exec, st) == cudaSuccess) {
+                c->launches += c->small_launches;
+                replayed = true;
+            } else {
+                cudaGetLastError();
+                c->graphs_ok = false;
+            }
+        }
+        if (!replayed && (rc = small_sequence(c, n, st))) return rc;
         CK(cudaStreamSynchronize(st));
         memcpy(chi2, h_out, (size_t)n * sizeof(double));
         memcpy(lnlike, h_out + n, (size_t)n * sizeof(double));
