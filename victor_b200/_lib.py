@@ -10,7 +10,8 @@ from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_void_
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvictor_b200.so")
+# VICTOR_B200_LIB selects another build of the same library (A/B timing of kernel variants)
+LIB_PATH = os.environ.get("VICTOR_B200_LIB") or os.path.join(_HERE, "libvictor_b200.so")
 
 MAX_POLES = 3
 c_double_p = POINTER(c_double)
