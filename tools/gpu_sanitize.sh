@@ -4,3 +4,6 @@ python tools/sanitize_target.py > gpurun_out/sanitize_plain.log 2>&1 || { echo "
 timeout 600 compute-sanitizer --tool memcheck --log-file gpurun_out/memcheck.log python tools/sanitize_target.py > gpurun_out/sanitize_run.log 2>&1
 echo "sanitizer rc=$?"
 tail -5 gpurun_out/sanitize_run.log; tail -8 gpurun_out/memcheck.log
+timeout 900 compute-sanitizer --tool racecheck --log-file gpurun_out/racecheck.log python tools/sanitize_target.py > gpurun_out/sanitize_race.log 2>&1
+echo "racecheck rc=$?"
+tail -6 gpurun_out/racecheck.log
