@@ -557,6 +557,7 @@ int vb200_create(const vb200_model_tables *m, const vb200_fit_tables *f, int dev
 
 int vb200_set_option(vb200_ctx *c, const char *key, int64_t value) {
     if (!c || !key) return fail(VB200_EINVAL, "null argument");
+    DeviceGuard g(c->device);
     drop_small_graph(c);   // the captured small-call sequence bakes the kernel variant in
     if (!strcmp(key, "graph")) c->opt_graph = value ? 1 : 0;
     else if (!strcmp(key, "fast_math")) c->opt_fast = value ? 1 : 0;
