@@ -195,8 +195,9 @@ k1_fn pick_general(int rsd_model, bool fast) {
     return fast ? k_multipoles_general<kRsdKaiser, true> : k_multipoles_general<kRsdKaiser, false>;
 }
 
-// blocks per parameter row: one once the rows alone fill the GPU a few times over, else the s range
-// is split so that a single row (MCMC step) still spreads over the SMs
+// blocks per parameter row: one once the rows alone fill the GPU a few times over, else the s range is split
+// so that a single row (MCMC step) still spreads over the SMs.  (A wave-count cost model choosing among all
+// splits was tried: within +-7 % of this rule over n = 1 ... 16 384, profiles/r01s_probe_nsplit.log.)
 int pick_nsplit(const vb200_ctx *c, long long n, int ns, bool pairwise) {
     int nsplit = pairwise ? 0 : c->opt_nsplit;
     if (nsplit <= 0) {
@@ -205,6 +206,8 @@ int pick_nsplit(const vb200_ctx *c, long long n, int ns, bool pairwise) {
     }
     return std::max(1, std::min(nsplit, ns));
 }
+
+k1_fn fused_variant(const vb200_ctx *c);
 
 // opt_fuse: 0 never, 1 where it pays, 2 always.  Measured (profiles/r01n_variants_fuse.log):
 //   general kernel, velocity-integral models: +0.5 % and no theory scratch -> fused by default;
