@@ -17,6 +17,7 @@ namespace vb200 {
 
 // per-cell record of the general kernel:
 //   xi_l cubics (3 x 4, unused ones zero) | V0 (4) | D0 (4) | SV (4) | origin | pad
+// (V0, D0 times the row's velocity amplitude B, G or M G, whichever the model uses them with)
 constexpr int kRecG = 26;
 constexpr int kGU = 2;   // velocity nodes in flight per thread (general kernel)
 template <int U>
@@ -153,9 +154,13 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
     for (int i = tid; i < m.nbucket; i += nthr) bbase[i] = m.bucket_base[i];
     if (tid < kExpTab) etab[tid] = m.exp_tab[tid];
     const unsigned etab_s = (unsigned)__cvta_generic_to_shared(etab);
-    if (m.v0b) __syncthreads();   // the cell records below need this row's empirical-correction amplitude
+    __syncthreads();   // the cell records below carry this row's velocity amplitude (and empirical correction)
     {
         const double Ae = m.v0b ? scal[8] : 0.0;
+        // V0 and D0 are stored times the amplitude they are always used with: B = A_v / sigma_v in the mean of
+        // the streaming pdf (:656), G = iaH A_v / f in the coordinate map and Jacobian of the dispersion model
+        // (:660-671), M G in the kaiser / euclid_special forms (:698-714) -- one multiply less per evaluation
+        const double vsc = kModel == kRsdStreaming ? scal[4] : (kModel == kRsdDispersion ? scal[5] : Mk * scal[5]);
         int kb = 0;
         double tb = 0.0;
         if (m.beta_dependent) {
@@ -177,14 +182,14 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
             }
             if (m.vd_beta_dep) {   // linear_bias: V0, D0 follow the monopole's beta dependence
                 const double *tv = m.v0 + (size_t)kb * 4 * per, *td = m.d0 + (size_t)kb * 4 * per;
-                r[kGV0 + c] = fma(fma(fma(tv[3 * per + i], tb, tv[2 * per + i]), tb, tv[per + i]), tb, tv[i]);
-                r[kGD0 + c] = fma(fma(fma(td[3 * per + i], tb, td[2 * per + i]), tb, td[per + i]), tb, td[i]);
+                r[kGV0 + c] = vsc * fma(fma(fma(tv[3 * per + i], tb, tv[2 * per + i]), tb, tv[per + i]), tb, tv[i]);
+                r[kGD0 + c] = vsc * fma(fma(fma(td[3 * per + i], tb, td[2 * per + i]), tb, td[per + i]), tb, td[i]);
             } else if (m.v0b) {    // empirical correction (1 + Av delta(r)) of the mean velocity, ccf_model.py:451-459
-                r[kGV0 + c] = fma(Ae, m.v0b[i], m.v0[i]);
-                r[kGD0 + c] = fma(Ae, m.d0b[i], m.d0[i]);
+                r[kGV0 + c] = vsc * fma(Ae, m.v0b[i], m.v0[i]);
+                r[kGD0 + c] = vsc * fma(Ae, m.d0b[i], m.d0[i]);
             } else {
-                r[kGV0 + c] = m.v0[i];
-                r[kGD0 + c] = m.d0[i];
+                r[kGV0 + c] = vsc * m.v0[i];
+                r[kGD0 + c] = vsc * m.d0[i];
             }
             r[kGSV + c] = m.sv[i];
             if (c == 0) {
@@ -195,7 +200,7 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
     }
     __syncthreads();
 
-    const double f = scal[0], sperp_f = scal[1], spar_f = scal[2], kappa = scal[3], B = scal[4], G = scal[5];
+    const double f = scal[0], sperp_f = scal[1], spar_f = scal[2], kappa = scal[3];
     const double apar = scal[6];
     GenCtx g;
     g.rec_s = (unsigned)__cvta_generic_to_shared(rec);
@@ -259,7 +264,7 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
             }
 #pragma unroll
             for (int i = 0; i < U; ++i) {
-                const double d = xm[i] - B * cubic_s(rc[i] + kGV0 * 8, t[i]) * mur[i];
+                const double d = fma(-cubic_s(rc[i] + kGV0 * 8, t[i]), mur[i], xm[i]);   // x - (B V0)(u) mu_r
                 z[i] = kFast ? d * isv[i] : d / sv[i];                 // :656
             }
 #pragma unroll
@@ -290,8 +295,8 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
                 for (int i = 0; i < U; ++i) rc[i] = locate(g, u[i], t[i]);
 #pragma unroll
                 for (int i = 0; i < U; ++i)
-                    rp[i] = kFast ? num[i] * rcp_cubic(fma(G * cubic_s(rc[i] + kGV0 * 8, t[i]), iu[i], 1.0))
-                                  : num[i] / (1.0 + G * cubic_s(rc[i] + kGV0 * 8, t[i]) / u[i]);
+                    rp[i] = kFast ? num[i] * rcp_cubic(fma(cubic_s(rc[i] + kGV0 * 8, t[i]), iu[i], 1.0))
+                                  : num[i] / (1.0 + cubic_s(rc[i] + kGV0 * 8, t[i]) / u[i]);
             }
             double mur[U];
 #pragma unroll
@@ -306,7 +311,7 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
                 const double sv = sv_at(g, rc[i], t[i], mur[i]);       // :667-668
                 const double v0 = cubic_s(rc[i] + kGV0 * 8, t[i]);
                 const double v0u = kFast ? v0 * iu[i] : v0 / u[i];
-                const double jd = 1.0 + G * v0u + G * mur[i] * mur[i] * (cubic_s(rc[i] + kGD0 * 8, t[i]) - v0u);
+                const double jd = fma(mur[i] * mur[i], cubic_s(rc[i] + kGD0 * 8, t[i]) - v0u, 1.0 + v0u);
                 const double xi = xi_at(rp[i], u[i], mur[i], rc[i], t[i]);
                 const double wm = a.xw[kMaxNx + mi + i];
                 if (kFast) {
@@ -333,8 +338,8 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
             M::root(Sperp2 + Spar * Spar, Strue, iS);
             double t0;
             const unsigned r0 = locate(g, Strue, t0);
-            const double first = kFast ? fma(G * cubic_s(r0 + kGV0 * 8, t0), iS, 1.0)
-                                       : 1.0 + G * cubic_s(r0 + kGV0 * 8, t0) / Strue;
+            const double first = kFast ? fma(cubic_s(r0 + kGV0 * 8, t0), iS, 1.0)
+                                       : 1.0 + cubic_s(r0 + kGV0 * 8, t0) / Strue;
             const double ifirst = kFast ? rcp_cubic(first) : 0.0;
             double acc = 0.0;
             int mi = 0;
@@ -343,7 +348,6 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
             result = acc - 1.0;
         } else {
             // kaiser / euclid_special: ccf_model.py:692-741
-            const double MG = Mk * G;
             double rp = Spar;
             double u, t;
             unsigned rc;
@@ -352,13 +356,13 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
                 double Strue;
                 M::root(Sperp2 + Spar * Spar, Strue, iu);
                 rc = locate(g, Strue, t);
-                rp = kFast ? Spar * rcp_cubic(fma(MG * cubic_s(rc + kGV0 * 8, t), iu, 1.0))
-                           : Spar / (1.0 + MG * cubic_s(rc + kGV0 * 8, t) / Strue);
+                rp = kFast ? Spar * rcp_cubic(fma(cubic_s(rc + kGV0 * 8, t), iu, 1.0))
+                           : Spar / (1.0 + cubic_s(rc + kGV0 * 8, t) / Strue);
                 for (int it = 0; it < m.niter; ++it) {
                     M::root(Sperp2 + rp * rp, u, iu);
                     rc = locate(g, u, t);
-                    rp = kFast ? Spar * rcp_cubic(fma(MG * cubic_s(rc + kGV0 * 8, t), iu, 1.0))
-                               : Spar / (1.0 + MG * cubic_s(rc + kGV0 * 8, t) / u);
+                    rp = kFast ? Spar * rcp_cubic(fma(cubic_s(rc + kGV0 * 8, t), iu, 1.0))
+                               : Spar / (1.0 + cubic_s(rc + kGV0 * 8, t) / u);
                 }
             }
             M::root(Sperp2 + rp * rp, u, iu);
@@ -366,7 +370,7 @@ __global__ void __launch_bounds__(256) k_multipoles_general(const __grid_constan
             rc = locate(g, u, t);
             const double v0u = kFast ? cubic_s(rc + kGV0 * 8, t) * iu : cubic_s(rc + kGV0 * 8, t) / u;
             const double ca = (m.rsd_model == kRsdEuclid) ? 3.0 : 1.0, cb = (m.rsd_model == kRsdEuclid) ? 2.0 : 1.0;
-            const double J = ca * MG * v0u + cb * MG * Qk * mur * mur * (cubic_s(rc + kGD0 * 8, t) - v0u);
+            const double J = ca * v0u + cb * Qk * mur * mur * (cubic_s(rc + kGD0 * 8, t) - v0u);
             const double xi = xi_at(rp, u, mur, rc, t);
             if (m.rsd_model == kRsdEuclid || m.kaiser_approx)
                 result = Mk * xi - J;
