@@ -184,7 +184,7 @@ k1_fn pick_general_fused(int rsd_model, bool fast) {
     if (!fast) return nullptr;
     if (rsd_model == kRsdStreaming) return k_multipoles_general<kRsdStreaming, true, true>;
     if (rsd_model == kRsdDispersion) return k_multipoles_general<kRsdDispersion, true, true>;
-    return k_multipoles_general<kRsdKaiser, true, true>;
+    return k_multipoles_kaiser<true, true>;
 }
 
 k1_fn pick_general(int rsd_model, bool fast) {
@@ -192,7 +192,7 @@ k1_fn pick_general(int rsd_model, bool fast) {
         return fast ? k_multipoles_general<kRsdStreaming, true> : k_multipoles_general<kRsdStreaming, false>;
     if (rsd_model == kRsdDispersion)
         return fast ? k_multipoles_general<kRsdDispersion, true> : k_multipoles_general<kRsdDispersion, false>;
-    return fast ? k_multipoles_general<kRsdKaiser, true> : k_multipoles_general<kRsdKaiser, false>;
+    return fast ? k_multipoles_kaiser<true> : k_multipoles_kaiser<false>;
 }
 
 // blocks per parameter row: one once the rows alone fill the GPU a few times over, else the s range is split
