@@ -461,8 +461,8 @@ int vb200_create(const vb200_model_tables *m, const vb200_fit_tables *f, int dev
     d.kaiser_shift = m->kaiser_coord_shift;
     d.niter = m->niter;
     for (int i = 0; i < kMaxPoles; ++i) d.ells[i] = m->ells[i];
-    c->tuned = (m->rsd_model == VB200_RSD_STREAMING && m->n_ell == 1 && !m->realspace_from_data && m->sv_ny == 0 &&
-                !m->vd_beta_dependent && !m->v0b);
+    // (beta-dependent or empirically corrected velocity tables only change the prologue: still the tuned kernel)
+    c->tuned = (m->rsd_model == VB200_RSD_STREAMING && m->n_ell == 1 && !m->realspace_from_data && m->sv_ny == 0);
     const size_t nc4 = (size_t)m->ncell * 4;
     if ((rc = upload(c, m->origin, (size_t)m->ncell, &d.origin))) return bail(rc);
     if ((rc = upload(c, m->upper, (size_t)m->ncell, &d.upper))) return bail(rc);

@@ -164,7 +164,14 @@ __global__ void __launch_bounds__(256, 4) k_multipoles(const __grid_constant__ K
             if (c == 0) v += 1.0;
             double *r = rec + cell * kRec;
             r[c] = v;
-            r[4 + c] = B * m.v0[i];
+            double v0 = m.v0[i];
+            if (m.vd_beta_dep) {   // linear_bias matter model: V0 follows the monopole's beta dependence (ccf_model.py:358-370)
+                const double *tv = m.v0 + (size_t)kb * 4 * per;
+                v0 = fma(fma(fma(tv[3 * per + i], tb, tv[2 * per + i]), tb, tv[per + i]), tb, tv[i]);
+            } else if (m.v0b) {    // empirical correction (1 + Av delta(r)) of the mean velocity (:451-455)
+                v0 = fma(scal[8], m.v0b[i], v0);
+            }
+            r[4 + c] = B * v0;
             // kFast: SV / sqrt(16 log2 e), so that its reciprocal carries the scale of the exp argument
             // (the weights a.xw are divided by the same constant on the host)
             r[8 + c] = C::kFast ? m.sv[i] * (1.0 / kGaussScale) : m.sv[i];
