@@ -553,6 +553,8 @@ def golden_helpers(victor):
     out["from_multipoles_q"] = f2(qx, qy)
     f2 = ccf.xi_2D_from_multipoles(dict(p1), rmax=60, rsd_model="dispersion")
     out["from_multipoles_disp60_q"] = f2(qx, qy)
+    out["five_poles"] = ccf.theory_multipole_vector(ccf.s, dict(p1), [0, 1, 2, 3, 4])        # more than three at once
+    out["even_four"] = ccf.theory_multipole_vector(ccf.s, dict(p1), [0, 2, 4, 6], rsd_model="dispersion")
     f1 = ccf.theory_xi_2D(dict(p1), rmax=85)
     out["xi2d_grid"] = f1(np.linspace(0.01, 85), np.linspace(-85, 85))
     out["xi2d_q"] = f1(qx, qy)

@@ -605,6 +605,8 @@ def test_two_dimensional_helpers(fit, golden):
     np.testing.assert_allclose(f1(gx, gy), g["xi2d_grid"], rtol=RTOL, atol=ATOL)
     np.testing.assert_allclose(f1(g["qx"], g["qy"]), g["xi2d_q"], rtol=RTOL, atol=ATOL)
     np.testing.assert_allclose(f1(12.5, -40.0), g["xi2d_scalar"], rtol=RTOL, atol=ATOL)
+    assert_theory(fit.theory_multipole_vector(fit.s, dict(p1), [0, 1, 2, 3, 4]), g["five_poles"], ns=30)
+    assert_theory(fit.theory_multipole_vector(fit.s, dict(p1), [0, 2, 4, 6], rsd_model="dispersion"), g["even_four"], ns=30)
     f2 = fit.xi_2D_from_multipoles(dict(p1), rmax=85)
     np.testing.assert_allclose(f2(gx, gy), g["from_multipoles_grid"], rtol=RTOL, atol=1e-12)
     np.testing.assert_allclose(f2(g["qx"], g["qy"]), g["from_multipoles_q"], rtol=RTOL, atol=1e-12)

@@ -480,7 +480,10 @@ class CCFModel:
         if np.any(np.diff(s) <= 0):
             raise InputError("theory_multipoles: s must be strictly increasing")
         mu, W = _tables.mu_projection_weights(poles, nmu=int(opts.get("mu_nodes", 100)))
-        return self._engine(opts).theory(params_to_rows(params), s, mu, W)[1]
+        eng, rows = self._engine(opts), params_to_rows(params)
+        # the kernels project onto at most MAX_POLES multipoles per launch; longer lists go in groups
+        groups = [eng.theory(rows, s, mu, W[a:a + _tables.MAX_POLES])[1] for a in range(0, len(poles), _tables.MAX_POLES)]
+        return groups[0] if len(groups) == 1 else np.concatenate(groups, axis=1)
 
     def theory_multipoles(self, s, params, poles=[0, 2], **kwargs):
         """Dict of model multipoles at ``s`` (reference: ccf_model.py:791-827)."""
