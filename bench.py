@@ -395,8 +395,16 @@ def run_dense(args):
     eng = fit._engine(opts)
     mu, W = T.mu_projection_weights(DENSE["poles"], nmu=DENSE["nmu"])
     s = np.asarray(fit.s, dtype=np.float64)
-    n = args.batch
-    rows_host = params_to_rows(synthetic_batch(n, SEED + rank))
+    if args.sweep:
+        # one parameter sweep of `--sweep` rows in total, sharded over the ranks (strong scaling: configs[3] reads
+        # "1M-point parameter sweep sharded over 2/4/8 B200")
+        from victor_b200.batch import shard_bounds
+        lo, hi = shard_bounds(args.sweep, world)[rank]
+        rows_host = params_to_rows(synthetic_batch(args.sweep, SEED)[lo:hi])
+        n = hi - lo
+    else:
+        n = args.batch
+        rows_host = params_to_rows(synthetic_batch(n, SEED + rank))
     d_params = torch.from_numpy(rows_host).to(dev)
     d_mult = torch.empty((n, len(DENSE["poles"]), len(s)), dtype=torch.float64, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -439,14 +447,16 @@ def run_dense(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms = float(t[0]), float(t[1])
     if rank == 0:
-        evals = n * world * args.steps
+        evals = (args.sweep if args.sweep else n * world) * args.steps
         fl = flop_k1(len(s), DENSE["nmu"], DENSE["nx"], len(DENSE["poles"]))
         achieved = n * args.steps * fl / (total_ms * 1e-3) / 1e12
         line = {"metric": "theory-vector evals/sec (streaming, dense grid, l=0,2,4)", "value": evals / (total_ms * 1e-3),
                 "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+                "scaling": "strong" if args.sweep else "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "BOSS tables, streaming model, dense grid (BASELINE.json configs[3])",
+                           "sweep_rows_total": args.sweep or None,
                            "rows_per_gpu": n, "ns": len(s), "nmu": DENSE["nmu"], "nx": DENSE["nx"],
                            "poles": DENSE["poles"], "l2": "flushed between timed steps (256 MiB write)",
                            "parallelism": f"rows sharded over {world} GPU(s), no collective"},
@@ -544,6 +554,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--sweep", type=int, default=0,
+                    help="dense workload: total rows of one sweep sharded over the GPUs (strong scaling), e.g. 1048576")
     ap.add_argument("--workload", default="boss", choices=["boss", "dense", "mcmc"],
                     help="boss: BASELINE metric (default); dense: configs[3]; mcmc: configs[4]")
     args = ap.parse_args()
