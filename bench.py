@@ -162,7 +162,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -358,7 +358,7 @@ def run_gpu(args):
             "flop_per_eval_total": FLOP_PER_EVAL,
             "check": {"lnl_finite": bool(np.all(np.isfinite(lnl_h))), "chi2_row0": float(chi2_h[0])},
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     fit.close()
@@ -469,7 +469,7 @@ def run_dense(args):
                              "peak_source": "nominal 148 SM x 64 lanes x 2 x 1.965 GHz", "flop_per_eval": fl,
                              "traffic": None},
                 "cpu_baseline": None}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     fit.close()
@@ -539,14 +539,33 @@ def run_mcmc(args):
                 "e2e": {"value": calls / wall, "unit": "calls/s", "h2d_bytes_per_step": calls_per_step * 80,
                         "d2h_bytes_per_step": calls_per_step * 16, "api": "CCFLikelihood.calculate"},
                 "gpu_launches": int(2 * calls_per_step * args.steps), "final_logp": float(cur)}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     like.ccf.close()
     return 0
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """Write the one JSON result line to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    # Libraries print banners on stdout (NCCL: "NCCL version ..."): from here on file descriptor 1 points at
+    # stderr, and only emit() writes to the real stdout -- exactly one JSON line from rank 0.
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
