@@ -562,6 +562,51 @@ def golden_helpers(victor):
     np.savez(os.path.join(OUT, "boss_helpers.npz"), **out, **meta())
 
 
+def golden_loader_options(victor):
+    """Input-side options of the loaders that no shipped configuration uses (ccf_model.py:99-297, ccf_fit.py:44-164):
+    `simulation_number` (files holding several realisations), an *integrated* matter template, an unfiltered
+    dispersion template, a non-default cosmology.  Inputs derived from the BOSS files and saved next to the outputs."""
+    import tempfile
+    from victor_b200.io_hdf5 import read_hdf5
+    model, data = boss_blocks()
+    msrc = read_hdf5(os.path.join(REF, model["input_model_data_file"]))
+    dsrc = read_hdf5(os.path.join(REF, data["redshift_space_ccf"]["data_file"]))
+    base = victor.CCFModel(copy.deepcopy(model))
+    rng = np.random.default_rng(SEED + 23)
+    wob = 1 + 0.03 * rng.standard_normal((3, 1, 1))
+    minp = dict(msrc)
+    minp["monopole_sims"] = msrc["monopole"][None] * wob
+    minp["quadrupole_sims"] = msrc["quadrupole"][None] * wob[::-1]
+    minp["rDelta"] = np.linspace(1.5, 140.0, 45)
+    minp["Delta"] = base.integrated_delta(minp["rDelta"])
+    dinp = dict(dsrc)
+    dinp["monopole_sims"] = dsrc["monopole"][None] * (1 + 0.01 * rng.standard_normal((3, 1, 1)))
+    dinp["quadrupole_sims"] = dsrc["quadrupole"][None] * (1 + 0.01 * rng.standard_normal((3, 1, 1)))
+    np.savez(os.path.join(OUT, "loader_inputs_model.npz"), **minp)
+    np.savez(os.path.join(OUT, "loader_inputs_data.npz"), **dinp)
+    tmp = tempfile.mkdtemp()
+    np.save(os.path.join(tmp, "m.npy"), minp, allow_pickle=True)
+    np.save(os.path.join(tmp, "d.npy"), dinp, allow_pickle=True)
+    mm, dd = copy.deepcopy(model), copy.deepcopy(data)
+    mm["dir"] = tmp
+    mm["input_model_data_file"] = "m.npy"
+    mm["cosmology"] = {"Omega_m": 0.29, "Omega_K": 0.01}
+    mm["realspace_ccf"].update(ccf_keys=["r", "monopole_sims", "quadrupole_sims"], simulation_number=2)
+    mm["matter_ccf"].update(template_keys=["rDelta", "Delta"], integrated=True)
+    mm["velocity_pdf"]["dispersion"]["filter"] = False
+    dd["redshift_space_ccf"].update(data_file=os.path.join(tmp, "d.npy"), ccf_keys=["s", "monopole_sims", "quadrupole_sims"],
+                                    simulation_number=1)
+    ccf = victor.CCFFit(mm, dd)
+    P = np.vstack([synthetic_batch(65536)[:4], edge_rows(ccf.beta)[[0, 9]]])
+    r31 = np.append([0.01], ccf.r)
+    out = dict(params=P, iaH=ccf.iaH, sv_rmu=ccf.sv_rmu, delta_r31=ccf.delta(r31), Delta_r31=ccf.integrated_delta(r31),
+               real_mono=ccf.real_multipoles["0"], data_mono=ccf.redshift_multipoles["0"])
+    for name, kw in (("streaming", {}), ("dispersion", {"rsd_model": "dispersion"})):
+        th, c2, ll = run_points(ccf, P, **kw)
+        out[f"{name}_theory"], out[f"{name}_chi2"], out[f"{name}_lnl"] = th, c2, ll
+    np.savez(os.path.join(OUT, "boss_loader_options.npz"), **out, **meta())
+
+
 def golden_example(victor):
     with open(os.path.join(REF, "config/example_model_input.yaml")) as fh:
         model = yaml.full_load(fh)["model"]
@@ -589,7 +634,7 @@ def golden_example(victor):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     v = refshim.install(REF)
-    which = sys.argv[1:] or ["boss", "more", "sv2d", "linear_bias", "misc", "fixed", "rmu", "velocity", "helpers", "example"]
+    which = sys.argv[1:] or ["boss", "more", "sv2d", "linear_bias", "misc", "fixed", "rmu", "velocity", "helpers", "loader", "example"]
     if "boss" in which:
         golden_boss(v)
     if "more" in which:
@@ -608,6 +653,8 @@ if __name__ == "__main__":
         golden_velocity(v)
     if "helpers" in which:
         golden_helpers(v)
+    if "loader" in which:
+        golden_loader_options(v)
     if "example" in which:
         golden_example(v)
     for fn in sorted(os.listdir(OUT)):

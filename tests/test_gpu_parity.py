@@ -630,6 +630,24 @@ def test_pairwise_points_match_the_grid_kernel(fit):
         np.testing.assert_array_equal(pairs, want)                  # same arithmetic per point: bit-identical
 
 
+@pytest.mark.parametrize("name,kw", [("streaming", {}), ("dispersion", {"rsd_model": "dispersion"})])
+def test_loader_options(boss_blocks, golden, name, kw):
+    """simulation_number, integrated matter template, unfiltered dispersion template, non-default cosmology."""
+    from victor_b200 import CCFFit
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["input_model_data_file"] = "tests/golden/loader_inputs_model.npz"
+    model["cosmology"] = {"Omega_m": 0.29, "Omega_K": 0.01}
+    model["realspace_ccf"].update(ccf_keys=["r", "monopole_sims", "quadrupole_sims"], simulation_number=2)
+    model["matter_ccf"].update(template_keys=["rDelta", "Delta"], integrated=True)
+    model["velocity_pdf"]["dispersion"]["filter"] = False
+    data["redshift_space_ccf"].update(data_file="tests/golden/loader_inputs_data.npz",
+                                      ccf_keys=["s", "monopole_sims", "quadrupole_sims"], simulation_number=1)
+    fm = CCFFit(model, data)
+    g = golden("boss_loader_options")
+    _check_fit(fm, g["params"], g, name, **kw)
+    fm.close()
+
+
 def test_direct_model_calls(fit, golden):
     """Notebook-style calls: odd poles, bare-integer poles, fine s grid, theory_xi on
     unsorted meshgrid input (sorted / uniqued like the reference) and at negative mu."""

@@ -672,3 +672,37 @@ def test_cell_tables_on_random_knot_sets():
         np.testing.assert_allclose(E._horner(coef, cell, t), want, rtol=1e-9, atol=1e-9 * np.abs(y).max())
 
     check()
+
+
+def loader_option_blocks(boss_blocks):
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["input_model_data_file"] = "tests/golden/loader_inputs_model.npz"
+    model["cosmology"] = {"Omega_m": 0.29, "Omega_K": 0.01}
+    model["realspace_ccf"].update(ccf_keys=["r", "monopole_sims", "quadrupole_sims"], simulation_number=2)
+    model["matter_ccf"].update(template_keys=["rDelta", "Delta"], integrated=True)
+    model["velocity_pdf"]["dispersion"]["filter"] = False
+    data["redshift_space_ccf"].update(data_file="tests/golden/loader_inputs_data.npz",
+                                      ccf_keys=["s", "monopole_sims", "quadrupole_sims"], simulation_number=1)
+    return model, data
+
+
+@pytest.mark.parametrize("name,kw", [("streaming", {}), ("dispersion", {"rsd_model": "dispersion"})])
+def test_tables_loader_options(boss_blocks, golden, name, kw):
+    """simulation_number, an integrated matter template, an unfiltered dispersion template and a non-default
+    cosmology (ccf_model.py:99-297, ccf_fit.py:44-114): loader state and results against the reference."""
+    from victor_b200 import CCFFit, InputError
+    from victor_b200.model import params_to_rows
+    fm = CCFFit(*loader_option_blocks(boss_blocks))
+    g = golden("boss_loader_options")
+    assert abs(fm.iaH - float(g["iaH"])) < 1e-16
+    r31 = np.append([0.01], fm.r)
+    np.testing.assert_allclose(fm.sv_rmu, g["sv_rmu"], rtol=1e-14)
+    np.testing.assert_allclose(fm.delta(r31), g["delta_r31"], rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(fm.integrated_delta(r31), g["Delta_r31"], rtol=1e-13)
+    np.testing.assert_array_equal(fm.real_multipoles["0"], g["real_mono"])
+    np.testing.assert_array_equal(fm.redshift_multipoles["0"], g["data_mono"])
+    _tables_vs_golden(fm, kw, params_to_rows(g["params"]), g[f"{name}_theory"], g[f"{name}_chi2"], g[f"{name}_lnl"])
+    bad = loader_option_blocks(boss_blocks)
+    bad[0]["realspace_ccf"]["simulation_number"] = 1.0
+    with pytest.raises(InputError):
+        CCFFit(*bad)

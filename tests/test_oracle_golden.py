@@ -252,3 +252,20 @@ def test_velocity_options(golden, boss_blocks):
                g["vtemplate_streaming_lnl"][[2]])
     check_rows(om, g["params"][[5]], g["vtemplate_dispersion_theory"][[5]], g["vtemplate_dispersion_chi2"][[5]],
                g["vtemplate_dispersion_lnl"][[5]], rsd_model="dispersion")
+
+
+def test_loader_options(golden, boss_blocks):
+    """simulation_number, integrated matter template, unfiltered dispersion template, non-default cosmology."""
+    g = golden("boss_loader_options")
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["input_model_data_file"] = "tests/golden/loader_inputs_model.npz"
+    model["cosmology"] = {"Omega_m": 0.29, "Omega_K": 0.01}
+    model["realspace_ccf"].update(ccf_keys=["r", "monopole_sims", "quadrupole_sims"], simulation_number=2)
+    model["matter_ccf"].update(template_keys=["rDelta", "Delta"], integrated=True)
+    model["velocity_pdf"]["dispersion"]["filter"] = False
+    data["redshift_space_ccf"].update(data_file="tests/golden/loader_inputs_data.npz",
+                                      ccf_keys=["s", "monopole_sims", "quadrupole_sims"], simulation_number=1)
+    om = OracleFit(model, data)
+    assert abs(om.iaH - float(g["iaH"])) < 1e-16
+    check_rows(om, g["params"][[1, 5]], g["dispersion_theory"][[1, 5]], g["dispersion_chi2"][[1, 5]],
+               g["dispersion_lnl"][[1, 5]], rsd_model="dispersion")
