@@ -553,6 +553,11 @@ def golden_helpers(victor):
     out["from_multipoles_q"] = f2(qx, qy)
     f2 = ccf.xi_2D_from_multipoles(dict(p1), rmax=60, rsd_model="dispersion")
     out["from_multipoles_disp60_q"] = f2(qx, qy)
+    out["corrmat_037"] = ccf.correlation_matrix(0.37)
+    out["errors_037"] = ccf.diagonal_errors(0.37)
+    out["data_multipoles_041"] = ccf.get_interpolated_redshift_multipoles(0.41)
+    out["precision_below_grid"] = ccf.get_interpolated_precision(0.10)
+    out["covariance_on_node"] = ccf.get_interpolated_covariance(float(ccf.beta_covmat[9]))
     out["five_poles"] = ccf.theory_multipole_vector(ccf.s, dict(p1), [0, 1, 2, 3, 4])        # more than three at once
     out["even_four"] = ccf.theory_multipole_vector(ccf.s, dict(p1), [0, 2, 4, 6], rsd_model="dispersion")
     f1 = ccf.theory_xi_2D(dict(p1), rmax=85)

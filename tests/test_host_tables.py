@@ -591,6 +591,12 @@ def test_profile_helpers_match_the_reference(fit, golden):
         np.testing.assert_allclose(dvr, g[f"dvr_{tag}"], rtol=1e-12, atol=1e-13)
     with pytest.raises(NotImplementedError):
         fit.delta_profiles(r, dict(p1), matter_model="excursion_set")
+    # host accessors of CCFFit (ccf_fit.py:166-323)
+    np.testing.assert_allclose(fit.correlation_matrix(0.37), g["corrmat_037"], rtol=1e-13, atol=1e-16)
+    np.testing.assert_allclose(fit.diagonal_errors(0.37), g["errors_037"], rtol=1e-14)
+    np.testing.assert_allclose(fit.get_interpolated_redshift_multipoles(0.41), g["data_multipoles_041"], rtol=1e-14)
+    np.testing.assert_array_equal(fit.get_interpolated_precision(0.10), g["precision_below_grid"])
+    np.testing.assert_array_equal(fit.get_interpolated_covariance(float(fit.beta_covmat[9])), g["covariance_on_node"])
 
 
 def test_grid_interpolator_follows_legacy_interp2d():
