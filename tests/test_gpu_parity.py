@@ -286,6 +286,16 @@ def test_nan_rows_follow_reference_convention(fit):
     assert lnl[2] == -np.inf and chi2[2] == np.inf
 
 
+def test_failed_point_is_logged(fit, caplog):
+    """A failing single-point call returns (-inf, inf) and reports it through logging, where the reference
+    prints (ccf_fit.py:477-481)."""
+    import logging
+    with caplog.at_level(logging.WARNING, logger="victor_b200"):
+        lnl, chi2 = fit.log_likelihood({"fsigma8": float("nan"), "beta": 0.37, "sigma_v": 380.0, "epsilon": 1.0})
+    assert lnl == -np.inf and chi2 == np.inf
+    assert any("Likelihood evaluation failed" in r.message for r in caplog.records)
+
+
 def test_full_batch_properties(fit):
     """BASELINE size (65,536 rows): size-independent properties instead of a CPU re-computation."""
     from bench import synthetic_batch

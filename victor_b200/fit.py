@@ -19,7 +19,7 @@ import numpy as np
 
 from . import tables as _tables
 from .model import CCFModel, params_to_rows
-from .utils import InputError, load_input_file
+from .utils import InputError, load_input_file, log
 
 
 class CCFFit(CCFModel):
@@ -203,6 +203,8 @@ class CCFFit(CCFModel):
         if fit_options["beta_interpolation"] == "likelihood" and not self.fixed_data:
             return self._likelihood_interpolated(eng, rows, return_theory)
         theory, chi2, lnl = eng.likelihood(rows, want_theory=return_theory)
+        if log.isEnabledFor(10) and len(lnl) > 1:    # logging.DEBUG
+            log.debug("log_likelihood_batch: %d rows, %d failed (-inf)", len(lnl), int(np.count_nonzero(lnl == -np.inf)))
         return (lnl, chi2, theory) if return_theory else (lnl, chi2)
 
     def _likelihood_interpolated(self, eng, rows, return_theory):
@@ -241,4 +243,6 @@ class CCFFit(CCFModel):
         """(lnlike, chisq) at one parameter point (reference: ccf_fit.py:356-483)."""
         self._check_point(params, kwargs)
         lnl, chi2 = self.log_likelihood_batch(params, **kwargs)
+        if lnl[0] == -np.inf:   # the reference prints here (ccf_fit.py:478-479)
+            log.warning("Likelihood evaluation failed, returning (-inf, inf). Parameters at fail point: %s", params)
         return float(lnl[0]), float(chi2[0])

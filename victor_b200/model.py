@@ -19,7 +19,7 @@ from scipy.interpolate import InterpolatedUnivariateSpline, RectBivariateSpline
 from scipy.special import legendre
 
 from . import tables as _tables
-from .utils import GridInterpolator2D, InputError, load_input_file, trapezoid
+from .utils import GridInterpolator2D, InputError, load_input_file, log, trapezoid
 
 
 def _ext3_spline(x, y):
@@ -338,6 +338,9 @@ class CCFModel:
             mt = _tables.build_model_tables(self, opts, nx=int(opts.get("velocity_nodes", 50)))
             fit = self._fit_tables(opts) if need_fit else None
             eng = Engine(mt, fit, device=self._device)
+            log.info("GPU context on device %s: rsd_model=%s, %d cells, %d real-space pole(s), beta-dependent=%s%s",
+                     eng.device, opts["rsd_model"], mt.ncell, mt.n_ell, mt.beta_dependent,
+                     ", with likelihood tables" if need_fit else "")
             self._engines[key] = eng
         return eng
 

@@ -4,9 +4,14 @@
 it is raised for anything wrong with user input (missing files or keys, bad shapes,
 invalid option values).
 """
+import logging
 import os
 
 import numpy as np
+
+# the reference reports failures with bare print() (ccf_fit.py:402, 408, 449, 478-479); here they go through
+# the standard logging module: logging.getLogger("victor_b200").setLevel(...) to see or silence them
+log = logging.getLogger("victor_b200")
 
 from .io_hdf5 import read_hdf5
 
