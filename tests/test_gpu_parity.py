@@ -259,6 +259,38 @@ def test_small_calls_replayed_as_graph(fit, golden):
     assert np.array_equal(c1, ref_c[:2]) and np.allclose(c0, c1, rtol=0, atol=1e-8) and not np.array_equal(c0, c1)
 
 
+def test_chunked_host_outputs_are_bit_identical(fit):
+    """Bulk outputs bound for host memory go in row chunks with the device-to-host copies overlapping later chunks;
+    any chunking gives the rows the single launch gives."""
+    rng = np.random.default_rng(21)
+    n = 5003
+    P = np.column_stack([rng.uniform(0.05, 1.5, n), rng.uniform(0.2, 0.6, n), rng.uniform(100, 500, n),
+                         rng.uniform(0.9, 1.1, n), rng.uniform(0.9, 1.1, n)])
+    for kw in ({}, {"rsd_model": "dispersion"}):
+        eng, _ = fit._fit_engine(kw)
+        out = {}
+        for chunks in (1, 5, 16):
+            eng.set_option("chunks", chunks)
+            out[chunks] = fit.log_likelihood_batch(P, return_theory=True, **kw)
+        eng.set_option("chunks", 0)
+        for chunks in (5, 16):
+            for a, b in zip(out[1], out[chunks]):
+                assert np.array_equal(a, b)
+    s = np.linspace(5.0, 100.0, 24)
+    mu = np.linspace(0, 1, 64)
+    meng = fit._engine(fit._merged_options({}))
+    ref = None
+    for chunks in (1, 7):
+        meng.set_option("chunks", chunks)
+        xi = fit.theory_xi_batch(s, mu, P[:700])
+        mult = fit.theory_multipoles_batch(s, P[:700], poles=[0, 2, 4], mu_nodes=64)
+        if ref is None:
+            ref = (xi, mult)
+        else:
+            assert np.array_equal(xi, ref[0]) and np.array_equal(mult, ref[1])
+    meng.set_option("chunks", 0)
+
+
 def test_against_oracle_fresh_points(fit, boss_blocks):
     """Seeded rows that are not in the golden files, checked against the CPU oracle."""
     from oracle.ccf_oracle import OracleFit

@@ -640,7 +640,7 @@ def test_cell_tables_on_random_knot_sets():
     from scipy.interpolate import InterpolatedUnivariateSpline
     from victor_b200 import tables as T
 
-    @settings(max_examples=40, deadline=None)
+    @settings(max_examples=60, deadline=None, derandomize=True, database=None)
     @given(st.integers(5, 40), st.floats(1e-3, 50.0), st.sampled_from(["uniform", "jitter", "cluster", "lattice"]),
            st.integers(0, 2 ** 31 - 1))
     def check(nk, scale, kind, seed):
@@ -668,11 +668,12 @@ def test_cell_tables_on_random_knot_sets():
                             np.nextafter(knots, np.inf), [0.0, 10 * knots[-1]]])
         cell, t = E._cells(m, u)
         want_cell = np.maximum(np.searchsorted(knots, u, side="right"), 1)
-        # a u that IS a knot may land in the cell on either side when the bucket spacing is not a lattice of
-        # the knots (floor(u inv_h) against bucket edges rounded the other way): the splines are continuous
-        # there, so both cells give the same value -- which is what the comparison below holds them to
+        # a u within an ulp or two of a knot may land in the cell on either side when the bucket spacing is not a
+        # lattice of the knots (floor(u inv_h) against bucket edges rounded the other way): the splines are
+        # continuous there, so both cells give the same value -- which is what the comparison below holds them to
         off = cell != want_cell
-        assert np.all(np.abs(cell - want_cell)[off] == 1) and np.all(np.isin(u[off], knots))
+        gap = np.abs(u[off][:, None] - knots[None, :]).min(axis=1) if off.any() else np.zeros(0)
+        assert np.all(np.abs(cell - want_cell)[off] == 1) and np.all(gap <= 4 * np.spacing(u[off]))
         coef = T.spline_cells(x, y, knots)
         want = InterpolatedUnivariateSpline(x, y, ext=3)(u)
         np.testing.assert_allclose(E._horner(coef, cell, t), want, rtol=1e-9, atol=1e-9 * np.abs(y).max())

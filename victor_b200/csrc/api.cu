@@ -115,6 +115,11 @@ struct vb200_ctx {
     cudaStream_t cap_stream = nullptr;
     bool graphs_ok = true;
     int opt_graph = 1;
+    // host-bound bulk outputs (theory vectors, xi blocks): rows go in chunks, and each chunk's device-to-host copy
+    // runs on `copy_stream` while later chunks compute
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t chunk_done[16] = {nullptr};
+    int opt_chunks = 0;           // 0 = automatic, 1 = never split, k = force k chunks
     long long launches = 0;
     size_t k1_smem_limit = 0;
     double xw[2 * kMaxNx] = {0};  // host copy of x_m | w_m for the kernel-parameter table
@@ -369,6 +374,22 @@ bool build_small_graph(vb200_ctx *c, int64_t n) {
     return true;
 }
 
+// how many row chunks for `bytes` of host-bound output over n rows: ~4 MB per chunk, at most 8, and never fewer
+// than 4096 rows per chunk (a chunk boundary idles the GPU for about half a wave of blocks)
+int plan_chunks(const vb200_ctx *c, long long n, size_t bytes) {
+    if (c->opt_chunks > 0) return (int)std::min<long long>(std::min(c->opt_chunks, 16), std::max<long long>(n, 1));
+    long long k = (long long)(bytes / ((size_t)4 << 20));
+    k = std::min<long long>(k, n / 4096);
+    return (int)std::max<long long>(1, std::min<long long>(k, 8));
+}
+
+int ensure_copy_stream(vb200_ctx *c, int nchunks) {
+    if (!c->copy_stream) CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < nchunks; ++i)
+        if (!c->chunk_done[i]) CK(cudaEventCreateWithFlags(&c->chunk_done[i], cudaEventDisableTiming));
+    return VB200_OK;
+}
+
 void fill_exp_table(double *t) {
     for (int j = 0; j < kExpTab; ++j) t[j] = std::exp2((double)j / kExpTab);
 }
@@ -412,6 +433,9 @@ void vb200_destroy(vb200_ctx *c) {
     c->sc_grid.release();
     if (c->small_exec) cudaGraphExecDestroy(c->small_exec);
     if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (cudaEvent_t e : c->chunk_done)
+        if (e) cudaEventDestroy(e);
     if (c->pin) cudaFreeHost(c->pin);
     if (c->d_small) cudaFree(c->d_small);
     if (c->d_small_theory) cudaFree(c->d_small_theory);
@@ -563,6 +587,7 @@ int vb200_set_option(vb200_ctx *c, const char *key, int64_t value) {
     DeviceGuard g(c->device);
     drop_small_graph(c);   // the captured small-call sequence bakes the kernel variant in
     if (!strcmp(key, "graph")) c->opt_graph = value ? 1 : 0;
+    else if (!strcmp(key, "chunks")) c->opt_chunks = (int)std::max<int64_t>(0, std::min<int64_t>(value, 16));
     else if (!strcmp(key, "fast_math")) c->opt_fast = value ? 1 : 0;
     else if (!strcmp(key, "nsplit")) c->opt_nsplit = (int)value;
     else if (!strcmp(key, "fuse")) c->opt_fuse = (int)std::max<int64_t>(0, std::min<int64_t>(value, 2));
@@ -642,12 +667,39 @@ static int theory_impl(vb200_ctx *c, const double *params, int64_t n, const doub
         if ((rc = c->sc_mult.ensure(nmult))) return rc;
         d_mult = c->sc_mult.ptr;
     }
-    if ((rc = launch_k1(c, d_params, n, d_s, ns, d_mu, d_sq, d_w, nmu, Lw, d_xi, d_mult, st, pairwise))) return rc;
-    if (xi_out && d_xi != xi_out)
-        CK(cudaMemcpyAsync(xi_out, d_xi, nxi * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (mult_out && d_mult != mult_out)
-        CK(cudaMemcpyAsync(mult_out, d_mult, nmult * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (host_io) CK(cudaStreamSynchronize(st));
+    const bool xi_to_host = xi_out && d_xi != xi_out, mult_to_host = mult_out && d_mult != mult_out;
+    const size_t sx = (size_t)nmu * ns, sm = (size_t)Lw * ns;   // doubles per row of each output
+    const int nchunks = plan_chunks(c, n, ((xi_to_host ? nxi : 0) + (mult_to_host ? nmult : 0)) * sizeof(double));
+    if (nchunks <= 1) {
+        if ((rc = launch_k1(c, d_params, n, d_s, ns, d_mu, d_sq, d_w, nmu, Lw, d_xi, d_mult, st, pairwise))) return rc;
+        if (xi_to_host) CK(cudaMemcpyAsync(xi_out, d_xi, nxi * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (mult_to_host) CK(cudaMemcpyAsync(mult_out, d_mult, nmult * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (host_io) CK(cudaStreamSynchronize(st));
+        return VB200_OK;
+    }
+    // all chunks are queued first; the (host-blocking, pageable) copies then trail the kernels chunk by chunk
+    if ((rc = ensure_copy_stream(c, nchunks))) return rc;
+    const int64_t per = (n + nchunks - 1) / nchunks;
+    for (int k = 0; k < nchunks; ++k) {
+        const int64_t lo = k * per, cnt = std::min<int64_t>(per, n - lo);
+        if (cnt <= 0) break;
+        if ((rc = launch_k1(c, d_params + lo * VB200_NPAR, cnt, d_s, ns, d_mu, d_sq, d_w, nmu, Lw,
+                            d_xi ? d_xi + lo * sx : nullptr, d_mult ? d_mult + lo * sm : nullptr, st, pairwise)))
+            return rc;
+        CK(cudaEventRecord(c->chunk_done[k], st));
+    }
+    for (int k = 0; k < nchunks; ++k) {
+        const int64_t lo = k * per, cnt = std::min<int64_t>(per, n - lo);
+        if (cnt <= 0) break;
+        CK(cudaStreamWaitEvent(c->copy_stream, c->chunk_done[k], 0));
+        if (xi_to_host)
+            CK(cudaMemcpyAsync(xi_out + lo * sx, d_xi + lo * sx, cnt * sx * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+        if (mult_to_host)
+            CK(cudaMemcpyAsync(mult_out + lo * sm, d_mult + lo * sm, cnt * sm * sizeof(double), cudaMemcpyDeviceToHost,
+                               c->copy_stream));
+    }
+    CK(cudaStreamSynchronize(c->copy_stream));
+    CK(cudaStreamSynchronize(st));
     return VB200_OK;
 }
 
@@ -737,16 +789,39 @@ int vb200_likelihood(vb200_ctx *c, const double *params, int64_t n, double *theo
         if ((rc = c->sc_lnl.ensure((size_t)n))) return rc;
         d_lnl = c->sc_lnl.ptr;
     }
-    bool fused = false;
-    if ((rc = launch_k1(c, d_params, n, c->fit_s, c->fit_ns, c->fit_mu, c->fit_sqmu, c->fit_wmu, c->fit_nmu,
-                        c->fit_L, nullptr, d_theory, st, false, d_chi2, d_lnl, &fused)))
-        return rc;
-    if ((chi2 || lnlike) && !fused) {
-        if (!d_theory) return fail(VB200_ECUDA, "internal: likelihood epilogue was expected to be fused");
-        if ((rc = launch_k2(c, d_params, d_theory, n, d_chi2, d_lnl, st))) return rc;
+    const bool theory_to_host = theory && d_theory != theory;
+    const int nchunks = theory_to_host ? plan_chunks(c, n, (size_t)n * p * sizeof(double)) : 1;
+    if (nchunks > 1 && (rc = ensure_copy_stream(c, nchunks))) return rc;
+    const int64_t per = (n + nchunks - 1) / nchunks;
+    for (int k = 0; k < nchunks; ++k) {
+        const int64_t lo = k * per, cnt = std::min<int64_t>(per, n - lo);
+        if (cnt <= 0) break;
+        bool fused = false;
+        if ((rc = launch_k1(c, d_params + lo * VB200_NPAR, cnt, c->fit_s, c->fit_ns, c->fit_mu, c->fit_sqmu, c->fit_wmu,
+                            c->fit_nmu, c->fit_L, nullptr, d_theory ? d_theory + lo * p : nullptr, st, false,
+                            d_chi2 ? d_chi2 + lo : nullptr, d_lnl ? d_lnl + lo : nullptr, &fused)))
+            return rc;
+        if ((chi2 || lnlike) && !fused) {
+            if (!d_theory) return fail(VB200_ECUDA, "internal: likelihood epilogue was expected to be fused");
+            if ((rc = launch_k2(c, d_params + lo * VB200_NPAR, d_theory + lo * p, cnt, d_chi2 ? d_chi2 + lo : nullptr,
+                                d_lnl ? d_lnl + lo : nullptr, st)))
+                return rc;
+        }
+        if (nchunks > 1) CK(cudaEventRecord(c->chunk_done[k], st));
     }
-    if (theory && d_theory != theory)
+    if (theory_to_host && nchunks > 1) {
+        // the copies (host-blocking for pageable memory) trail the kernels chunk by chunk on their own stream
+        for (int k = 0; k < nchunks; ++k) {
+            const int64_t lo = k * per, cnt = std::min<int64_t>(per, n - lo);
+            if (cnt <= 0) break;
+            CK(cudaStreamWaitEvent(c->copy_stream, c->chunk_done[k], 0));
+            CK(cudaMemcpyAsync(theory + lo * p, d_theory + lo * p, (size_t)cnt * p * sizeof(double), cudaMemcpyDeviceToHost,
+                               c->copy_stream));
+        }
+        CK(cudaStreamSynchronize(c->copy_stream));
+    } else if (theory_to_host) {
         CK(cudaMemcpyAsync(theory, d_theory, (size_t)n * p * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
     if (chi2 && d_chi2 != chi2) CK(cudaMemcpyAsync(chi2, d_chi2, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (lnlike && d_lnl != lnlike)
         CK(cudaMemcpyAsync(lnlike, d_lnl, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -20,6 +20,7 @@ piecewise-polynomial coefficient tables the device evaluates directly:
 * the log-determinant of the (linearly blended) covariance uses the generalised eigenvalues
   of (cov[hi], cov[lo]):  logdet((1-t) C_lo + t C_hi) = logdet C_lo + sum log1p(t (lam - 1)).
 """
+import functools
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -63,6 +64,14 @@ def mu_nodes(poles, nmu=100):
 
 
 def mu_projection_weights(poles, nmu=100, npts=200):
+    """(mu, W) -- see _mu_projection_weights; cached per (poles, nmu, npts): building the nmu unit splines takes
+    9 ms for 100 nodes, which would otherwise dominate every single-point theory_multipoles call."""
+    mu, W = _mu_projection_weights(tuple(int(p) for p in np.atleast_1d(poles)), int(nmu), int(npts))
+    return mu.copy(), W.copy()
+
+
+@functools.lru_cache(maxsize=64)
+def _mu_projection_weights(poles, nmu, npts):
     """Weights W[l, k] with  xi_l(s_j) = sum_k W[l, k] xi(s_j, mu_k).
 
     The reference builds ``interp2d(s, mu, xi, kind='cubic')`` and integrates it over 200 mu
