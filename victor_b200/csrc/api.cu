@@ -117,6 +117,7 @@ struct vb200_ctx {
     int opt_graph = 1;
     // host-bound bulk outputs (theory vectors, xi blocks): rows go in chunks, and each chunk's device-to-host copy
     // runs on `copy_stream` while later chunks compute
+    std::vector<double> grid_host;   // what sc_grid holds (s | mu | sqrt(1-mu^2) | wmu of the last vb200_theory call)
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_done[16] = {nullptr};
     int opt_chunks = 0;           // 0 = automatic, 1 = never split, k = force k chunks
@@ -639,9 +640,13 @@ static int theory_impl(vb200_ctx *c, const double *params, int64_t n, const doub
         std::copy(mu, mu + nmu, h.begin() + ns);
         for (int k = 0; k < nmu; ++k) h[(size_t)ns + nmu + k] = std::sqrt(1.0 - mu[k] * mu[k]);
         if (Lw) std::copy(wmu, wmu + (size_t)Lw * nmu, h.begin() + ns + 2 * (size_t)nmu);
-        // the copy is stream-ordered; the pageable source is consumed before the call returns
-        CK(cudaMemcpyAsync(c->sc_grid.ptr, h.data(), ng * sizeof(double), cudaMemcpyHostToDevice, st));
-        CK(cudaStreamSynchronize(st));
+        // repeated calls on the same grids (the usual case) find them on the device already
+        if (h.size() != c->grid_host.size() || memcmp(h.data(), c->grid_host.data(), ng * sizeof(double)) != 0) {
+            // the copy is stream-ordered; the pageable source is consumed before the call returns
+            CK(cudaMemcpyAsync(c->sc_grid.ptr, h.data(), ng * sizeof(double), cudaMemcpyHostToDevice, st));
+            CK(cudaStreamSynchronize(st));
+            c->grid_host.swap(h);
+        }
     }
     const double *d_s = c->sc_grid.ptr, *d_mu = d_s + ns, *d_sq = d_mu + nmu;
     const double *d_w = Lw ? d_sq + nmu : nullptr;
