@@ -312,9 +312,9 @@ int launch_k2(vb200_ctx *c, const double *d_params, const double *d_theory, long
         // few rows: a block per row, so that one row's matrix reads are spread over eight warps
         k_chi2_block<<<(unsigned)n, kK2Warps * 32, (size_t)fused_fit_doubles(c->fd.p) * sizeof(double), st>>>(a);
     } else {
-        const long long blocks = (n + kK2Warps - 1) / kK2Warps;
-        const size_t smem = (size_t)kK2Warps * c->fd.p * sizeof(double);
-        k_chi2<<<(unsigned)blocks, kK2Warps * 32, smem, st>>>(a);
+        const long long rows_per_block = (long long)kK2Warps * kK2RowsPerWarp;
+        const long long blocks = (n + rows_per_block - 1) / rows_per_block;
+        k_chi2<<<(unsigned)blocks, kK2Warps * 32, k2_smem_bytes(c->fd.p), st>>>(a);
     }
     CK(cudaGetLastError());
     c->launches++;
