@@ -4,11 +4,12 @@
 //   anisotropic real-space input                victor/ccf_model.py:684-687  (assume_isotropic: False)
 //   real-space ccf measured from data           victor/ccf_model.py:675-679  (realspace_ccf.from_data)
 //   sigma_v(r, mu) dispersion templates         victor/ccf_model.py:654-655, 667-668 (3 template keys)
-//   empirical correction of the mean velocity   victor/ccf_model.py:451-459  (velocity_pdf.mean.empirical_corr)
-// and the streaming model combined with the last two.  Same tiling as the tuned kernel (one block
-// per parameter row x s-range, one thread per (s_j, mu_k) pair, velocity nodes in registers), plain
-// the same hand-rolled rsqrt / reciprocal / exp as the tuned kernel (kFast) or CUDA libm (a test
-// variant: both must pass parity).  No instruction-level tuning beyond that.
+//   empirical correction of the mean velocity   victor/ccf_model.py:451-459  (with the dispersion / kaiser models;
+//                                               the streaming case runs on the tuned kernel)
+// and the streaming model combined with anisotropic, from-data or sigma_v(r, mu) input.  Same tiling as the
+// tuned kernel (one block per parameter row x s-range, one thread per (s_j, mu_k) pair, velocity nodes in
+// registers), the same hand-rolled rsqrt / reciprocal / exp (kFast) or CUDA libm (a test variant: both must
+// pass parity), the same branch-free cell search; two velocity nodes in flight per thread.
 #pragma once
 #include "common.cuh"
 #include "k2_chi2.cuh"
