@@ -110,6 +110,20 @@ def _oracle_eval(rows):
     return time.perf_counter() - t0, out
 
 
+def cpu_table_walk(fit, rows_host, chi2_gpu, nrows=8192):
+    """oracle/table_walk.c on all host cores over the first `nrows` rows of the batch (a few seconds)."""
+    from oracle.table_walk import TableWalk
+    tw = TableWalk(fit)
+    rows = rows_host[:nrows]
+    tw.likelihood(rows[:64])
+    t0 = time.perf_counter()
+    _, chi2, _ = tw.likelihood(rows)
+    wall = time.perf_counter() - t0
+    return {"value": len(rows) / wall, "unit": UNIT, "cores": os.cpu_count() or 1,
+            "sample": f"first {len(rows)} rows of the batch, plain C + OpenMP walk through the same tables, wall {wall:.2f}s",
+            "max_abs_chi2_difference_to_gpu": float(np.nanmax(np.abs(chi2 - chi2_gpu[:len(rows)])))}
+
+
 def cpu_oracle_throughput(rows_per_worker=160, repeats=1):
     """Oracle port on all host cores: evals / max worker time."""
     import multiprocessing as mp
@@ -342,6 +356,10 @@ def run_gpu(args):
             with open(prof) as fh:
                 roofline["traffic"] = json.load(fh).get("dram_bytes_per_launch")
         cpu = cpu_oracle_throughput() if (world == 1 and not args.no_cpu) else None
+        if cpu is not None:
+            # second CPU figure: the same table-driven algebra as the kernels, as plain C + OpenMP on the host cores
+            # (oracle/table_walk.c) -- also a row-by-row check of the sample against the GPU results
+            cpu["table_walk_c"] = cpu_table_walk(fit, rows_host, chi2_gpu=d_chi2.cpu().numpy())
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,

@@ -1,0 +1,84 @@
+"""The plain C table walk (oracle/table_walk.c, test infrastructure): held to golden outputs of the unmodified
+reference on the CPU, and used on the GPU box to recompute whole bench batches row by row."""
+import copy
+
+import numpy as np
+import pytest
+
+from oracle import table_walk as TW
+
+RTOL, ATOL, C2_ATOL = 1e-9, 1e-13, 1e-6
+
+
+@pytest.fixture(scope="module")
+def fit(boss_blocks):
+    from victor_b200 import CCFFit
+    TW.build()
+    return CCFFit(copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1]))
+
+
+def test_streaming_rows_match_the_reference(fit, golden):
+    from victor_b200.model import params_to_rows
+    g = golden("boss_streaming_points")
+    tw = TW.TableWalk(fit)
+    th, c2, ll = tw.likelihood(params_to_rows(g["params"]), want_theory=True)
+    np.testing.assert_allclose(th, g["theory"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(c2, g["chi2"], rtol=0, atol=C2_ATOL)
+    np.testing.assert_allclose(ll, g["lnl"], rtol=0, atol=C2_ATOL)
+    assert np.abs(th - g["theory"]).max() < 1e-13 and np.nanmax(np.abs(c2 - g["chi2"])) < 1e-9   # measured: 1e-15, 6e-12
+
+
+def test_xi_and_options_match_the_reference(fit, golden, boss_blocks):
+    from victor_b200 import CCFFit, tables as T
+    from victor_b200.model import params_to_rows
+    e = golden("boss_epsilon_points")
+    tw = TW.TableWalk(fit)
+    rows = params_to_rows({"fsigma8": e["params"][:, 0], "beta": e["params"][:, 1], "sigma_v": e["params"][:, 2],
+                           "epsilon": e["params"][:, 3], "alpha": e["params"][:, 4]})
+    xi, _ = tw.theory(rows, np.asarray(fit.s, float), e["mu"])
+    np.testing.assert_allclose(xi, e["xi_smu"], rtol=RTOL, atol=ATOL)
+    # anisotropic real-space input (three-term Legendre sum), likelihood forms
+    v = golden("boss_variant_points")
+    th, c2, ll = TW.TableWalk(fit, options={"assume_isotropic": False}).likelihood(params_to_rows(v["params"]), True)
+    np.testing.assert_allclose(th, v["anisotropic_theory"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(c2, v["anisotropic_chi2"], rtol=0, atol=C2_ATOL)
+    f = golden("boss_forms")
+    for form in ("gaussian", "hartlap", "percival"):
+        like = {"form": form, "nmocks": 1000, "nparams": 4}
+        _, c2, ll = TW.TableWalk(fit, likelihood=like).likelihood(params_to_rows(f["params"]))
+        np.testing.assert_allclose(ll, f[f"{form}_lnl"], rtol=0, atol=C2_ATOL)
+    # empirical velocity correction, velocity template, linear_bias with a bias among the parameters
+    o = golden("boss_velocity_options")
+    rows = params_to_rows(o["params"])
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["velocity_pdf"]["mean"]["empirical_corr"] = True
+    r2 = rows.copy()
+    r2[:, 8] = o["Av"]
+    _, c2, _ = TW.TableWalk(CCFFit(model, data)).likelihood(r2)
+    np.testing.assert_allclose(c2, o["emp_streaming_chi2"], rtol=0, atol=C2_ATOL)
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["matter_ccf"]["model"] = "linear_bias"
+    r2 = rows.copy()
+    r2[:, 9] = o["bias"]
+    _, c2, _ = TW.TableWalk(CCFFit(model, data)).likelihood(r2)
+    np.testing.assert_allclose(c2, o["rowbias_streaming_chi2"], rtol=0, atol=C2_ATOL)
+    with pytest.raises(NotImplementedError):
+        TW.TableWalk(fit, options={"rsd_model": "dispersion"}).likelihood(rows)
+    assert T.NPAR == 10
+
+
+@pytest.mark.gpu
+def test_whole_bench_batch_against_the_c_table_walk(fit):
+    """A quarter of the BASELINE batch (the first 16 384 of the 65 536 seeded rows), every row recomputed on the
+    CPU by the C table walk: multipoles to 1e-9 relative, chi-square and lnL to 1e-6 absolute, row by row."""
+    from bench import synthetic_batch
+    from victor_b200.model import params_to_rows
+    rows = params_to_rows(synthetic_batch(65536)[:16384])
+    lnl, chi2, th = fit.log_likelihood_batch(rows, return_theory=True)
+    wth, wc2, wll = TW.TableWalk(fit).likelihood(rows, want_theory=True)
+    np.testing.assert_allclose(th, wth, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(chi2, wc2, rtol=0, atol=C2_ATOL)
+    np.testing.assert_allclose(lnl, wll, rtol=0, atol=C2_ATOL)
+    scale = np.abs(wth).reshape(len(rows), 2, -1).max(axis=2)
+    err = np.abs(th - wth).reshape(len(rows), 2, -1).max(axis=2)
+    assert np.all(err <= RTOL * scale)
