@@ -1,5 +1,5 @@
 /*
- * TEST INFRASTRUCTURE ONLY - plain C walk through the packed tables, streaming model + likelihood.
+ * TEST INFRASTRUCTURE ONLY - plain C walk through the packed tables: all four rsd models + likelihood.
  *
  * The same table-driven algebra the CUDA kernels run (reference lines below are
  * victor/ccf_model.py and victor/ccf_fit.py), written as straightforward scalar C with libm sqrt / exp /
@@ -10,9 +10,9 @@
  * cpu_baseline leg do).  It is itself held to the scipy oracle and to the goldens of the unmodified
  * reference by tests/test_table_walk.py.
  *
- * Scope: rsd_model 'streaming' with up to three real-space multipoles, isotropic sigma_v(r) template,
- * template coordinates (no from_data), every growth mode, the empirical velocity correction, and the
- * chi-square / log-likelihood with all forms.  Anything else returns -4.
+ * Scope: rsd_model 'streaming', 'dispersion', 'kaiser' and 'euclid_special' with up to three real-space
+ * multipoles, isotropic sigma_v(r) template, template coordinates (no from_data), every growth mode, the
+ * empirical velocity correction, and the chi-square / log-likelihood with all forms.  Anything else returns -4.
  *
  *   gcc -O2 -fopenmp -shared -fPIC -o oracle/_build/libtable_walk.so oracle/table_walk.c -lm
  */
@@ -89,7 +89,8 @@ static void row_xi(const vb200_model_tables *m, const double *pr, const double *
         kb = beta_interval(m->beta_grid, m->nbeta, beta);
         tb = beta - m->beta_grid[kb];
     }
-    double *xi_c = cells, *v0_c = cells + 3 * (size_t)per;
+    double *xi_c = cells, *v0_c = cells + 3 * (size_t)per, *d0_c = cells + 4 * (size_t)per;
+    const double G = iaHt * Av / f, Mk = pr[6], Qk = pr[7];
     const size_t ell_stride = (size_t)(m->nbeta - 1) * 4 * per;
     for (int l = 0; l < m->n_ell; ++l) {
         const double *tab = m->xi_tab + l * ell_stride + (size_t)kb * 4 * per;
@@ -107,35 +108,104 @@ static void row_xi(const vb200_model_tables *m, const double *pr, const double *
             v = m->v0[i];
         }
         v0_c[i] = v;
+        double d;
+        if (m->vd_beta_dependent) {
+            const double *td = m->d0 + (size_t)kb * 4 * per;
+            d = ((td[3 * per + i] * tb + td[2 * per + i]) * tb + td[per + i]) * tb + td[i];
+        } else if (m->d0b) {
+            d = m->d0[i] + Ae * m->d0b[i]; /* :456-459 */
+        } else {
+            d = m->d0[i];
+        }
+        d0_c[i] = d;
     }
 
     for (int k = 0; k < nmu; ++k) {
         const double sq = sqrt(1.0 - mu[k] * mu[k]);
         for (int j = 0; j < ns; ++j) {
             const double Sperp = s[j] * sq * (aperp / f), Spar = s[j] * mu[k] * (apar / f); /* :642-643 */
-            double acc = 0.0;
-            for (int mi = 0; mi < m->nx; ++mi) {
-                const double xm = m->x[mi];
-                const double rp = Spar - xm * kappa;                 /* :648 */
-                const double u = sqrt(Sperp * Sperp + rp * rp);       /* :651 */
-                const double mur = rp / u;                            /* :652 */
-                double t;
-                const int cell = find_cell(m, u, &t);
-                const double sv = cubic(m->sv + 4 * (size_t)cell, t); /* :654-655 */
-                const double z = (xm - B * cubic(v0_c + 4 * (size_t)cell, t) * mur) / sv; /* :656 */
-                double xir = cubic(xi_c + 4 * (size_t)cell, t);       /* :683-687 */
-                for (int l = 1; l < m->n_ell; ++l)
-                    xir += cubic(xi_c + (size_t)l * per + 4 * (size_t)cell, t) * legendre_even(m->ells[l], mur);
-                acc += m->wx[mi] * (1.0 + xir) * exp(-0.5 * z * z) / sv; /* :690 */
+            const double Sp2 = Sperp * Sperp;
+            double acc = 0.0, result;
+#define XI_REAL(cell_, t_, mur_, out_)                                                                       \
+    do {                                                                                                       \
+        (out_) = cubic(xi_c + 4 * (size_t)(cell_), (t_)); /* :683-687 */                                       \
+        for (int l_ = 1; l_ < m->n_ell; ++l_)                                                                  \
+            (out_) += cubic(xi_c + (size_t)l_ * per + 4 * (size_t)(cell_), (t_)) * legendre_even(m->ells[l_], (mur_)); \
+    } while (0)
+            if (m->rsd_model == VB200_RSD_STREAMING) {
+                for (int mi = 0; mi < m->nx; ++mi) {
+                    const double xm = m->x[mi];
+                    const double rp = Spar - xm * kappa;              /* :648 */
+                    const double u = sqrt(Sp2 + rp * rp);              /* :651 */
+                    const double mur = rp / u;                         /* :652 */
+                    double t, xir;
+                    const int cell = find_cell(m, u, &t);
+                    const double sv = cubic(m->sv + 4 * (size_t)cell, t); /* :654-655 */
+                    const double z = (xm - B * cubic(v0_c + 4 * (size_t)cell, t) * mur) / sv; /* :656 */
+                    XI_REAL(cell, t, mur, xir);
+                    acc += m->wx[mi] * (1.0 + xir) * exp(-0.5 * z * z) / sv; /* :690 */
+                }
+                result = acc - 1.0;
+            } else if (m->rsd_model == VB200_RSD_DISPERSION) {       /* :659-671 */
+                const double Strue = sqrt(Sp2 + Spar * Spar);
+                double t0;
+                const int c0 = find_cell(m, Strue, &t0);
+                const double first = 1.0 + G * cubic(v0_c + 4 * (size_t)c0, t0) / Strue;
+                for (int mi = 0; mi < m->nx; ++mi) {
+                    const double xm = m->x[mi], num = Spar - xm * kappa;
+                    double rp = num / first, u, t;
+                    int cell;
+                    for (int it = 0; it < m->niter; ++it) {
+                        u = sqrt(Sp2 + rp * rp);
+                        cell = find_cell(m, u, &t);
+                        rp = num / (1.0 + G * cubic(v0_c + 4 * (size_t)cell, t) / u);
+                    }
+                    u = sqrt(Sp2 + rp * rp);
+                    const double mur = rp / u;
+                    cell = find_cell(m, u, &t);
+                    const double sv = cubic(m->sv + 4 * (size_t)cell, t);
+                    const double v0u = cubic(v0_c + 4 * (size_t)cell, t) / u;
+                    const double jd = 1.0 + G * v0u + G * mur * mur * (cubic(d0_c + 4 * (size_t)cell, t) - v0u);
+                    const double z = xm / sv;
+                    double xir;
+                    XI_REAL(cell, t, mur, xir);
+                    acc += m->wx[mi] * (1.0 + xir) * (1.0 / jd) * exp(-0.5 * z * z) / sv;
+                }
+                result = acc - 1.0;
+            } else {                                                    /* kaiser / euclid_special :692-741 */
+                const double MG = Mk * G;
+                double rp = Spar, u, t;
+                int cell;
+                if (m->kaiser_coord_shift) {
+                    const double Strue = sqrt(Sp2 + Spar * Spar);
+                    cell = find_cell(m, Strue, &t);
+                    rp = Spar / (1.0 + MG * cubic(v0_c + 4 * (size_t)cell, t) / Strue);
+                    for (int it = 0; it < m->niter; ++it) {
+                        u = sqrt(Sp2 + rp * rp);
+                        cell = find_cell(m, u, &t);
+                        rp = Spar / (1.0 + MG * cubic(v0_c + 4 * (size_t)cell, t) / u);
+                    }
+                }
+                u = sqrt(Sp2 + rp * rp);
+                const double mur = rp / u;
+                cell = find_cell(m, u, &t);
+                const double v0u = cubic(v0_c + 4 * (size_t)cell, t) / u;
+                const int euclid = m->rsd_model == VB200_RSD_EUCLID;
+                const double J = (euclid ? 3.0 : 1.0) * MG * v0u +
+                                 (euclid ? 2.0 : 1.0) * MG * Qk * mur * mur * (cubic(d0_c + 4 * (size_t)cell, t) - v0u);
+                double xir;
+                XI_REAL(cell, t, mur, xir);
+                result = (euclid || m->kaiser_approximation) ? Mk * xir - J : (1.0 + Mk * xir) / (1.0 + J) - 1.0;
             }
-            xi[(size_t)k * ns + j] = acc - 1.0;
+#undef XI_REAL
+            xi[(size_t)k * ns + j] = result;
         }
     }
 }
 
 static int supported(const vb200_model_tables *m) {
-    return m->rsd_model == VB200_RSD_STREAMING && !m->realspace_from_data && m->sv_ny == 0 && m->n_ell >= 1 &&
-           m->n_ell <= VB200_MAX_POLES;
+    return m->rsd_model >= VB200_RSD_STREAMING && m->rsd_model <= VB200_RSD_EUCLID && !m->realspace_from_data &&
+           m->sv_ny == 0 && m->n_ell >= 1 && m->n_ell <= VB200_MAX_POLES;
 }
 
 /* multipoles [n][L][ns] and / or xi [n][nmu][ns] on caller-supplied grids */

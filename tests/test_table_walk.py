@@ -62,9 +62,38 @@ def test_xi_and_options_match_the_reference(fit, golden, boss_blocks):
     r2[:, 9] = o["bias"]
     _, c2, _ = TW.TableWalk(CCFFit(model, data)).likelihood(r2)
     np.testing.assert_allclose(c2, o["rowbias_streaming_chi2"], rtol=0, atol=C2_ATOL)
-    with pytest.raises(NotImplementedError):
-        TW.TableWalk(fit, options={"rsd_model": "dispersion"}).likelihood(rows)
     assert T.NPAR == 10
+
+
+def test_other_rsd_models_match_the_reference(fit, golden, boss_blocks):
+    """dispersion, kaiser (+ M, Q, no coordinate shift, linear approximation), euclid_special, with isotropic and
+    anisotropic real-space input; from-data coordinates are outside the C walk."""
+    from victor_b200 import CCFFit
+    from victor_b200.model import params_to_rows
+    v = golden("boss_variant_points")
+    rows = params_to_rows(v["params"])
+    for name, kw in (("dispersion", {"rsd_model": "dispersion"}), ("kaiser", {"rsd_model": "kaiser"})):
+        th, c2, ll = TW.TableWalk(fit, options=kw).likelihood(rows, want_theory=True)
+        np.testing.assert_allclose(th, v[f"{name}_theory"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(c2, v[f"{name}_chi2"], rtol=0, atol=C2_ATOL)
+        np.testing.assert_allclose(ll, v[f"{name}_lnl"], rtol=0, atol=C2_ATOL)
+    mv = golden("boss_more_variants")
+    rows = params_to_rows(mv["params"])
+    rows[:, 6:8] = mv["MQ"]
+    for name, kw in (("euclid", {"rsd_model": "euclid_special"}),
+                     ("kaiser_noshift", {"rsd_model": "kaiser", "kaiser_coord_shift": False}),
+                     ("kaiser_approx", {"rsd_model": "kaiser", "kaiser_approximation": True}),
+                     ("kaiser_mq", {"rsd_model": "kaiser"}),
+                     ("aniso_dispersion", {"rsd_model": "dispersion", "assume_isotropic": False})):
+        th, c2, _ = TW.TableWalk(fit, options=kw).likelihood(rows, want_theory=True)
+        np.testing.assert_allclose(th, mv[f"{name}_theory"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(c2, mv[f"{name}_chi2"], rtol=0, atol=C2_ATOL)
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["input_model_data_file"] = "data/boss_dr12_cmass/cmass_measured_model.npz"
+    model["realspace_ccf"]["from_data"] = True
+    data["covariance_matrix"]["data_file"] = "data/boss_dr12_cmass/cmass_variable_isotropic_MD_covariance.npz"
+    with pytest.raises(NotImplementedError):
+        TW.TableWalk(CCFFit(model, data)).likelihood(rows)
 
 
 @pytest.mark.gpu
@@ -82,3 +111,21 @@ def test_whole_bench_batch_against_the_c_table_walk(fit):
     scale = np.abs(wth).reshape(len(rows), 2, -1).max(axis=2)
     err = np.abs(th - wth).reshape(len(rows), 2, -1).max(axis=2)
     assert np.all(err <= RTOL * scale)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw,n", [({"rsd_model": "dispersion"}, 4096), ({"assume_isotropic": False}, 8192),
+                                  ({"rsd_model": "kaiser"}, 16384), ({"rsd_model": "euclid_special"}, 16384)])
+def test_general_kernel_batches_against_the_c_table_walk(fit, kw, n):
+    """The general kernel, thousands of seeded rows per model, every row recomputed by the C table walk."""
+    from bench import synthetic_batch
+    from victor_b200.model import params_to_rows
+    rows = params_to_rows(synthetic_batch(65536)[:n])
+    rng = np.random.default_rng(8)
+    rows[:, 6] = rng.uniform(0.8, 1.2, n)          # M, Q (kaiser forms)
+    rows[:, 7] = rng.uniform(0.8, 1.2, n)
+    lnl, chi2, th = fit.log_likelihood_batch(rows, return_theory=True, **kw)
+    wth, wc2, wll = TW.TableWalk(fit, options=kw).likelihood(rows, want_theory=True)
+    np.testing.assert_allclose(th, wth, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(chi2, wc2, rtol=0, atol=C2_ATOL)
+    np.testing.assert_allclose(lnl, wll, rtol=0, atol=C2_ATOL)
