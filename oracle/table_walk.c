@@ -10,9 +10,9 @@
  * cpu_baseline leg do).  It is itself held to the scipy oracle and to the goldens of the unmodified
  * reference by tests/test_table_walk.py.
  *
- * Scope: rsd_model 'streaming', 'dispersion', 'kaiser' and 'euclid_special' with up to three real-space
- * multipoles, isotropic sigma_v(r) template, template coordinates (no from_data), every growth mode, the
- * empirical velocity correction, and the chi-square / log-likelihood with all forms.  Anything else returns -4.
+ * Scope: everything the kernels cover -- rsd_model 'streaming', 'dispersion', 'kaiser' and 'euclid_special', up
+ * to three real-space multipoles, sigma_v(r) and sigma_v(r, mu) templates, template or from-data coordinates,
+ * every growth mode, the empirical velocity correction, and the chi-square / log-likelihood with all forms.
  *
  *   gcc -O2 -fopenmp -shared -fPIC -o oracle/_build/libtable_walk.so oracle/table_walk.c -lm
  */
@@ -44,6 +44,23 @@ static int beta_interval(const double *grid, int n, double b) {
     int k = 0;
     for (int i = 1; i < n - 1; ++i) k += (b >= grid[i]) ? 1 : 0;
     return k;
+}
+
+/* normalised dispersion template: the 1-D cubic, or the bicubic patch of a sigma_v(r, mu) template with mu
+ * clamped to the template's range (RectBivariateSpline.ev -> bispeu clamps its arguments), :654-655 */
+static double sv_at(const vb200_model_tables *m, int cell, double t, double mur) {
+    if (m->sv_ny == 0) return cubic(m->sv + 4 * (size_t)cell, t);
+    const double *yb = m->sv_ybreaks;
+    double mc = mur;
+    if (mc < yb[0]) mc = yb[0];
+    if (mc > yb[m->sv_ny]) mc = yb[m->sv_ny];
+    int yc = 0;
+    for (int i = 1; i < m->sv_ny; ++i) yc += (mc >= yb[i]) ? 1 : 0;
+    const double w = mc - yb[yc];
+    const double *T = m->sv2d + ((size_t)cell * m->sv_ny + yc) * 16;
+    double py[4];
+    for (int q = 0; q < 4; ++q) py[q] = cubic(T + 4 * q, w);
+    return cubic(py, t);
 }
 
 static double legendre_even(int ell, double x) {
@@ -126,11 +143,20 @@ static void row_xi(const vb200_model_tables *m, const double *pr, const double *
             const double Sperp = s[j] * sq * (aperp / f), Spar = s[j] * mu[k] * (apar / f); /* :642-643 */
             const double Sp2 = Sperp * Sperp;
             double acc = 0.0, result;
-#define XI_REAL(cell_, t_, mur_, out_)                                                                       \
+            const double rt_data = s[j] * sq; /* s_perp / aperp in the fiducial cosmology, :676 */
+#define XI_REAL(cell_, t_, mur_, rp_, out_)                                                                  \
     do {                                                                                                       \
-        (out_) = cubic(xi_c + 4 * (size_t)(cell_), (t_)); /* :683-687 */                                       \
+        int c__ = (cell_);                                                                                     \
+        double t__ = (t_), m__ = (mur_);                                                                       \
+        if (m->realspace_from_data) { /* :675-679: back to fiducial coordinates */                             \
+            const double rpd__ = (rp_) * f / apar;                                                             \
+            const double rd__ = sqrt(rpd__ * rpd__ + rt_data * rt_data);                                       \
+            c__ = find_cell(m, rd__, &t__);                                                                    \
+            m__ = rpd__ / rd__;                                                                                \
+        }                                                                                                      \
+        (out_) = cubic(xi_c + 4 * (size_t)c__, t__); /* :683-687 */                                            \
         for (int l_ = 1; l_ < m->n_ell; ++l_)                                                                  \
-            (out_) += cubic(xi_c + (size_t)l_ * per + 4 * (size_t)(cell_), (t_)) * legendre_even(m->ells[l_], (mur_)); \
+            (out_) += cubic(xi_c + (size_t)l_ * per + 4 * (size_t)c__, t__) * legendre_even(m->ells[l_], m__); \
     } while (0)
             if (m->rsd_model == VB200_RSD_STREAMING) {
                 for (int mi = 0; mi < m->nx; ++mi) {
@@ -140,9 +166,9 @@ static void row_xi(const vb200_model_tables *m, const double *pr, const double *
                     const double mur = rp / u;                         /* :652 */
                     double t, xir;
                     const int cell = find_cell(m, u, &t);
-                    const double sv = cubic(m->sv + 4 * (size_t)cell, t); /* :654-655 */
+                    const double sv = sv_at(m, cell, t, mur);             /* :654-655 */
                     const double z = (xm - B * cubic(v0_c + 4 * (size_t)cell, t) * mur) / sv; /* :656 */
-                    XI_REAL(cell, t, mur, xir);
+                    XI_REAL(cell, t, mur, rp, xir);
                     acc += m->wx[mi] * (1.0 + xir) * exp(-0.5 * z * z) / sv; /* :690 */
                 }
                 result = acc - 1.0;
@@ -163,12 +189,12 @@ static void row_xi(const vb200_model_tables *m, const double *pr, const double *
                     u = sqrt(Sp2 + rp * rp);
                     const double mur = rp / u;
                     cell = find_cell(m, u, &t);
-                    const double sv = cubic(m->sv + 4 * (size_t)cell, t);
+                    const double sv = sv_at(m, cell, t, mur);
                     const double v0u = cubic(v0_c + 4 * (size_t)cell, t) / u;
                     const double jd = 1.0 + G * v0u + G * mur * mur * (cubic(d0_c + 4 * (size_t)cell, t) - v0u);
                     const double z = xm / sv;
                     double xir;
-                    XI_REAL(cell, t, mur, xir);
+                    XI_REAL(cell, t, mur, rp, xir);
                     acc += m->wx[mi] * (1.0 + xir) * (1.0 / jd) * exp(-0.5 * z * z) / sv;
                 }
                 result = acc - 1.0;
@@ -194,7 +220,7 @@ static void row_xi(const vb200_model_tables *m, const double *pr, const double *
                 const double J = (euclid ? 3.0 : 1.0) * MG * v0u +
                                  (euclid ? 2.0 : 1.0) * MG * Qk * mur * mur * (cubic(d0_c + 4 * (size_t)cell, t) - v0u);
                 double xir;
-                XI_REAL(cell, t, mur, xir);
+                XI_REAL(cell, t, mur, rp, xir);
                 result = (euclid || m->kaiser_approximation) ? Mk * xir - J : (1.0 + Mk * xir) / (1.0 + J) - 1.0;
             }
 #undef XI_REAL
@@ -204,8 +230,8 @@ static void row_xi(const vb200_model_tables *m, const double *pr, const double *
 }
 
 static int supported(const vb200_model_tables *m) {
-    return m->rsd_model >= VB200_RSD_STREAMING && m->rsd_model <= VB200_RSD_EUCLID && !m->realspace_from_data &&
-           m->sv_ny == 0 && m->n_ell >= 1 && m->n_ell <= VB200_MAX_POLES;
+    return m->rsd_model >= VB200_RSD_STREAMING && m->rsd_model <= VB200_RSD_EUCLID && m->n_ell >= 1 &&
+           m->n_ell <= VB200_MAX_POLES && m->sv_ny >= 0;
 }
 
 /* multipoles [n][L][ns] and / or xi [n][nmu][ns] on caller-supplied grids */

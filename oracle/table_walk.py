@@ -65,7 +65,7 @@ class TableWalk:
     @staticmethod
     def _check(rc):
         if rc == -4:
-            raise NotImplementedError("table_walk.c covers template coordinates with an isotropic dispersion template")
+            raise NotImplementedError("table_walk.c: unsupported table set")
         if rc != 0:
             raise RuntimeError(f"table walk failed ({rc})")
 

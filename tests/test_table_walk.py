@@ -10,6 +10,22 @@ from oracle import table_walk as TW
 RTOL, ATOL, C2_ATOL = 1e-9, 1e-13, 1e-6
 
 
+def measured_blocks(boss_blocks):
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["input_model_data_file"] = "data/boss_dr12_cmass/cmass_measured_model.npz"
+    model["realspace_ccf"]["from_data"] = True
+    model["realspace_ccf"]["assume_isotropic"] = False
+    data["covariance_matrix"]["data_file"] = "data/boss_dr12_cmass/cmass_variable_anisotropic_MD_covariance.npz"
+    return model, data
+
+
+def sv2d_blocks(boss_blocks):
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    model["input_model_data_file"] = "tests/golden/model_sv2d_inputs.npz"
+    model["velocity_pdf"]["dispersion"]["template_keys"] = ["rsv", "musv", "sigmav2d"]
+    return model, data
+
+
 @pytest.fixture(scope="module")
 def fit(boss_blocks):
     from victor_b200 import CCFFit
@@ -67,7 +83,7 @@ def test_xi_and_options_match_the_reference(fit, golden, boss_blocks):
 
 def test_other_rsd_models_match_the_reference(fit, golden, boss_blocks):
     """dispersion, kaiser (+ M, Q, no coordinate shift, linear approximation), euclid_special, with isotropic and
-    anisotropic real-space input; from-data coordinates are outside the C walk."""
+    anisotropic real-space input, from-data coordinates, a sigma_v(r, mu) template."""
     from victor_b200 import CCFFit
     from victor_b200.model import params_to_rows
     v = golden("boss_variant_points")
@@ -88,12 +104,19 @@ def test_other_rsd_models_match_the_reference(fit, golden, boss_blocks):
         th, c2, _ = TW.TableWalk(fit, options=kw).likelihood(rows, want_theory=True)
         np.testing.assert_allclose(th, mv[f"{name}_theory"], rtol=RTOL, atol=ATOL)
         np.testing.assert_allclose(c2, mv[f"{name}_chi2"], rtol=0, atol=C2_ATOL)
-    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
-    model["input_model_data_file"] = "data/boss_dr12_cmass/cmass_measured_model.npz"
-    model["realspace_ccf"]["from_data"] = True
-    data["covariance_matrix"]["data_file"] = "data/boss_dr12_cmass/cmass_variable_isotropic_MD_covariance.npz"
-    with pytest.raises(NotImplementedError):
-        TW.TableWalk(CCFFit(model, data)).likelihood(rows)
+    # from-data coordinates (measured model + MD covariance) and a sigma_v(r, mu) template
+    fm = CCFFit(*measured_blocks(boss_blocks))
+    rows = params_to_rows(mv["measured_params"])
+    for name, kw in (("measured_aniso", {}), ("measured_aniso_dispersion", {"rsd_model": "dispersion"})):
+        th, c2, _ = TW.TableWalk(fm, options=kw).likelihood(rows, want_theory=True)
+        np.testing.assert_allclose(th, mv[f"{name}_theory"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(c2, mv[f"{name}_chi2"], rtol=0, atol=C2_ATOL)
+    sv = golden("boss_sv2d")
+    fs = CCFFit(*sv2d_blocks(boss_blocks))
+    for name, kw in (("streaming", {}), ("dispersion", {"rsd_model": "dispersion"})):
+        th, c2, _ = TW.TableWalk(fs, options=kw).likelihood(params_to_rows(sv["params"]), want_theory=True)
+        np.testing.assert_allclose(th, sv[f"{name}_theory"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(c2, sv[f"{name}_chi2"], rtol=0, atol=C2_ATOL)
 
 
 @pytest.mark.gpu
@@ -129,3 +152,24 @@ def test_general_kernel_batches_against_the_c_table_walk(fit, kw, n):
     np.testing.assert_allclose(th, wth, rtol=RTOL, atol=ATOL)
     np.testing.assert_allclose(chi2, wc2, rtol=0, atol=C2_ATOL)
     np.testing.assert_allclose(lnl, wll, rtol=0, atol=C2_ATOL)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which,kw,n", [("measured", {}, 4096), ("measured", {"rsd_model": "dispersion"}, 2048),
+                                        ("sv2d", {}, 4096), ("sv2d", {"rsd_model": "dispersion"}, 2048)])
+def test_from_data_and_sv2d_batches_against_the_c_table_walk(boss_blocks, which, kw, n):
+    """From-data coordinates (measured model, anisotropic, MD covariance) and a sigma_v(r, mu) template: thousands
+    of seeded rows, every row recomputed by the C table walk."""
+    from bench import synthetic_batch
+    from victor_b200 import CCFFit
+    from victor_b200.model import params_to_rows
+    fm = CCFFit(*(measured_blocks(boss_blocks) if which == "measured" else sv2d_blocks(boss_blocks)))
+    rows = params_to_rows(synthetic_batch(65536)[:n])
+    if which == "measured":
+        rows[:, 1] = np.clip(rows[:, 1], 0.25, 0.55)     # the measured model's beta grid is narrower
+    lnl, chi2, th = fm.log_likelihood_batch(rows, return_theory=True, **kw)
+    wth, wc2, wll = TW.TableWalk(fm, options=kw).likelihood(rows, want_theory=True)
+    np.testing.assert_allclose(th, wth, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(chi2, wc2, rtol=0, atol=C2_ATOL)
+    np.testing.assert_allclose(lnl, wll, rtol=0, atol=C2_ATOL)
+    fm.close()
