@@ -2,7 +2,6 @@
 """GPU: measured parity margins of the tuned kernel variants against the golden rows of the
 unmodified reference (tests/golden/boss_streaming_points.npz): multipoles inf-norm-relative and
 elementwise, chi2 / lnL absolute.  Prints one JSON line per variant."""
-import copy
 import json
 import os
 import sys

@@ -10,7 +10,6 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from . import tables as _tables
 
 
 def default_device():
