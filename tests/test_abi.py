@@ -88,3 +88,19 @@ def test_product_never_imports_the_oracle(repo_root):
                     text = fh.read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), fn
                 assert "ccf_oracle" not in text and "table_emul" not in text, fn
+
+
+def test_package_surface_mirrors_the_reference():
+    """Names exported by victor/__init__.py that lie on or next to the path (plotting and the excursion-set profile
+    are outside it)."""
+    import numpy as np
+    import victor_b200
+    for name in ("CCFModel", "CCFFit", "BackgroundCosmology", "InputError", "utils", "__version__"):
+        assert hasattr(victor_b200, name), name
+    for name in ("InputError", "multipoles_from_fn", "fn_from_multipoles"):
+        assert hasattr(victor_b200.utils, name), name
+    from conftest import load_golden
+    iaH = float(load_golden("boss_tables")["iaH"])
+    cosmo = victor_b200.BackgroundCosmology({"Omega_m": 0.31})
+    assert abs((1 + 0.57) / (100 * cosmo.Ez(0.57)) - iaH) < 1e-16       # ccf_model.py:44-45
+    assert abs(cosmo.Om(0.0) - 0.31) < 1e-15 and np.allclose(cosmo.H([0.0, 0.57]), [67.5, 67.5 * cosmo.Ez(0.57)])
