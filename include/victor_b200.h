@@ -176,25 +176,6 @@ int vb200_synchronize(vb200_ctx *ctx);
 /* Kernel launches issued by this context so far (for bench.py's gpu_launches). */
 int64_t vb200_launch_count(const vb200_ctx *ctx);
 
-/* Device self-test of the hand-rolled math for n HOST inputs x > 0; out has 4n entries:
- * out[0..n) = exp(-x/2) (degree-6 remainder polynomial), out[n..2n) = 1/sqrt(x),
- * out[2n..3n) = 1/x, out[3n..4n) = exp(-x/2) (degree-5 economised polynomial). */
-int vb200_math_selftest(int device, const double *x, int64_t n, double *out);
-
-/* Measurement hooks used while tuning (tools/probe_pipes.py): time of a kernel issuing only
- * DFMA (mode 0), only one kind of FP64 conversion (1, 3, 5) or both interleaved (2, 4, 6);
- * and the raw MUFU seeds rsqrt.approx / rcp.approx for n HOST inputs (out has 2n entries). */
-int vb200_pipe_probe(int device, int mode, int iters, double *ms);
-int vb200_seed_probe(int device, const double *x, int64_t n, double *out);
-/* DFMA issue-model probe: `chains` dependent FMA chains per thread, `mix` other instructions
- * (kind 0 integer, 1 shared-memory load; kind 2 = DMUL-with-constant-operand chains) after every
- * DFMA, `blocks_per_sm` blocks of 128 threads (= warps per SM sub-partition). */
-int vb200_mix_probe(int device, int chains, int mix, int kind, int blocks_per_sm, int iters, double *ms);
-
-/* FP64 FMA issue-rate probe (8 independent DFMA chains per thread, whole GPU): the measured
- * roofline denominator for this FP64-CUDA-core-bound path.  tflops counts 2 flop per FMA. */
-int vb200_fp64_peak(int device, int iters, double *tflops, double *ms);
-
 #ifdef __cplusplus
 }
 #endif

@@ -636,10 +636,68 @@ def golden_example(victor):
     np.savez(os.path.join(OUT, "example_points.npz"), **out, **meta())
 
 
+def golden_example_fit(victor):
+    """BASELINE.json configs[0], fit half: chi-square and lnL of the example void model against a data vector
+    and covariance.  The reference ships NO data or covariance file for its example configuration
+    (config/example_model_input.yaml has a model block only), so the INPUTS here are builder-made and flagged
+    ``non_reference_inputs`` in the fixture: a seeded synthetic data vector (the reference's own theory at a
+    fiducial point plus Gaussian noise) and a synthetic positive-definite covariance, written as .npy dict files
+    -- a format the unmodified reference reads itself.  The OUTPUTS are the unmodified reference's
+    CCFFit.chi_squared / log_likelihood on those inputs (ccf_fit.py:325-354, 356-483: fixed data vector, fixed
+    covariance, so no log-det term)."""
+    import tempfile
+    with open(os.path.join(REF, "config/example_model_input.yaml")) as fh:
+        model = yaml.full_load(fh)["model"]
+    model["dir"] = REF
+    base = victor.CCFModel(copy.deepcopy(model))
+    rng = np.random.default_rng(SEED + 7)
+    s = np.linspace(0.2, 2.6, 20)
+    fid = dict(fsigma8=0.47, sigma_v=7.0, epsilon=1.0)
+    truth = base.theory_multipole_vector(s, dict(fid), [0, 2])
+    p = len(truth)
+    sig = 0.02 * (1 + np.abs(truth))
+    idx = np.arange(p)
+    corr = 0.4 ** np.abs(idx[:, None] - idx[None, :])
+    corr[:20, 20:] *= 0.5
+    corr[20:, :20] *= 0.5
+    cov = corr * np.outer(sig, sig)
+    dvec = truth + np.linalg.cholesky(cov) @ rng.standard_normal(p)
+    rows = np.array([[0.47, 7.0, 1.0], [0.3, 4.0, 0.97], [0.7, 10.0, 1.04], [0.55, 6.0, 1.0], [0.2, 9.0, 1.1]])
+    out = dict(params=rows, s=s, xi0=dvec[:20], xi2=dvec[20:], covmat=cov, non_reference_inputs=True)
+    with tempfile.TemporaryDirectory() as tmp:
+        np.save(os.path.join(tmp, "example_data.npy"), {"s": s, "xi0": dvec[:20], "xi2": dvec[20:]}, allow_pickle=True)
+        np.save(os.path.join(tmp, "example_cov.npy"), {"covmat": cov}, allow_pickle=True)
+        data = {"dir": tmp,
+                "redshift_space_ccf": {"data_file": "example_data.npy", "reconstruction": False, "format": "multipoles",
+                                       "ccf_keys": ["s", "xi0", "xi2"]},
+                "covariance_matrix": {"data_file": "example_cov.npy", "cov_key": "covmat"}}
+        for form, like in (("gaussian", {"form": "Gaussian"}), ("sellentin", {"form": "Sellentin", "nmocks": 500}),
+                           ("hartlap", {"form": "Hartlap", "nmocks": 500})):
+            d = copy.deepcopy(data)
+            d["likelihood"] = like
+            fit = victor.CCFFit(copy.deepcopy(model), d)
+            for name, kw in (("streaming", {}), ("dispersion", {"rsd_model": "dispersion"})):
+                if form != "gaussian" and name != "streaming":
+                    continue
+                th, c2, ll = [], [], []
+                for row in rows:
+                    pr = dict(fsigma8=row[0], sigma_v=row[1], epsilon=row[2])
+                    th.append(fit.theory_multipole_vector(fit.s, dict(pr), fit.poles_s, **kw))
+                    l, c = fit.log_likelihood(dict(pr), **kw)
+                    c_only, covm = fit.chi_squared(dict(pr), **kw)
+                    assert c_only == c and covm.shape == (p, p)
+                    c2.append(c)
+                    ll.append(l)
+                out[f"{form}_{name}_theory"], out[f"{form}_{name}_chi2"], out[f"{form}_{name}_lnl"] = (
+                    np.array(th), np.array(c2), np.array(ll))
+    np.savez(os.path.join(OUT, "example_fit.npz"), **out, **meta())
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     v = refshim.install(REF)
-    which = sys.argv[1:] or ["boss", "more", "sv2d", "linear_bias", "misc", "fixed", "rmu", "velocity", "helpers", "loader", "example"]
+    which = sys.argv[1:] or ["boss", "more", "sv2d", "linear_bias", "misc", "fixed", "rmu", "velocity", "helpers", "loader", "example",
+                             "example_fit"]
     if "boss" in which:
         golden_boss(v)
     if "more" in which:
@@ -662,5 +720,7 @@ if __name__ == "__main__":
         golden_loader_options(v)
     if "example" in which:
         golden_example(v)
+    if "example_fit" in which:
+        golden_example_fit(v)
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))

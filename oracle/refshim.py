@@ -155,9 +155,46 @@ class _Likelihood:
         pass
 
 
-def install(reference_root="/root/reference"):
+def find_reference():
+    """Where an importable copy of the unmodified reference lives, or None: ``baseline/_ref`` (the offline
+    ``pip install --no-deps --target baseline/_ref`` of /root/reference; git-ignored, shipped to the GPU box)
+    first, then the read-only checkout in the dev container."""
+    if os.environ.get("VB200_NO_REFERENCE"):      # tests: exercise the fallback to the oracle port
+        return None
+    for root in (os.path.join(_ROOT, "baseline", "_ref"), "/root/reference"):
+        if os.path.isfile(os.path.join(root, "victor", "ccf_fit.py")):
+            return root
+    return None
+
+
+def npy_twins(blocks, outdir):
+    """Rewrite the (model, data) option blocks of this repository so that the UNMODIFIED reference can read
+    their input files: the committed ``.npz`` re-encodings of the reference's HDF5 inputs become ``.npy``
+    dict files in ``outdir`` -- a format the reference reads itself (ccf_model.py:62-63, ccf_fit.py:51-52),
+    so no file-reader shim sits on its path."""
+    import copy
+    model, data = copy.deepcopy(blocks[0]), copy.deepcopy(blocks[1])
+
+    def twin(base_dir, rel):
+        src = os.path.join(base_dir, rel)
+        dst = os.path.join(outdir, os.path.splitext(os.path.basename(rel))[0] + ".npy")
+        if not os.path.isfile(dst):
+            with np.load(src) as z:
+                np.save(dst, {k: z[k] for k in z.files}, allow_pickle=True)
+        return os.path.basename(dst)
+
+    model["input_model_data_file"] = twin(model.get("dir", ""), model["input_model_data_file"])
+    model["dir"] = outdir
+    for key in ("redshift_space_ccf", "covariance_matrix"):
+        data[key]["data_file"] = twin(data.get("dir", ""), data[key]["data_file"])
+    data["dir"] = outdir
+    return model, data
+
+
+def install(reference_root=None):
     """Install the shims and put the reference on sys.path.  Idempotent."""
-    if not os.path.isdir(os.path.join(reference_root, "victor")):
+    reference_root = reference_root or find_reference()
+    if not reference_root or not os.path.isdir(os.path.join(reference_root, "victor")):
         raise FileNotFoundError(f"reference not found under {reference_root}")
 
     h5 = types.ModuleType("h5py")

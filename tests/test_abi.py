@@ -15,16 +15,16 @@ def lib():
     return _lib.load()
 
 
-def header_functions(repo_root):
-    with open(os.path.join(repo_root, "include", "victor_b200.h")) as fh:
+def header_functions(repo_root, header="victor_b200.h", prefix="vb200_"):
+    with open(os.path.join(repo_root, "include", header)) as fh:
         text = re.sub(r"/\*.*?\*/", "", fh.read(), flags=re.S)
-    return sorted(set(re.findall(r"\b(vb200_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(" + prefix + r"[a-z0-9_]+)\s*\(", text)))
 
 
 def test_header_symbols_are_exported(lib, repo_root):
     from victor_b200 import _lib
     names = header_functions(repo_root)
-    assert len(names) >= 12
+    assert len(names) == 12 and not any("probe" in n or "selftest" in n for n in names)
     for name in names:
         assert hasattr(lib, name), f"{name} declared in include/victor_b200.h but not exported"
     assert set(_lib.EXPORTS) == set(names)
@@ -33,6 +33,18 @@ def test_header_symbols_are_exported(lib, repo_root):
     assert set(names) <= dyn
     # nothing but the C ABI (and no C++-mangled API) is part of the contract
     assert all(not n.startswith("_Z") for n in dyn)
+
+
+def test_probe_library_is_separate(repo_root):
+    """Self-test and measurement hooks live in their own library and header, not in the product ABI."""
+    from victor_b200 import _lib, _probes
+    plib = _probes.load()
+    names = header_functions(repo_root, "victor_b200_probes.h", "vb200p_")
+    assert set(names) == set(_probes.EXPORTS)
+    for name in names:
+        assert hasattr(plib, name)
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "vb200p_" not in out and "probe" not in out
 
 
 def test_struct_layout_matches(lib):

@@ -713,3 +713,53 @@ def test_tables_loader_options(boss_blocks, golden, name, kw):
     bad[0]["realspace_ccf"]["simulation_number"] = 1.0
     with pytest.raises(InputError):
         CCFFit(*bad)
+
+
+def test_one_bad_grid_covariance_fails_only_its_own_points(boss_blocks):
+    """The reference checks slogdet per evaluation and returns (-inf, inf) only for points whose blended matrix
+    fails it (ccf_fit.py:445-450): a non-positive-definite grid matrix must not stop the fit from loading."""
+    import copy as _copy
+    from victor_b200 import CCFFit, tables as T
+    model, data = boss_blocks
+    f = CCFFit(_copy.deepcopy(model), _copy.deepcopy(data))
+    f.covmat = np.array(f.covmat, copy=True)
+    f.covmat[4] = -f.covmat[4]
+    ft = T.build_fit_tables(f, f.fit_options["likelihood"])
+    assert np.isnan(ft.logdet[4]) and np.all(np.isnan(ft.lam[4]))
+    ok = np.ones(len(ft.logdet), dtype=bool)
+    ok[4] = False
+    assert np.all(np.isfinite(ft.logdet[ok])) and np.all(np.isfinite(ft.lam[ok]))
+    # walk-through with the kernels' algebra: beta in interval 4 fails, the others evaluate
+    g = np.asarray(f.beta_covmat)
+    betas = np.array([0.5 * (g[4] + g[5]), 0.5 * (g[7] + g[8]), g[4], 0.37])
+    theory = np.tile(f.multipole_datavector(0.37), (len(betas), 1)) * 1.01
+    chi2, lnl = E.chi2_lnl(ft, betas, theory)
+    assert lnl[0] == -np.inf and chi2[0] == np.inf and lnl[2] == -np.inf
+    assert np.isfinite(lnl[1]) and np.isfinite(lnl[3]) and np.isfinite(chi2[1])
+
+
+def test_engine_key_follows_option_changes(fit, monkeypatch):
+    """fit.model / fit.fit_options may be edited between calls (the reference re-reads both every call,
+    ccf_fit.py:379-381, ccf_model.py:565-567): the engine is resolved from the current options each time,
+    and `niter` (ccf_model.py:661) is part of the key."""
+    built = []
+
+    def fake_engine(self, opts, need_fit=False):
+        built.append((opts["rsd_model"], int(opts.get("niter", 5)), self._fit_key(opts) if need_fit else None))
+        return object()
+
+    from victor_b200 import CCFFit
+    monkeypatch.setattr(CCFFit, "_engine", fake_engine)
+    fit._fit_engine({})
+    old_model, old_like = fit.model["rsd_model"], fit.fit_options["likelihood"]
+    try:
+        fit.model["rsd_model"] = "dispersion"
+        fit._fit_engine({})
+        fit.fit_options["likelihood"] = {"form": "gaussian"}
+        fit._fit_engine({"niter": 3})
+    finally:
+        fit.model["rsd_model"], fit.fit_options["likelihood"] = old_model, old_like
+    assert [b[0] for b in built] == [old_model, "dispersion", "dispersion"]
+    assert built[2][1] == 3 and built[2][2][0] == "gaussian" and built[0][2][0] == "sellentin"
+    from victor_b200 import tables as T
+    assert T.build_model_tables(fit, fit._merged_options({"rsd_model": "dispersion", "niter": 2})).niter == 2

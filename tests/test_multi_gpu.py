@@ -16,7 +16,7 @@ import os, sys, copy
 import numpy as np, torch, torch.distributed as dist, yaml
 sys.path.insert(0, os.environ["VB200_ROOT"])
 from victor_b200 import CCFFit
-from victor_b200.batch import evaluate_sharded
+from victor_b200.batch import evaluate_sharded, likelihood_sharded
 from victor_b200.model import params_to_rows
 from bench import synthetic_batch
 rank = int(os.environ["RANK"]); local = int(os.environ["LOCAL_RANK"])
@@ -28,6 +28,11 @@ info["model"]["dir"] = info["data"]["dir"] = root
 fit = CCFFit(info["model"], info["data"], device=local)
 rows = params_to_rows(synthetic_batch(65536)[:1001])
 lnl, chi2, (lo, hi) = evaluate_sharded(fit.log_likelihood_batch, rows, gather=True)
+# the device-to-device form: slices evaluated into device buffers, all-gather over NCCL, one D2H
+lnl_d, chi2_d, (lo_d, hi_d) = likelihood_sharded(fit, rows, gather=True)
+assert (lo_d, hi_d) == (lo, hi) and np.array_equal(lnl_d, lnl) and np.array_equal(chi2_d, chi2)
+lnl_s, chi2_s, _ = likelihood_sharded(fit, rows, gather=False)
+assert np.array_equal(lnl_s, lnl[lo:hi]) and np.array_equal(chi2_s, chi2[lo:hi])
 np.savez(os.path.join(os.environ["VB200_OUT"], f"rank{rank}.npz"), lnl=lnl, chi2=chi2, lo=lo, hi=hi)
 if rank == 0:
     l1, c1 = fit.log_likelihood_batch(rows)

@@ -41,7 +41,7 @@ def _worker(rank, world, port, n_rows, out_dir):
     import yaml
     from oracle import table_emul as E
     from victor_b200 import CCFFit, tables as T
-    from victor_b200.batch import evaluate_sharded
+    from victor_b200.batch import evaluate_sharded, likelihood_sharded
     from victor_b200.model import params_to_rows
     from bench import synthetic_batch
 
@@ -64,7 +64,13 @@ def _worker(rank, world, port, n_rows, out_dir):
     rows = params_to_rows(synthetic_batch(65536)[:n_rows])
     lnl, chi2, (lo, hi) = evaluate_sharded(evaluate, rows, gather=True)
     lnl_s, chi2_s, _ = evaluate_sharded(evaluate, rows, gather=False)
-    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), lnl=lnl, chi2=chi2, lo=lo, hi=hi, calls=np.array(calls),
+    ncalls = len(calls)
+    # likelihood_sharded is the device-to-device form for NCCL; on any other backend it must route through
+    # evaluate_sharded with the fit's own host-array evaluator
+    fit.log_likelihood_batch = lambda part, **kw: evaluate(part)
+    lnl_l, chi2_l, (lo_l, hi_l) = likelihood_sharded(fit, rows, gather=True)
+    assert (lo_l, hi_l) == (lo, hi) and np.array_equal(lnl_l, lnl) and np.array_equal(chi2_l, chi2)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), lnl=lnl, chi2=chi2, lo=lo, hi=hi, calls=np.array(calls[:ncalls]),
              lnl_slice=lnl_s, chi2_slice=chi2_s)
     dist.destroy_process_group()
 

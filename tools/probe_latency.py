@@ -41,9 +41,26 @@ def main():
     print("CCFFit.log_likelihood(dict)            us median/p95:", med(lambda: fit.log_likelihood(prm)))
     st = {}
     print("CCFLikelihood.calculate(**dict)        us median/p95:", med(lambda: like.calculate(st, **prm)))
-    for opt, val in (("nsplit", 30), ("nsplit", 15), ("nsplit", 10), ("nsplit", 6), ("nsplit", 0)):
+    for opt, val in (("tiny", 0), ("graph", 0), ("tiny", 1), ("graph", 1)):
         eng.set_option(opt, val)
-        print(f"C ABI call with {opt}={val}              us median/p95:", med(lambda: lib.vb200_likelihood(h, rp, 1, None, cp, lp, None)))
+        print(f"C ABI call after {opt}={val}              us median/p95:", med(lambda: lib.vb200_likelihood(h, rp, 1, None, cp, lp, None)))
+    # device-resident buffers: kernel time of the one-launch path by CUDA events
+    import torch
+    d_rows = torch.from_numpy(rows).cuda()
+    d_out = torch.empty((2, 1), dtype=torch.float64, device="cuda")
+    for tiny in (1, 0):
+        eng.set_option("tiny", tiny)
+        ts = []
+        for i in range(300):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            eng.likelihood_ptr(d_rows.data_ptr(), 1, None, d_out[1].data_ptr(), d_out[0].data_ptr(), None)
+            b.record()
+            torch.cuda.synchronize()
+            if i >= 50:
+                ts.append(a.elapsed_time(b) * 1e3)
+        print(f"CUDA events around the device-buffer call, tiny={tiny}: us median {np.median(ts):.2f}")
+    eng.set_option("tiny", 1)
     fit.close()
 
 

@@ -9,20 +9,20 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from victor_b200 import _lib  # noqa: E402
+from victor_b200 import _probes as _lib  # noqa: E402
 
 lib = _lib.load()
 names = {0: "dfma", 1: "f2i_f64_floor", 2: "dfma+f2i", 3: "f2f_f32_f64", 4: "dfma+f2f", 5: "i2f_f64", 6: "dfma+i2f"}
 rep = {}
 for mode, name in names.items():
     ms = ctypes.c_double()
-    rc = lib.vb200_pipe_probe(0, mode, 2048, ctypes.byref(ms))
+    rc = lib.vb200p_pipe_probe(0, mode, 2048, ctypes.byref(ms))
     assert rc == 0, _lib.last_error()
     rep[name + "_ms"] = ms.value
 rng = np.random.default_rng(0)
 x = np.ascontiguousarray(np.concatenate([rng.uniform(0.25, 4.0, 400000), 10.0 ** rng.uniform(-3, 5, 100000)]))
 out = np.empty(2 * len(x))
-assert lib.vb200_seed_probe(0, x.ctypes.data, len(x), out.ctypes.data) == 0
+assert lib.vb200p_seed_probe(0, x.ctypes.data, len(x), out.ctypes.data) == 0
 rs, rc_ = out[:len(x)], out[len(x):]
 e_rs = rs * np.sqrt(x) - 1
 e_rc = rc_ * x - 1

@@ -24,13 +24,14 @@ def main():
     ap.add_argument("--threads", type=int, default=256)
     ap.add_argument("--nsplit", type=int, default=0)
     ap.add_argument("--ilp", type=int, default=4)
-    ap.add_argument("--expdeg", type=int, default=5)
-    ap.add_argument("--newton", type=int, default=3)
+    ap.add_argument("--expdeg", type=int, default=None)
+    ap.add_argument("--newton", type=int, default=None)
     ap.add_argument("--fuse", type=int, default=1, help="1: chi2 / lnL in the K1 epilogue; 0: separate K2 launch")
     ap.add_argument("--theory", type=int, default=1, help="0: do not ask for the theory vectors (chi2 / lnL only)")
     ap.add_argument("--sigma-v", type=float, default=None, help="override the sigma_v column (access-pattern probe)")
     ap.add_argument("--rsd", default="streaming", help="rsd_model (general kernel for anything but streaming)")
-    ap.add_argument("--aniso", type=int, default=0, help="1: assume_isotropic False (general kernel)")
+    ap.add_argument("--aniso", type=int, default=0, help="1: assume_isotropic False")
+    ap.add_argument("--tuned", type=int, default=1, help="0: force the general kernel")
     args = ap.parse_args()
     model, data = boss_blocks()
     fit = CCFFit(model, data, device=0)
@@ -44,9 +45,12 @@ def main():
     eng.set_option("threads", args.threads)
     eng.set_option("nsplit", args.nsplit)
     eng.set_option("ilp", args.ilp)
-    eng.set_option("exp_degree", args.expdeg)
-    eng.set_option("newton", args.newton)
+    if args.expdeg is not None:
+        eng.set_option("exp_degree", args.expdeg)
+    if args.newton is not None:
+        eng.set_option("newton", args.newton)
     eng.set_option("fuse", args.fuse)
+    eng.set_option("tuned", args.tuned)
     n = args.batch
     dev = torch.device("cuda", 0)
     rows = params_to_rows(synthetic_batch(n))
@@ -65,7 +69,7 @@ def main():
         b.record()
         torch.cuda.synchronize()
         times.append(a.elapsed_time(b))
-    print(f"batch={n} fast={args.fast} threads={args.threads} nsplit={args.nsplit} ilp={args.ilp} expdeg={args.expdeg} newton={args.newton} fuse={args.fuse} theory={args.theory} sigma_v={args.sigma_v} rsd={args.rsd} aniso={args.aniso} "
+    print(f"batch={n} fast={args.fast} threads={args.threads} nsplit={args.nsplit} ilp={args.ilp} expdeg={args.expdeg} newton={args.newton} fuse={args.fuse} theory={args.theory} sigma_v={args.sigma_v} rsd={args.rsd} aniso={args.aniso} tuned={args.tuned} lib={os.path.basename(os.environ.get('VICTOR_B200_LIB', 'default'))} "
           f"ms={['%.3f' % t for t in times]} evals/s={n / (min(times) * 1e-3):.4g} "
           f"chi2[0]={float(d_chi2[0]):.10f}")
     fit.close()

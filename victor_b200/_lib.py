@@ -19,8 +19,7 @@ c_int32_p = POINTER(c_int32)
 
 EXPORTS = ("vb200_version", "vb200_abi_check", "vb200_last_error", "vb200_device_count", "vb200_create", "vb200_destroy",
            "vb200_set_option", "vb200_theory", "vb200_theory_pairs", "vb200_likelihood", "vb200_synchronize",
-           "vb200_launch_count", "vb200_math_selftest", "vb200_fp64_peak", "vb200_pipe_probe", "vb200_seed_probe",
-           "vb200_mix_probe")
+           "vb200_launch_count")
 
 
 class ModelTablesC(ctypes.Structure):
@@ -92,16 +91,6 @@ def load():
     lib.vb200_synchronize.argtypes = [c_void_p]
     lib.vb200_launch_count.restype = c_int64
     lib.vb200_launch_count.argtypes = [c_void_p]
-    lib.vb200_math_selftest.restype = c_int
-    lib.vb200_math_selftest.argtypes = [c_int, c_void_p, c_int64, c_void_p]
-    lib.vb200_pipe_probe.restype = c_int
-    lib.vb200_pipe_probe.argtypes = [c_int, c_int, c_int, POINTER(c_double)]
-    lib.vb200_mix_probe.restype = c_int
-    lib.vb200_mix_probe.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_double)]
-    lib.vb200_seed_probe.restype = c_int
-    lib.vb200_seed_probe.argtypes = [c_int, c_void_p, c_int64, c_void_p]
-    lib.vb200_fp64_peak.restype = c_int
-    lib.vb200_fp64_peak.argtypes = [c_int, c_int, POINTER(c_double), POINTER(c_double)]
     _lib = lib
     return lib
 

@@ -5,11 +5,13 @@ shards trivially: each GPU holds a replica of the tables and evaluates a contigu
 the rows.  There is no exchange step on the data path; the only optional communication is a
 gather of the 16 bytes per row of results (chi2, lnL).
 
-Two ways to drive N GPUs:
+Ways to drive N GPUs:
 
-* ``evaluate_sharded`` -- one process per GPU under ``torch.distributed`` (torchrun): every
-  rank passes the SAME full table, evaluates its own slice on its own context and, if asked,
-  all-gathers the per-row results (NCCL for device tensors; gloo works for the CPU tests).
+* ``likelihood_sharded`` -- one process per GPU under ``torch.distributed`` (torchrun, NCCL): every rank
+  passes the SAME full table, evaluates its own slice into a device buffer and the per-row results are
+  all-gathered device to device, then copied to the host once.
+* ``evaluate_sharded`` -- the same split for any host-array evaluator (and the gloo backend of the CPU
+  tests): results travel as host arrays staged through a tensor.
 * ``MultiDeviceFit`` -- one process, one context per visible GPU, one host thread per context
   (the ctypes calls release the GIL, so the launches and copies of the N devices overlap).
 
@@ -67,6 +69,43 @@ def evaluate_sharded(evaluate, rows, gather=True, group=None):
     out = out.cpu().numpy()
     lnl_all = np.concatenate([out[r, 0, :b - a] for r, (a, b) in enumerate(bounds)])
     chi2_all = np.concatenate([out[r, 1, :b - a] for r, (a, b) in enumerate(bounds)])
+    return lnl_all, chi2_all, (lo, hi)
+
+
+def likelihood_sharded(fit, rows, gather=True, group=None, **kwargs):
+    """One parameter table, N ranks, results gathered device to device.
+
+    Every rank passes the SAME ``rows``; rank r copies its own contiguous slice to its GPU, evaluates it into its
+    slot of a device buffer (``CCFFit.log_likelihood_device``: nothing comes back to the host in between) and the
+    slots are exchanged with one ``all_gather_into_tensor`` over NCCL (16 B per row); one device-to-host copy of the
+    gathered table follows.  Returns ``(lnl, chi2, (lo, hi))`` like ``evaluate_sharded`` -- which remains the path
+    for host-array evaluators, the gloo backend and the 'likelihood' beta-interpolation mode."""
+    import torch
+    import torch.distributed as dist
+
+    rows = np.ascontiguousarray(rows, dtype=np.float64)
+    n = rows.shape[0]
+    distributed = dist.is_available() and dist.is_initialized()
+    like_mode = fit.fit_options.get("beta_interpolation") == "likelihood" or kwargs.get("beta_interpolation") == "likelihood"
+    if not distributed or dist.get_backend(group) != "nccl" or like_mode:
+        return evaluate_sharded(lambda part: fit.log_likelihood_batch(part, **kwargs), rows, gather=gather, group=group)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    bounds = shard_bounds(n, world)
+    lo, hi = bounds[rank]
+    per = bounds[0][1] - bounds[0][0]
+    eng, _ = fit._fit_engine(kwargs)
+    dev = torch.device("cuda", eng.device)
+    table = torch.full((world, 2, per), float("nan"), dtype=torch.float64, device=dev) if gather else None
+    mine = table[rank] if gather else torch.empty((2, per), dtype=torch.float64, device=dev)
+    if hi > lo:
+        fit.log_likelihood_device(rows[lo:hi], out=mine, **kwargs)
+    if not gather:
+        host = mine[:, :hi - lo].cpu().numpy()
+        return host[0], host[1], (lo, hi)
+    dist.all_gather_into_tensor(table.view(-1), mine.reshape(-1), group=group)   # in place: rank r's slot is table[r]
+    host = table.cpu().numpy()
+    lnl_all = np.concatenate([host[r, 0, :b - a] for r, (a, b) in enumerate(bounds)])
+    chi2_all = np.concatenate([host[r, 1, :b - a] for r, (a, b) in enumerate(bounds)])
     return lnl_all, chi2_all, (lo, hi)
 
 

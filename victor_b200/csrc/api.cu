@@ -10,10 +10,18 @@
 #include <nvtx3/nvToolsExt.h>
 
 #include "../../include/victor_b200.h"
+
+// defaults of the tuned kernel's math (vb200_set_option "exp_degree", "newton" select the others)
+#ifndef VB200_DEFAULT_EXP
+#define VB200_DEFAULT_EXP 5
+#endif
+#ifndef VB200_DEFAULT_NEWTON
+#define VB200_DEFAULT_NEWTON 2   // one Newton step on the MUFU seeds: +3.9 % and 5.5e-12 / 7.5e-10 measured margins
+#endif
 #include "k1_general.cuh"
+#include "k1_small.cuh"
 #include "k1_streaming.cuh"
 #include "k2_chi2.cuh"
-#include "probes.cuh"
 
 using namespace vb200;
 
@@ -103,9 +111,14 @@ struct vb200_ctx {
     std::vector<void *> owned;
     Scratch sc_params, sc_theory, sc_chi2, sc_lnl, sc_xi, sc_mult, sc_grid;
     // options
-    int opt_fast = 1, opt_nsplit = 0, opt_threads = 256, opt_ilp = 4, opt_expdeg = 5, opt_newton = 3;
+    int opt_fast = 1, opt_nsplit = 0, opt_threads = 256, opt_ilp = 4;
+    int opt_expdeg = 0, opt_newton = 0;   // 0 = the kernel family's default (kDefExp / kDefNewton; dispersion: cubic)
     int opt_fuse = 1;             // batch mode: chi2 / lnL in the epilogue of K1 instead of a K2 launch
-    bool tuned = false;           // streaming + isotropic xi + model coordinates: the tuned kernel applies
+    int opt_tuned = 1;            // 0: force the general kernel (A/B checks of the tuned kernels)
+    int opt_tiny = 1;             // calls of <= kSmallRows rows: one launch of k_small instead of K1 + K2 (0: off)
+    double *tiny_xi = nullptr;    // k_small scratch: xi(s, mu) of kSmallRows rows, and the rows' ticket counters
+    unsigned *tiny_tickets = nullptr;
+    int family = 0;               // kernel family the tables are eligible for (kTunedIso / kTunedWide / kGeneral)
     // small-call path (MCMC steps): page-locked staging for the rows in and (chi2 | lnL) out
     double *pin = nullptr, *d_small = nullptr, *d_small_theory = nullptr;
     // the small-call sequence (H2D, K1, K2, D2H) as an instantiated CUDA graph, rebuilt when n or an option changes
@@ -164,26 +177,88 @@ int check_model(const vb200_model_tables *m) {
 
 typedef void (*k1_fn)(const K1Args);
 
-// Tuned streaming kernel variants in this build.  The default is <fast, U = 4, degree-5 exp>; the
-// others exist for parity tests (libm math) and for measurement (ILP, exp degree).
-// Variants with the fused likelihood epilogue exist for the default tuned configuration only
-// (nullptr otherwise: the caller then launches K2 after the plain kernel).
-k1_fn pick_k1_fused(bool fast, bool flags, int ilp, int expdeg, int newton) {
-    if (!fast || ilp < 4 || expdeg != 5 || newton != 3) return nullptr;
-    return flags ? k_multipoles<K1Cfg<true, true, 4, 5>, true> : k_multipoles<K1Cfg<true, false, 4, 5>, true>;
+// ---- kernel variants in this build --------------------------------------------------------------------
+// Tuned kernel, streaming model + isotropic xi (the BOSS likelihood).  Default <fast, U = 4, exp kDefExp,
+// refinement kDefNewton>; the others exist for parity tests (libm math) and for measurement (ILP, exp
+// polynomial, refinement order).  Tables with knots off the bucket lattice (kFlags) get the default and the
+// libm variant only.
+constexpr int kDefExp = VB200_DEFAULT_EXP, kDefNewton = VB200_DEFAULT_NEWTON;
+
+// a kernel and the exp variant it was built with (the host folds that variant's argument scale into the weights
+// and sizes the exp table in shared memory accordingly)
+struct K1Pick {
+    k1_fn fn;
+    int exp;
+};
+
+template <bool kFlags>
+K1Pick k1_iso_variant(bool fast, int ilp, int expdeg, int newton) {
+    if (!fast) return {k_multipoles<K1Cfg<false, kFlags, 1, 6>>, 6};
+    if (kFlags) return {k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, kDefNewton>>, kDefExp};
+    if (ilp < 4) return {k_multipoles<K1Cfg<true, kFlags, 1, kDefExp, kDefNewton>>, kDefExp};
+#define VB_V(E, N) if (expdeg == E && newton == N) return {k_multipoles<K1Cfg<true, kFlags, 4, E, N>>, E};
+    VB_V(5, 3) VB_V(5, 2) VB_V(53, 2) VB_V(6, 3) VB_V(3, 3) VB_V(3, 2) VB_V(30, 2)
+#undef VB_V
+    return {k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, kDefNewton>>, kDefExp};
 }
 
-k1_fn pick_k1(bool fast, bool flags, int ilp, int expdeg, int newton = 3) {
-    if (fast && newton == 2 && ilp >= 4 && expdeg == 5)
-        return flags ? k_multipoles<K1Cfg<true, true, 4, 5, 2>> : k_multipoles<K1Cfg<true, false, 4, 5, 2>>;
-    if (!fast) return flags ? k_multipoles<K1Cfg<false, true, 1, 6>> : k_multipoles<K1Cfg<false, false, 1, 6>>;
-    if (flags) {
-        if (ilp < 4) return k_multipoles<K1Cfg<true, true, 1, 5>>;
-        return expdeg == 5 ? k_multipoles<K1Cfg<true, true, 4, 5>> : k_multipoles<K1Cfg<true, true, 4, 6>>;
+K1Pick pick_k1(bool fast, bool flags, int ilp, int expdeg, int newton) {
+    if (!expdeg) expdeg = kDefExp;
+    if (!newton) newton = kDefNewton;
+    return flags ? k1_iso_variant<true>(fast, ilp, expdeg, newton) : k1_iso_variant<false>(fast, ilp, expdeg, newton);
+}
+
+// fused likelihood epilogue: for the default tuned configuration only (nullptr otherwise: the caller then
+// launches K2 after the plain kernel)
+k1_fn pick_k1_fused(bool fast, bool flags, int ilp, int expdeg, int newton) {
+    if (!expdeg) expdeg = kDefExp;
+    if (!newton) newton = kDefNewton;
+    if (!fast || ilp < 4 || expdeg != kDefExp || newton != kDefNewton) return nullptr;
+    return flags ? k_multipoles<K1Cfg<true, true, 4, kDefExp, kDefNewton>, true>
+                 : k_multipoles<K1Cfg<true, false, 4, kDefExp, kDefNewton>, true>;
+}
+
+// Tuned kernel, the other velocity-integral setups on model coordinates: anisotropic streaming
+// (xi_0 + xi_2 L_2 [+ xi_4 L_4]) and the dispersion model.  Fast math only (the libm test variant of these
+// models is the general kernel); `ilp` 2 selects two nodes in flight for measurement.
+// (the dispersion model keeps the cubic refinement whatever the streaming default is: its coordinate iteration
+// amplifies seed errors, see k1_streaming.cuh: disp_nodes; `newton` 2 selects the one-step variant for measurement)
+template <bool kFlags>
+k1_fn k1_wide_variant(int rsd_model, int n_ell, int ilp, int newton) {
+    if (rsd_model == kRsdDispersion) {
+        if (n_ell == 1) {
+            if (newton == 2 && !kFlags) return k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, 2, kRsdDispersion, 1>>;
+            return ilp < 4 ? k_multipoles<K1Cfg<true, kFlags, 2, kDefExp, 3, kRsdDispersion, 1>>
+                           : k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, 3, kRsdDispersion, 1>>;
+        }
+        if (n_ell == 2) return k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, 3, kRsdDispersion, 2>>;
+        return k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, 3, kRsdDispersion, 3>>;
     }
-    if (ilp == 1) return k_multipoles<K1Cfg<true, false, 1, 5>>;
-    if (ilp == 2) return k_multipoles<K1Cfg<true, false, 2, 5>>;
-    return expdeg == 5 ? k_multipoles<K1Cfg<true, false, 4, 5>> : k_multipoles<K1Cfg<true, false, 4, 6>>;
+    if (n_ell == 2)
+        return ilp < 4 ? k_multipoles<K1Cfg<true, kFlags, 2, kDefExp, kDefNewton, kRsdStreaming, 2>>
+                       : k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, kDefNewton, kRsdStreaming, 2>>;
+    return k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, kDefNewton, kRsdStreaming, 3>>;
+}
+
+k1_fn pick_k1_wide(int rsd_model, int n_ell, bool flags, int ilp, int newton) {
+    return flags ? k1_wide_variant<true>(rsd_model, n_ell, ilp, newton) : k1_wide_variant<false>(rsd_model, n_ell, ilp, newton);
+}
+
+// k_small: the few-rows kernel, default math of the tuned families (fast only)
+typedef void (*small_fn)(const K1Args, const SmallArgs);
+template <bool kFlags>
+small_fn small_variant(int rsd_model, int n_ell) {
+    if (rsd_model == kRsdDispersion) {
+        if (n_ell == 1) return k_small<K1Cfg<true, kFlags, 4, kDefExp, 3, kRsdDispersion, 1>>;
+        if (n_ell == 2) return k_small<K1Cfg<true, kFlags, 4, kDefExp, 3, kRsdDispersion, 2>>;
+        return k_small<K1Cfg<true, kFlags, 4, kDefExp, 3, kRsdDispersion, 3>>;
+    }
+    if (n_ell == 1) return k_small<K1Cfg<true, kFlags, 4, kDefExp, kDefNewton>>;
+    if (n_ell == 2) return k_small<K1Cfg<true, kFlags, 4, kDefExp, kDefNewton, kRsdStreaming, 2>>;
+    return k_small<K1Cfg<true, kFlags, 4, kDefExp, kDefNewton, kRsdStreaming, 3>>;
+}
+small_fn pick_small(int rsd_model, int n_ell, bool flags) {
+    return flags ? small_variant<true>(rsd_model, n_ell) : small_variant<false>(rsd_model, n_ell);
 }
 
 k1_fn pick_general_fused(int rsd_model, bool fast) {
@@ -201,6 +276,13 @@ k1_fn pick_general(int rsd_model, bool fast) {
     return fast ? k_multipoles_kaiser<true> : k_multipoles_kaiser<false>;
 }
 
+// which kernel family serves this context with the current options
+//   kTunedIso : streaming + isotropic xi + model coordinates + sigma_v(r): every variant of pick_k1
+//   kTunedWide: anisotropic streaming or dispersion on model coordinates + sigma_v(r), fast math, "tuned" option on
+//   kGeneral  : everything else
+enum { kGeneral = 0, kTunedIso = 1, kTunedWide = 2 };
+int kernel_family(const vb200_ctx *c);
+
 // blocks per parameter row: one once the rows alone fill the GPU a few times over, else the s range is split
 // so that a single row (MCMC step) still spreads over the SMs.  (A wave-count cost model choosing among all
 // splits was tried: within +-7 % of this rule over n = 1 ... 16 384, profiles/r01s_probe_nsplit.log.)
@@ -215,6 +297,30 @@ int pick_nsplit(const vb200_ctx *c, long long n, int ns, bool pairwise) {
 
 k1_fn fused_variant(const vb200_ctx *c);
 
+int kernel_family(const vb200_ctx *c) {
+    if (!c->opt_tuned) return kGeneral;
+    if (c->family == kTunedWide && !c->opt_fast) return kGeneral;
+    return c->family;
+}
+
+int rec_doubles(const vb200_ctx *c) { return k1_rec_doubles(c->md.rsd_model, c->md.n_ell); }
+
+// exp variant the tuned kernel of this context runs with (the measurement variants exist for kTunedIso without
+// bucket flags only; everything else runs the build's default)
+int tuned_exp(const vb200_ctx *c) {
+    if (kernel_family(c) == kTunedIso)
+        return pick_k1(c->opt_fast != 0, c->has_flags, c->opt_ilp, c->opt_expdeg, c->opt_newton).exp;
+    return kDefExp;
+}
+bool big_table(int expdeg) { return expdeg == 3 || expdeg == 30; }
+
+size_t k1_smem_for(const vb200_ctx *c, int jper, int nmu, int fitd) {
+    return kernel_family(c) != kGeneral
+               ? k1_smem_bytes(c->md.ncell, jper, nmu, c->md.nbucket, fitd, rec_doubles(c),
+                               c->opt_fast && big_table(tuned_exp(c)) ? kExpTabBig : kExpTab)
+               : k1g_smem_bytes(c->md.ncell, jper, nmu, c->md.nbucket, fitd);
+}
+
 // opt_fuse: 0 never, 1 where it pays, 2 always.  Measured (profiles/r01n_variants_fuse.log):
 //   general kernel, velocity-integral models: +0.5 % and no theory scratch -> fused by default;
 //   general kernel, kaiser / euclid_special (3000 points per row, short blocks): the epilogue's L2 reads sit
@@ -224,8 +330,10 @@ k1_fn fused_variant(const vb200_ctx *c);
 k1_fn fused_variant(const vb200_ctx *c) {
     if (!c->opt_fuse || !c->has_fit) return nullptr;
     const bool always = c->opt_fuse >= 2;
-    if (c->tuned)
+    const int fam = kernel_family(c);
+    if (fam == kTunedIso)
         return always ? pick_k1_fused(c->opt_fast != 0, c->has_flags, c->opt_ilp, c->opt_expdeg, c->opt_newton) : nullptr;
+    if (fam == kTunedWide) return nullptr;   // K2 is < 1 % of these steps: separate launch
     if (c->md.rsd_model >= kRsdKaiser && !always) return nullptr;
     return pick_general_fused(c->md.rsd_model, c->opt_fast != 0);
 }
@@ -243,10 +351,8 @@ int launch_k1(vb200_ctx *c, const double *d_params, long long n, const double *d
     k1_fn fused_fn = ((d_chi2 || d_lnl) && nsplit == 1 && !pairwise) ? fused_variant(c) : nullptr;
     const bool want_fuse = fused_fn != nullptr;
     const int fitd = want_fuse ? fused_fit_doubles(c->fd.p) : 0;
-    auto smem_for = [&](int jp) {
-        return c->tuned ? k1_smem_bytes(c->md.ncell, jp, nmu, c->md.nbucket, fitd)
-                        : k1g_smem_bytes(c->md.ncell, jp, nmu, c->md.nbucket, fitd);
-    };
+    auto smem_for = [&](int jp) { return k1_smem_for(c, jp, nmu, fitd); };
+    const int fam = kernel_family(c);
     // long s grids: split further until a block's xi(s, mu) stage leaves room for 4 blocks per SM
     // (or, failing that, at least fits)
     const size_t want = std::min<size_t>(c->k1_smem_limit, (size_t)56 * 1024);
@@ -286,10 +392,13 @@ int launch_k1(vb200_ctx *c, const double *d_params, long long n, const double *d
     a.xi_out = d_xi;
     a.mult_out = d_mult;
     memcpy(a.xw, c->xw, sizeof(a.xw));
-    if (c->tuned && c->opt_fast)   // the fast kernel's reciprocal of SV carries sqrt(16 log2 e): take it out of the weights
-        for (int i = 0; i < c->md.nx; ++i) a.xw[kMaxNx + i] = c->xw[kMaxNx + i] / kGaussScale;
-    auto fn = c->tuned ? pick_k1(c->opt_fast != 0, c->has_flags, c->opt_ilp, c->opt_expdeg, c->opt_newton)
-                       : pick_general(c->md.rsd_model, c->opt_fast != 0);
+    if (fam != kGeneral && c->opt_fast) {   // the fast kernel's reciprocal of SV carries the scale of the exp argument: take it out of the weights
+        const double scale = big_table(tuned_exp(c)) ? kGaussScaleBig : kGaussScale;
+        for (int i = 0; i < c->md.nx; ++i) a.xw[kMaxNx + i] = c->xw[kMaxNx + i] / scale;
+    }
+    k1_fn fn = fam == kTunedIso    ? pick_k1(c->opt_fast != 0, c->has_flags, c->opt_ilp, c->opt_expdeg, c->opt_newton).fn
+               : fam == kTunedWide ? pick_k1_wide(c->md.rsd_model, c->md.n_ell, c->has_flags, c->opt_ilp, c->opt_newton)
+                                   : pick_general(c->md.rsd_model, c->opt_fast != 0);
     if (a.fuse) fn = fused_fn;
     void *kargs[] = {(void *)&a};
     CK(cudaLaunchKernel((const void *)fn, dim3((unsigned)blocks), dim3(threads), kargs, smem, st));
@@ -321,16 +430,80 @@ int launch_k2(vb200_ctx *c, const double *d_params, const double *d_theory, long
     return VB200_OK;
 }
 
+// does a likelihood call of n rows go through k_small?  (tuned kernel families with their default math only)
+bool use_small(const vb200_ctx *c, long long n) {
+    return c->opt_tiny && c->has_fit && n >= 1 && n <= kSmallRows && c->opt_fast && kernel_family(c) != kGeneral &&
+           c->opt_ilp >= 4 && !c->opt_expdeg && !c->opt_newton && c->opt_nsplit <= 0 &&
+           small_smem_bytes(c->md.ncell, c->md.nbucket, c->fd.p, rec_doubles(c), big_table(kDefExp) ? kExpTabBig : kExpTab) <=
+               c->k1_smem_limit;
+}
+
+// theory (optional), chi2 and lnL of n <= kSmallRows rows on the fit's grids in ONE launch (k1_small.cuh)
+int launch_small(vb200_ctx *c, const double *d_params, long long n, double *d_theory, double *d_chi2, double *d_lnl,
+                 cudaStream_t st) {
+    if (!c->tiny_xi) {
+        double *xi = nullptr;
+        unsigned *tk = nullptr;
+        cudaError_t e = cudaMalloc(&xi, (size_t)kSmallRows * c->fit_ns * c->fit_nmu * sizeof(double));
+        if (e == cudaSuccess) e = cudaMalloc(&tk, kSmallRows * sizeof(unsigned));
+        if (e == cudaSuccess) e = cudaMemset(tk, 0, kSmallRows * sizeof(unsigned));
+        if (e != cudaSuccess) {
+            if (xi) cudaFree(xi);
+            if (tk) cudaFree(tk);
+            return fail(VB200_ENOMEM, std::string("k_small scratch: ") + cudaGetErrorString(e));
+        }
+        c->tiny_xi = xi;
+        c->tiny_tickets = tk;
+    }
+    K1Args a{};
+    a.m = c->md;
+    a.params = d_params;
+    a.n = n;
+    a.s = c->fit_s;
+    a.mu = c->fit_mu;
+    a.sqmu = c->fit_sqmu;
+    a.wmu = c->fit_wmu;
+    a.ns = c->fit_ns;
+    a.nmu = c->fit_nmu;
+    a.L = c->fit_L;
+    a.jper = 1;
+    a.nsplit = c->fit_ns;
+    a.has_flags = c->has_flags ? 1 : 0;
+    a.fuse = 1;
+    a.f = c->fd;
+    a.chi2 = d_chi2;
+    a.lnl = d_lnl;
+    const bool big = big_table(kDefExp);
+    const double scale = big ? kGaussScaleBig : kGaussScale;
+    for (int i = 0; i < c->md.nx; ++i) {
+        a.xw[i] = c->xw[i];
+        a.xw[kMaxNx + i] = c->xw[kMaxNx + i] / scale;
+    }
+    SmallArgs sm{c->tiny_xi, c->tiny_tickets, d_theory};
+    const int nchunk = (c->fit_nmu + kSmallPairs - 1) / kSmallPairs;
+    const long long blocks = n * c->fit_ns * nchunk;
+    const size_t smem = small_smem_bytes(c->md.ncell, c->md.nbucket, c->fd.p, rec_doubles(c), big ? kExpTabBig : kExpTab);
+    void *kargs[] = {(void *)&a, (void *)&sm};
+    CK(cudaLaunchKernel((const void *)pick_small(c->md.rsd_model, c->md.n_ell, c->has_flags), dim3((unsigned)blocks),
+                        dim3(kSmallPairs * kSmallLanes), kargs, smem, st));
+    c->launches++;
+    return VB200_OK;
+}
+
 // H2D of the staged rows, K1, K2 (unless fused), D2H of (chi2 | lnL) -- the whole small call on one stream
 int small_sequence(vb200_ctx *c, int64_t n, cudaStream_t st) {
     int rc;
     double *h_out = c->pin + (size_t)kSmallCall * VB200_NPAR, *d_out = c->d_small + (size_t)kSmallCall * VB200_NPAR;
     CK(cudaMemcpyAsync(c->d_small, c->pin, (size_t)n * VB200_NPAR * sizeof(double), cudaMemcpyHostToDevice, st));
-    bool fused = false;
-    if ((rc = launch_k1(c, c->d_small, n, c->fit_s, c->fit_ns, c->fit_mu, c->fit_sqmu, c->fit_wmu, c->fit_nmu,
-                        c->fit_L, nullptr, c->d_small_theory, st, false, d_out, d_out + n, &fused)))
-        return rc;
-    if (!fused && (rc = launch_k2(c, c->d_small, c->d_small_theory, n, d_out, d_out + n, st))) return rc;
+    if (use_small(c, n)) {
+        if ((rc = launch_small(c, c->d_small, n, nullptr, d_out, d_out + n, st))) return rc;
+    } else {
+        bool fused = false;
+        if ((rc = launch_k1(c, c->d_small, n, c->fit_s, c->fit_ns, c->fit_mu, c->fit_sqmu, c->fit_wmu, c->fit_nmu,
+                            c->fit_L, nullptr, c->d_small_theory, st, false, d_out, d_out + n, &fused)))
+            return rc;
+        if (!fused && (rc = launch_k2(c, c->d_small, c->d_small_theory, n, d_out, d_out + n, st))) return rc;
+    }
     CK(cudaMemcpyAsync(h_out, d_out, (size_t)2 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
     return VB200_OK;
 }
@@ -391,8 +564,8 @@ int ensure_copy_stream(vb200_ctx *c, int nchunks) {
     return VB200_OK;
 }
 
-void fill_exp_table(double *t) {
-    for (int j = 0; j < kExpTab; ++j) t[j] = std::exp2((double)j / kExpTab);
+void fill_exp_table(double *t, int n = kExpTab) {
+    for (int j = 0; j < n; ++j) t[j] = std::exp2((double)j / n);
 }
 
 }  // namespace
@@ -440,6 +613,8 @@ void vb200_destroy(vb200_ctx *c) {
     if (c->pin) cudaFreeHost(c->pin);
     if (c->d_small) cudaFree(c->d_small);
     if (c->d_small_theory) cudaFree(c->d_small_theory);
+    if (c->tiny_xi) cudaFree(c->tiny_xi);
+    if (c->tiny_tickets) cudaFree(c->tiny_tickets);
     delete c;
 }
 
@@ -486,8 +661,15 @@ int vb200_create(const vb200_model_tables *m, const vb200_fit_tables *f, int dev
     d.kaiser_shift = m->kaiser_coord_shift;
     d.niter = m->niter;
     for (int i = 0; i < kMaxPoles; ++i) d.ells[i] = m->ells[i];
-    // (beta-dependent or empirically corrected velocity tables only change the prologue: still the tuned kernel)
-    c->tuned = (m->rsd_model == VB200_RSD_STREAMING && m->n_ell == 1 && !m->realspace_from_data && m->sv_ny == 0);
+    // (beta-dependent or empirically corrected velocity tables only change the prologue: still the tuned kernels)
+    {
+        const bool vel_integral = m->rsd_model == VB200_RSD_STREAMING || m->rsd_model == VB200_RSD_DISPERSION;
+        bool ells_ok = m->ells[0] == 0;
+        for (int i = 1; i < m->n_ell; ++i) ells_ok = ells_ok && m->ells[i] == 2 * i;
+        c->family = kGeneral;
+        if (vel_integral && ells_ok && !m->realspace_from_data && m->sv_ny == 0)
+            c->family = (m->rsd_model == VB200_RSD_STREAMING && m->n_ell == 1) ? kTunedIso : kTunedWide;
+    }
     const size_t nc4 = (size_t)m->ncell * 4;
     if ((rc = upload(c, m->origin, (size_t)m->ncell, &d.origin))) return bail(rc);
     if ((rc = upload(c, m->upper, (size_t)m->ncell, &d.upper))) return bail(rc);
@@ -521,6 +703,11 @@ int vb200_create(const vb200_model_tables *m, const vb200_fit_tables *f, int dev
     double etab[kExpTab];
     fill_exp_table(etab);
     if ((rc = upload(c, etab, (size_t)kExpTab, &d.exp_tab))) return bail(rc);
+    {
+        std::vector<double> big(kExpTabBig);
+        fill_exp_table(big.data(), kExpTabBig);
+        if ((rc = upload(c, big.data(), big.size(), &d.exp_tab_big))) return bail(rc);
+    }
     for (int i = 0; i < m->nbucket; ++i) c->has_flags = c->has_flags || (m->bucket_base[i] < 0);
     for (int i = 0; i < m->nx; ++i) {
         c->xw[i] = m->x[i];
@@ -569,11 +756,24 @@ int vb200_create(const vb200_model_tables *m, const vb200_fit_tables *f, int dev
     // allow the large dynamic shared memory carve-out (dense mu grids stage up to ~200 KB)
     c->k1_smem_limit = std::min<size_t>((size_t)prop.sharedMemPerBlockOptin, (size_t)200 * 1024);
     std::vector<const void *> fns;
-    for (int v = 0; v < 32; ++v) fns.push_back((const void *)pick_k1(v & 1, v & 2, 1 << ((v >> 2) & 3), (v & 16) ? 5 : 6));
+    const int exps[] = {5, 53, 6, 3, 30};
+    for (int fl = 0; fl < 2; ++fl) {
+        fns.push_back((const void *)pick_k1(false, fl, 1, 6, 3).fn);
+        fns.push_back((const void *)pick_k1(true, fl, 1, kDefExp, kDefNewton).fn);
+        for (int e : exps)
+            for (int nw = 2; nw <= 3; ++nw) fns.push_back((const void *)pick_k1(true, fl, 4, e, nw).fn);
+        fns.push_back((const void *)pick_k1_fused(true, fl, 4, kDefExp, kDefNewton));
+        for (int r = 0; r < 2; ++r)
+            for (int l = 1; l <= 3; ++l)
+                for (int ilp = 2; ilp <= 4; ilp += 2)
+                    for (int nw = 2; nw <= 3; ++nw)
+                        if (r || l > 1) fns.push_back((const void *)pick_k1_wide(r, l, fl, ilp, nw));
+    }
     for (int r = 0; r < 6; ++r) fns.push_back((const void *)pick_general(r >> 1, r & 1));
-    for (int fl = 0; fl < 2; ++fl) fns.push_back((const void *)pick_k1(true, fl, 4, 5, 2));
-    for (int fl = 0; fl < 2; ++fl) fns.push_back((const void *)pick_k1_fused(true, fl, 4, 5, 3));
     for (int r = 0; r < 3; ++r) fns.push_back((const void *)pick_general_fused(r, true));
+    for (int fl = 0; fl < 2; ++fl)
+        for (int r = 0; r < 2; ++r)
+            for (int l = 1; l <= 3; ++l) fns.push_back((const void *)pick_small(r, l, fl));
     for (const void *fn : fns) {
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k1_smem_limit);
         if (e != cudaSuccess)
@@ -592,12 +792,16 @@ int vb200_set_option(vb200_ctx *c, const char *key, int64_t value) {
     else if (!strcmp(key, "fast_math")) c->opt_fast = value ? 1 : 0;
     else if (!strcmp(key, "nsplit")) c->opt_nsplit = (int)value;
     else if (!strcmp(key, "fuse")) c->opt_fuse = (int)std::max<int64_t>(0, std::min<int64_t>(value, 2));
+    else if (!strcmp(key, "tuned")) c->opt_tuned = value ? 1 : 0;
+    else if (!strcmp(key, "tiny")) c->opt_tiny = value ? 1 : 0;
     else if (!strcmp(key, "newton")) {
-        if (value != 2 && value != 3) return fail(VB200_EINVAL, "newton must be 2 (one Newton step) or 3 (cubic step)");
+        if (value != 0 && value != 2 && value != 3)
+            return fail(VB200_EINVAL, "newton must be 0 (default), 2 (one Newton step) or 3 (cubic step)");
         c->opt_newton = (int)value;
     } else if (!strcmp(key, "ilp")) c->opt_ilp = value >= 4 ? 4 : (value >= 2 ? 2 : 1);
     else if (!strcmp(key, "exp_degree")) {
-        if (value != 5 && value != 6) return fail(VB200_EINVAL, "exp_degree must be 5 or 6");
+        if (value != 0 && value != 5 && value != 6 && value != 53 && value != 3 && value != 30)
+            return fail(VB200_EINVAL, "exp_degree must be 0 (default), 3, 30, 5, 53 or 6");
         c->opt_expdeg = (int)value;
     } else if (!strcmp(key, "threads")) {
         if (value < 32 || value > 256 || value % 32) return fail(VB200_EINVAL, "threads must be 32..256, multiple of 32");
@@ -738,10 +942,21 @@ int vb200_likelihood(vb200_ctx *c, const double *params, int64_t n, double *theo
         !is_device_ptr(lnlike)) {
         // one pinned H2D of the rows, two launches, one pinned D2H of (chi2 | lnL), one sync -- replayed as a
         // CUDA graph (one submission instead of four) while n and the options stay the same
-        if (!c->pin) {
-            CK(cudaMallocHost(&c->pin, (size_t)kSmallCall * (VB200_NPAR + 2) * sizeof(double)));
-            CK(cudaMalloc(&c->d_small, (size_t)kSmallCall * (VB200_NPAR + 2) * sizeof(double)));
-            CK(cudaMalloc(&c->d_small_theory, (size_t)kSmallCall * p * sizeof(double)));
+        if (!c->pin || !c->d_small || !c->d_small_theory) {
+            // all three or none: a failed allocation must not leave a half-initialised staging set behind
+            double *pin = nullptr, *d_small = nullptr, *d_theory = nullptr;
+            cudaError_t e = cudaMallocHost(&pin, (size_t)kSmallCall * (VB200_NPAR + 2) * sizeof(double));
+            if (e == cudaSuccess) e = cudaMalloc(&d_small, (size_t)kSmallCall * (VB200_NPAR + 2) * sizeof(double));
+            if (e == cudaSuccess) e = cudaMalloc(&d_theory, (size_t)kSmallCall * p * sizeof(double));
+            if (e != cudaSuccess) {
+                if (pin) cudaFreeHost(pin);
+                if (d_small) cudaFree(d_small);
+                if (d_theory) cudaFree(d_theory);
+                return fail(VB200_ENOMEM, std::string("small-call staging: ") + cudaGetErrorString(e));
+            }
+            c->pin = pin;
+            c->d_small = d_small;
+            c->d_small_theory = d_theory;
         }
         double *h_out = c->pin + (size_t)kSmallCall * VB200_NPAR;
         memcpy(c->pin, params, (size_t)n * VB200_NPAR * sizeof(double));
@@ -773,8 +988,7 @@ int vb200_likelihood(vb200_ctx *c, const double *params, int64_t n, double *theo
     double *d_theory = theory;
     // chi2 / lnL from the epilogue of K1: the theory vectors only leave the SM if the caller wants them
     const bool will_fuse = (chi2 || lnlike) && pick_nsplit(c, n, c->fit_ns, false) == 1 && fused_variant(c) &&
-                           (c->tuned ? k1_smem_bytes(c->md.ncell, c->fit_ns, c->fit_nmu, c->md.nbucket, fused_fit_doubles(p))
-                                     : k1g_smem_bytes(c->md.ncell, c->fit_ns, c->fit_nmu, c->md.nbucket, fused_fit_doubles(p))) <=
+                           k1_smem_for(c, c->fit_ns, c->fit_nmu, fused_fit_doubles(p)) <=
                                std::min<size_t>(c->k1_smem_limit, (size_t)56 * 1024);
     if (!theory && will_fuse) {
         d_theory = nullptr;
@@ -795,6 +1009,16 @@ int vb200_likelihood(vb200_ctx *c, const double *params, int64_t n, double *theo
         d_lnl = c->sc_lnl.ptr;
     }
     const bool theory_to_host = theory && d_theory != theory;
+    if ((chi2 || lnlike) && use_small(c, n)) {
+        // a handful of rows (device buffers, or the theory vectors wanted too): still one launch
+        if ((rc = launch_small(c, d_params, n, theory ? d_theory : nullptr, d_chi2, d_lnl, st))) return rc;
+        if (theory_to_host) CK(cudaMemcpyAsync(theory, d_theory, (size_t)n * p * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (chi2 && d_chi2 != chi2) CK(cudaMemcpyAsync(chi2, d_chi2, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (lnlike && d_lnl != lnlike)
+            CK(cudaMemcpyAsync(lnlike, d_lnl, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (host_io) CK(cudaStreamSynchronize(st));
+        return VB200_OK;
+    }
     const int nchunks = theory_to_host ? plan_chunks(c, n, (size_t)n * p * sizeof(double)) : 1;
     if (nchunks > 1 && (rc = ensure_copy_stream(c, nchunks))) return rc;
     const int64_t per = (n + nchunks - 1) / nchunks;
@@ -831,152 +1055,6 @@ int vb200_likelihood(vb200_ctx *c, const double *params, int64_t n, double *theo
     if (lnlike && d_lnl != lnlike)
         CK(cudaMemcpyAsync(lnlike, d_lnl, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (host_io) CK(cudaStreamSynchronize(st));
-    return VB200_OK;
-}
-
-int vb200_math_selftest(int device, const double *x, int64_t n, double *out) {
-    if (!x || !out || n <= 0) return fail(VB200_EINVAL, "bad arguments");
-    DeviceGuard g(device);
-    if (!g.ok) return fail(VB200_ECUDA, "cudaSetDevice failed");
-    double *dx = nullptr, *dout = nullptr, *dtab = nullptr;
-    double etab[kExpTab];
-    fill_exp_table(etab);
-    CK(cudaMalloc(&dx, n * sizeof(double)));
-    CK(cudaMalloc(&dout, 4 * n * sizeof(double)));
-    CK(cudaMalloc(&dtab, sizeof(etab)));
-    CK(cudaMemcpy(dx, x, n * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dtab, etab, sizeof(etab), cudaMemcpyHostToDevice));
-    k_math_selftest<<<(unsigned)((n + 255) / 256), 256>>>(dx, n, dtab, dout);
-    CK(cudaGetLastError());
-    CK(cudaMemcpy(out, dout, 4 * n * sizeof(double), cudaMemcpyDeviceToHost));
-    cudaFree(dx);
-    cudaFree(dout);
-    cudaFree(dtab);
-    return VB200_OK;
-}
-
-int vb200_pipe_probe(int device, int mode, int iters, double *ms) {
-    if (!ms || iters < 1 || mode < 0 || mode > 6) return fail(VB200_EINVAL, "bad arguments");
-    DeviceGuard g(device);
-    if (!g.ok) return fail(VB200_ECUDA, "cudaSetDevice failed");
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
-    double *d = nullptr;
-    CK(cudaMalloc(&d, sizeof(double)));
-    const int blocks = prop.multiProcessorCount * 8, threads = 256;
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
-    auto run = [&](int it) {
-        switch (mode) {
-            case 0: k_pipe_probe<0><<<blocks, threads>>>(d, it, 0.999999, 1e-9); break;
-            case 1: k_pipe_probe<1><<<blocks, threads>>>(d, it, 0.999999, 1e-9); break;
-            case 2: k_pipe_probe<2><<<blocks, threads>>>(d, it, 0.999999, 1e-9); break;
-            case 3: k_pipe_probe<3><<<blocks, threads>>>(d, it, 0.999999, 1e-9); break;
-            case 4: k_pipe_probe<4><<<blocks, threads>>>(d, it, 0.999999, 1e-9); break;
-            case 5: k_pipe_probe<5><<<blocks, threads>>>(d, it, 0.999999, 1e-9); break;
-            default: k_pipe_probe<6><<<blocks, threads>>>(d, it, 0.999999, 1e-9); break;
-        }
-    };
-    run(iters / 4 + 1);
-    CK(cudaEventRecord(e0));
-    run(iters);
-    CK(cudaEventRecord(e1));
-    CK(cudaEventSynchronize(e1));
-    CK(cudaGetLastError());
-    float t = 0.f;
-    CK(cudaEventElapsedTime(&t, e0, e1));
-    *ms = t;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(d);
-    return VB200_OK;
-}
-
-int vb200_mix_probe(int device, int chains, int mix, int kind, int blocks_per_sm, int iters, double *ms) {
-    if (!ms || iters < 1 || blocks_per_sm < 1) return fail(VB200_EINVAL, "bad arguments");
-    DeviceGuard g(device);
-    if (!g.ok) return fail(VB200_ECUDA, "cudaSetDevice failed");
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
-    double *d = nullptr;
-    CK(cudaMalloc(&d, 128 * sizeof(double)));
-    {
-        double h[128];
-        for (int i = 0; i < 128; ++i) h[i] = (i < 33) ? 0.999999 - 1e-9 * i : 1e-9 + 1e-12 * i;
-        CK(cudaMemcpy(d, h, sizeof(h), cudaMemcpyHostToDevice));
-    }
-    const int blocks = prop.multiProcessorCount * blocks_per_sm;
-    typedef void (*fn_t)(double *, int, double, double, int);
-    fn_t fn = nullptr;
-#define VB_MIX(C, M, K) if (chains == C && mix == M && kind == K) fn = k_mix_probe<C, M, K>;
-    VB_MIX(1, 0, 0) VB_MIX(2, 0, 0) VB_MIX(4, 0, 0) VB_MIX(8, 0, 0)
-    VB_MIX(4, 1, 0) VB_MIX(4, 2, 0) VB_MIX(8, 1, 0) VB_MIX(2, 1, 0)
-    VB_MIX(4, 1, 1) VB_MIX(8, 1, 1) VB_MIX(2, 1, 1)
-    VB_MIX(4, 0, 2) VB_MIX(8, 0, 2)
-    VB_MIX(4, 0, 3) VB_MIX(4, 0, 4)
-    VB_MIX(8, 0, 5) VB_MIX(8, 0, 6) VB_MIX(8, 0, 7) VB_MIX(4, 0, 5) VB_MIX(4, 0, 6) VB_MIX(4, 0, 7)
-#undef VB_MIX
-    if (!fn) return fail(VB200_EINVAL, "no such probe variant");
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
-    fn<<<blocks, 128>>>(d, iters / 4 + 1, 0.999999, 1e-9, 3);
-    CK(cudaEventRecord(e0));
-    fn<<<blocks, 128>>>(d, iters, 0.999999, 1e-9, 3);
-    CK(cudaEventRecord(e1));
-    CK(cudaEventSynchronize(e1));
-    CK(cudaGetLastError());
-    float t = 0.f;
-    CK(cudaEventElapsedTime(&t, e0, e1));
-    *ms = t;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(d);
-    return VB200_OK;
-}
-
-int vb200_seed_probe(int device, const double *x, int64_t n, double *out) {
-    if (!x || !out || n <= 0) return fail(VB200_EINVAL, "bad arguments");
-    DeviceGuard g(device);
-    if (!g.ok) return fail(VB200_ECUDA, "cudaSetDevice failed");
-    double *dx = nullptr, *dout = nullptr;
-    CK(cudaMalloc(&dx, n * sizeof(double)));
-    CK(cudaMalloc(&dout, 2 * n * sizeof(double)));
-    CK(cudaMemcpy(dx, x, n * sizeof(double), cudaMemcpyHostToDevice));
-    k_seed_probe<<<(unsigned)((n + 255) / 256), 256>>>(dx, n, dout);
-    CK(cudaGetLastError());
-    CK(cudaMemcpy(out, dout, 2 * n * sizeof(double), cudaMemcpyDeviceToHost));
-    cudaFree(dx);
-    cudaFree(dout);
-    return VB200_OK;
-}
-
-int vb200_fp64_peak(int device, int iters, double *tflops, double *ms) {
-    if (!tflops || iters < 1) return fail(VB200_EINVAL, "bad arguments");
-    DeviceGuard g(device);
-    if (!g.ok) return fail(VB200_ECUDA, "cudaSetDevice failed");
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
-    double *d = nullptr;
-    CK(cudaMalloc(&d, sizeof(double)));
-    const int blocks = prop.multiProcessorCount * 8, threads = 256;
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
-    k_fp64_peak<<<blocks, threads>>>(d, iters / 4 + 1, 0.999999, 1e-9);  // warm-up
-    CK(cudaEventRecord(e0));
-    k_fp64_peak<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
-    CK(cudaEventRecord(e1));
-    CK(cudaEventSynchronize(e1));
-    float t = 0.f;
-    CK(cudaEventElapsedTime(&t, e0, e1));
-    const double fma_count = (double)blocks * threads * (double)iters * 64.0;
-    *tflops = 2.0 * fma_count / (t * 1e-3) / 1e12;
-    if (ms) *ms = t;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(d);
     return VB200_OK;
 }
 

@@ -9,6 +9,7 @@ namespace vb200 {
 
 constexpr int kMaxPoles = 3;
 constexpr int kExpTab = 32;
+constexpr int kExpTabBig = 1024;  // 2^(j/1024): exp variants 3 / 30 (degree-3 remainder polynomial)
 constexpr int kMaxNx = 128;       // velocity nodes that fit in the kernel-parameter table
 constexpr int kBucketFlag = (int)0x80000000;
 constexpr int kNPar = 10;         // doubles per parameter row (VB200_NPAR)
@@ -26,6 +27,7 @@ struct ModelDev {
     const int *bucket_base;
     const double *beta_grid, *xi_tab, *v0, *d0, *sv, *x, *wx, *mu_resc, *w_resc;
     const double *exp_tab;  // [kExpTab] 2^(j/32)
+    const double *exp_tab_big;  // [kExpTabBig] 2^(j/1024)
     const double *sv2d;     // [ncell][sv_ny][4][4] bicubic sigma_v(u, mu) patches (sv_ny > 0), else null
     const double *sv_yb;    // [sv_ny + 1] mu breakpoints
     int sv_ny;
@@ -206,6 +208,13 @@ __device__ __forceinline__ double gauss_tab(double z2, unsigned etab_s) {
 // zs^2 only ever appears inside an FMA (exact product, one instruction and four register reads
 // fewer than forming z^2 first).  kGaussScale is folded into the sigma_v table by the caller.
 constexpr double kGaussScale = 4.804489635145799;   // sqrt(16 log2(e))
+__constant__ float kExpPoly5f[5] = {2.166084939249829e-02f, 2.345961981994449e-04f, 1.6938509724285119e-06f,
+                                    9.172607532092245e-09f, 3.9737238568525983e-11f};
+
+// kDeg: 6 Taylor, 5 economised, 52 / 53 economised with the two / three highest Horner steps in FP32:
+// the remainder satisfies |r ln2 / 32| <= 0.011, so the part of the polynomial multiplying r^3 (52) or
+// r^2 (53) contributes at most 2e-7 / 6e-5 of the result and its FP32 rounding 1.2e-14 / 3.6e-12 -- the
+// FP32 pipe and the two conversions (XU pipe) run beside the FP64 pipe, which is the bound.
 template <int kDeg>
 __device__ __forceinline__ double gauss_tab_scaled(double zs, unsigned etab_s) {
     const double kMagic = 6755399441055744.0;   // 1.5 * 2^52
@@ -220,6 +229,15 @@ __device__ __forceinline__ double gauss_tab_scaled(double zs, unsigned etab_s) {
         p = fma(p, r, kExpPoly[2]);
         p = fma(p, r, kExpPoly[1]);
         p = fma(p, r, kExpPoly[0]);
+    } else if (kDeg == 52) {
+        const float rf = __double2float_rn(r);
+        const float pf = fmaf(fmaf(kExpPoly5f[4], rf, kExpPoly5f[3]), rf, kExpPoly5f[2]);
+        p = fma((double)pf, r, kExpPoly5[1]);
+        p = fma(p, r, kExpPoly5[0]);
+    } else if (kDeg == 53) {
+        const float rf = __double2float_rn(r);
+        const float pf = fmaf(fmaf(fmaf(kExpPoly5f[4], rf, kExpPoly5f[3]), rf, kExpPoly5f[2]), rf, kExpPoly5f[1]);
+        p = fma((double)pf, r, kExpPoly5[0]);
     } else {
         p = fma(kExpPoly5[4], r, kExpPoly5[3]);
         p = fma(p, r, kExpPoly5[2]);
@@ -229,6 +247,40 @@ __device__ __forceinline__ double gauss_tab_scaled(double zs, unsigned etab_s) {
     p = fma(p, r, 1.0);
     const int n = max(ni >> 5, -1000);
     double t = lds_f64(etab_s + ((ni & (kExpTab - 1)) << 3));
+    t = __hiloint2double(__double2hiint(t) + (n << 20), __double2loint(t));
+    return p * t;
+}
+
+// exp(-z^2/2) from a 1024-entry table 2^(j/1024): zs = z sqrt(512 log2 e), -z^2/2 = -(zs^2) ln2 / 1024.
+// The remainder |r ln2 / 1024| <= 3.4e-4 needs a degree-3 polynomial only (economised, max relative error
+// 1.4e-16 -- the same as the degree-5 one on the 32-entry table): two FP64 instructions fewer.
+//   kCvt: n = round(-zs^2) and its value back as a double through the conversion unit (F2I / I2F run on the
+//   XU pipe beside the FP64 pipe; F2I saturates, so a huge z gives exp = 0 instead of a wrapped exponent)
+//   instead of the 1.5 * 2^52 magic-number FMA + subtraction: one more FP64 instruction off the pipe.  zs^2 is
+//   then rounded once (relative 1.1e-16, i.e. z^2/2 * 1.1e-16 relative in the result -- the conditioning of
+//   exp(-z^2/2) itself, and what libm's exp(-0.5 * z * z) carries too).
+constexpr double kGaussScaleBig = 27.178297609216609367;   // sqrt(512 log2(e))
+__constant__ double kExpPoly3[3] = {0.0006769015435155716, 2.2909785144706367e-07, 5.169222960550727e-11};
+
+template <bool kCvt>
+__device__ __forceinline__ double gauss_big(double zs, unsigned etab_s) {
+    int ni;
+    double r;
+    if (kCvt) {
+        const double q = zs * zs;
+        asm("cvt.rni.s32.f64 %0, %1;" : "=r"(ni) : "d"(-q));
+        r = -q - (double)ni;
+    } else {
+        const double kMagic = 6755399441055744.0;   // 1.5 * 2^52
+        const double tn = fma(-zs, zs, kMagic);
+        ni = __double2loint(tn);
+        r = fma(-zs, zs, -(tn - kMagic));
+    }
+    double p = fma(kExpPoly3[2], r, kExpPoly3[1]);
+    p = fma(p, r, kExpPoly3[0]);
+    p = fma(p, r, 1.0);
+    const int n = max(ni >> 10, -1000);
+    double t = lds_f64(etab_s + ((ni & (kExpTabBig - 1)) << 3));
     t = __hiloint2double(__double2hiint(t) + (n << 20), __double2loint(t));
     return p * t;
 }

@@ -7,17 +7,35 @@ namespace vb200 {
 // ---------------------------------------------------------------------------------------
 // math self-test kernel
 // ---------------------------------------------------------------------------------------
+constexpr int kSelftestOutputs = 10;
+
 __global__ void k_math_selftest(const double *x, long long n, const double *etab, double *out) {
     __shared__ double tab[kExpTab];
+    __shared__ double big[kExpTabBig];
     if (threadIdx.x < kExpTab) tab[threadIdx.x] = etab[threadIdx.x];
+    for (int j = threadIdx.x; j < kExpTabBig; j += blockDim.x) big[j] = etab[kExpTab + j];
     __syncthreads();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double v = x[i];
-    out[i] = gauss_tab<6>(v, (unsigned)__cvta_generic_to_shared(tab));   // exp(-v/2)
+    const unsigned tab_s = (unsigned)__cvta_generic_to_shared(tab);
+    out[i] = gauss_tab<6>(v, tab_s);   // exp(-v/2)
     out[n + i] = fast_rsqrt(v);
     out[2 * n + i] = rcp_cubic(v);
-    out[3 * n + i] = gauss_tab<5>(v, (unsigned)__cvta_generic_to_shared(tab));
+    out[3 * n + i] = gauss_tab<5>(v, tab_s);
+    // the scaled-argument forms the tuned kernel uses: zs = sqrt(v) sqrt(16 log2 e)
+    const double zs = sqrt(v) * kGaussScale;
+    out[4 * n + i] = gauss_tab_scaled<52>(zs, tab_s);
+    out[5 * n + i] = gauss_tab_scaled<53>(zs, tab_s);
+    double u, mur;
+    radius<2>(v, 1.0, u, mur);         // one Newton step: mur = 1 / sqrt(v)
+    out[6 * n + i] = mur;
+    out[7 * n + i] = rcp_newton(v);
+    // 1024-entry table, degree-3 remainder ("exp_degree" 3: conversion-unit range reduction; 30: magic-number FMA)
+    const unsigned big_s = (unsigned)__cvta_generic_to_shared(big);
+    const double zb = sqrt(v) * kGaussScaleBig;
+    out[8 * n + i] = gauss_big<true>(zb, big_s);
+    out[9 * n + i] = gauss_big<false>(zb, big_s);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -159,6 +177,45 @@ __global__ void __launch_bounds__(128) k_mix_probe(double *out, int iters, doubl
         t += n[c];
     }
     if (s == 12345.678 || t == 123456789) out[0] = s + t;
+}
+
+// Load-path probe: a cubic's four coefficients per lane and evaluation, fetched either from shared memory
+// (2 x LDS.128, the kernels' way) or from the kernel-parameter constant bank with a per-lane index (4 x LDC.64),
+// followed by the three Horner DFMAs.  `distinct` = different cells among the 32 lanes of a warp (1 = broadcast).
+// Answers: is the constant path a usable second source of per-lane table data beside the shared-memory crossbar?
+struct LoadProbeArgs {
+    double tab[128 * 4];   // 128 cells x 4 coefficients = 4 KB of kernel parameters (constant bank 0)
+    double *out;
+    int iters, distinct, stride;
+};
+
+template <int kPath>
+__global__ void __launch_bounds__(256) k_load_probe(const __grid_constant__ LoadProbeArgs a) {
+    __shared__ __align__(16) double sh[128 * 4];
+    for (int i = threadIdx.x; i < 128 * 4; i += blockDim.x) sh[i] = a.tab[i];
+    __syncthreads();
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(sh);
+    const int lane = threadIdx.x & 31;
+    int cell = (lane * a.distinct) >> 5;
+    double t = 1e-3 * threadIdx.x, acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    for (int i = 0; i < a.iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            double c0, c1, c2, c3;
+            const int c = (cell + r * a.stride) & 127;
+            if (kPath == 0) {
+                const double2 c01 = lds_f64x2(sbase + c * 32), c23 = lds_f64x2(sbase + c * 32 + 16);
+                c0 = c01.x; c1 = c01.y; c2 = c23.x; c3 = c23.y;
+            } else {
+                c0 = a.tab[c * 4]; c1 = a.tab[c * 4 + 1]; c2 = a.tab[c * 4 + 2]; c3 = a.tab[c * 4 + 3];
+            }
+            const double v = fma(fma(fma(c3, t, c2), t, c1), t, c0);
+            if (r == 0) acc0 += v; else if (r == 1) acc1 += v; else if (r == 2) acc2 += v; else acc3 += v;
+        }
+        cell = (cell + 1) & 127;
+    }
+    const double s = (acc0 + acc1) + (acc2 + acc3);
+    if (s == 12345.678) a.out[0] = s;
 }
 
 // raw MUFU seeds (no refinement): out[0..n) = rsqrt.approx(x), out[n..2n) = rcp.approx(x)

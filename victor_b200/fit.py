@@ -181,20 +181,15 @@ class CCFFit(CCFModel):
                 "mu": mu, "wmu": wmu}
 
     def _fit_engine(self, kwargs):
-        # the reference feeds the same kwargs to the fit options and to the model options
-        # (ccf_fit.py:379-381, 444)
-        if not kwargs:   # the MCMC step: no overrides, reuse the resolved engine
-            cached = getattr(self, "_default_engine", None)
-            if cached is not None and cached[0].handle:
-                return cached
+        # the reference rebuilds its options from self.model / self.fit_options on every call and feeds the
+        # same kwargs to the fit options and to the model options (ccf_fit.py:379-381, 444; ccf_model.py:565-567),
+        # so a user may change either dict between calls: the engine is looked up by the resolved option key
+        # every time (a tuple compare; the tables are only rebuilt for a key not seen before)
         fit_options = dict(self.fit_options)
         fit_options.update(kwargs)
         opts = self._merged_options(kwargs)
         opts["likelihood"] = fit_options["likelihood"]
-        out = (self._engine(opts, need_fit=True), fit_options)
-        if not kwargs:
-            self._default_engine = out
-        return out
+        return self._engine(opts, need_fit=True), fit_options
 
     def log_likelihood_batch(self, params, return_theory=False, **kwargs):
         """(lnlike[n], chisq[n]) for every parameter row, optionally with the theory vectors."""
@@ -206,6 +201,37 @@ class CCFFit(CCFModel):
         if log.isEnabledFor(10) and len(lnl) > 1:    # logging.DEBUG
             log.debug("log_likelihood_batch: %d rows, %d failed (-inf)", len(lnl), int(np.count_nonzero(lnl == -np.inf)))
         return (lnl, chi2, theory) if return_theory else (lnl, chi2)
+
+    def log_likelihood_device(self, params, out=None, stream=None, **kwargs):
+        """Device-resident form of ``log_likelihood_batch``: returns ``(lnlike, chisq)`` as float64 CUDA
+        tensors on this fit's GPU, asynchronously on ``stream`` (a ``torch.cuda.Stream``, default: the current
+        one).  ``params`` is a float64 CUDA tensor ``[n, 10]`` in the row layout of ``params_to_rows`` (used in
+        place) or anything ``params_to_rows`` accepts (copied to the device once).  ``out`` = a float64 CUDA
+        tensor ``[2, m >= n]`` to write (lnlike | chisq) into, e.g. a slot of a gather buffer.
+        Nothing is copied back to the host; torch tensors are only the buffers (data_ptr) handed to the C ABI."""
+        import torch
+        eng, fit_options = self._fit_engine(kwargs)
+        if fit_options["beta_interpolation"] == "likelihood" and not self.fixed_data:
+            raise NotImplementedError("log_likelihood_device: beta_interpolation 'likelihood' blends two evaluations "
+                                      "on the host; use log_likelihood_batch")
+        dev = torch.device("cuda", eng.device)
+        if isinstance(params, torch.Tensor):
+            rows = params
+            if rows.device != dev or rows.dtype != torch.float64 or rows.dim() != 2 or rows.shape[1] != 10 \
+                    or not rows.is_contiguous():
+                raise ValueError(f"params tensor must be contiguous float64 [n, 10] on {dev}")
+        else:
+            rows = torch.from_numpy(params_to_rows(params)).to(dev, non_blocking=True)
+        n = rows.shape[0]
+        if out is None:
+            out = torch.empty((2, n), dtype=torch.float64, device=dev)
+        elif out.device != dev or out.dtype != torch.float64 or out.dim() != 2 or out.shape[0] != 2 \
+                or out.shape[1] < n or out.stride(1) != 1:
+            raise ValueError(f"out must be a float64 [2, m >= {n}] tensor on {dev} with contiguous rows")
+        st = torch.cuda.current_stream(dev) if stream is None else stream
+        if n:
+            eng.likelihood_ptr(rows.data_ptr(), n, None, out[1].data_ptr(), out[0].data_ptr(), st.cuda_stream)
+        return out[0, :n], out[1, :n]
 
     def _likelihood_interpolated(self, eng, rows, return_theory):
         """'likelihood' beta mode (ccf_fit.py:383-440): evaluate at the two bracketing grid

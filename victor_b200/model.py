@@ -331,7 +331,7 @@ class CCFModel:
                opts["matter_model"], opts["mean_model"], bool(opts["empirical_corr"]),
                bool(opts["realspace_ccf_from_data"]), bool(opts.get("kaiser_approximation", False)),
                bool(opts.get("kaiser_coord_shift", True)), int(opts.get("velocity_nodes", 50)),
-               int(opts.get("mu_nodes", 100)), float(opts.get("bias", 1.9)),
+               int(opts.get("mu_nodes", 100)), float(opts.get("bias", 1.9)), int(opts.get("niter", 5)),
                self._fit_key(opts) if need_fit else None)
         eng = self._engines.get(key)
         if eng is None:

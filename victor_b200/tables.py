@@ -465,7 +465,8 @@ def build_model_tables(state, options, nx=50):
         template_fsigma8=template_fsigma8, growth_scale=growth_scale, v0b=v0b, d0b=d0b,
         sv2d=sv2d, sv_ybreaks=sv_ybreaks, from_data=bool(options["realspace_ccf_from_data"]),
         kaiser_approximation=bool(options.get("kaiser_approximation", False)),
-        kaiser_coord_shift=bool(options.get("kaiser_coord_shift", True)), niter=5)
+        kaiser_coord_shift=bool(options.get("kaiser_coord_shift", True)),
+        niter=int(options.get("niter", 5)))    # model.get('niter', 5), ccf_model.py:661, 701, 752
 
 
 def likelihood_constants(like, p):
@@ -512,18 +513,27 @@ def build_fit_tables(fit, like):
     lam = np.ones((nbc, p))
     use_logdet = not fit.fixed_covmat
     if use_logdet:
+        # The reference takes slogdet of the blended covariance per evaluation and returns (-inf, inf) for a point
+        # whose matrix is not positive definite (ccf_fit.py:445-450).  A grid matrix that fails the check gets NaN
+        # here: every row whose bracket uses it then ends in the NaN guard, (-inf, +inf); the other rows are served.
+        good = np.zeros(nbc, dtype=bool)
         for i in range(nbc):
             sign, ld = np.linalg.slogdet(cov[i])
             try:
                 np.linalg.cholesky(cov[i])
             except np.linalg.LinAlgError:
                 sign = 0
-            if sign != 1:
-                raise InputError(f"covariance matrix {i} is not positive definite; the reference would "
-                                 "return (-inf, inf) or an unnormalised likelihood for it")
-            logdet[i] = ld
+            good[i] = sign == 1
+            logdet[i] = ld if good[i] else np.nan
         for i in range(nbc - 1):
-            lam[i] = eigh(cov[-1], cov[i], eigvals_only=True)
+            if good[i] and good[-1]:
+                lam[i] = eigh(cov[-1], cov[i], eigvals_only=True)
+            else:
+                lam[i] = np.nan
+        if not good.all():
+            from .utils import log
+            log.warning("covariance matrices %s of the beta grid are not positive definite: parameter points that "
+                        "use them evaluate to (-inf, inf)", np.flatnonzero(~good).tolist())
     kind, a, nm1 = likelihood_constants(like, p)
     return FitTables(p=p, data_beta_dependent=not fit.fixed_data, beta_ccf=beta_ccf,
                      data_tab=np.ascontiguousarray(data_tab), cov_fixed=bool(fit.fixed_covmat),
