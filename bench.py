@@ -380,7 +380,7 @@ def extra_dispersion(job, fit, n, steps):
                                                     d_lnl.data_ptr(), None), steps, 1)
     k1 = job.timed_steps(lambda: eng.likelihood_ptr(d_params.data_ptr(), n, d_theory.data_ptr(), None, None, None),
                          steps, 0)
-    finite = bool(torch.isfinite(d_lnl).all())
+    nonfinite = int((~torch.isfinite(d_lnl)).sum())
 
     def finish(step_ms, k1_ms):
         fl = flop_k1(NS, NMU, NX, L, rsd="dispersion")
@@ -388,7 +388,9 @@ def extra_dispersion(job, fit, n, steps):
                 "value": n * job.world / (step_ms * 1e-3), "unit": UNIT, "ms_per_step": step_ms, "steps": steps,
                 "roofline": roofline_block("k_multipoles<dispersion>", n, fl, k1_ms,
                                            {"flop_per_point": FLOP_POINT["dispersion"]}),
-                "lnl_finite": finite}
+                # the reference's fixed-point coordinate iteration diverges for a few prior-box rows (high growth,
+                # large separation): those end in its NaN guard, (-inf, inf), on the CPU too
+                "nonfinite_rows_rank0": nonfinite}
     return [sum(ms) / len(ms), sum(k1) / len(k1)], finish
 
 

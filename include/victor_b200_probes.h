@@ -44,6 +44,11 @@ int vb200p_mix_probe(int device, int chains, int mix, int kind, int blocks_per_s
  * among the lanes of a warp, `stride` = cell distance between the four cubics of one trip; blocks of 256 threads. */
 int vb200p_load_probe(int device, int path, int distinct, int stride, int blocks_per_sm, int iters, double *ms);
 
+/* Quadratic forms q[i] = r_i^T P r_i of n HOST rows R [n][64] against one HOST matrix P [64][64] (p = 60 padded with
+ * zeros): kind 0 = warp-tiled FMA (k_chi2's arrangement), kind 1 = FP64 DMMA (mma.sync m8n8k4).  ms = average kernel
+ * time over `reps` launches; q = results (for the equality check). */
+int vb200p_quad_probe(int device, int kind, const double *R, const double *P, int64_t n, int reps, double *q, double *ms);
+
 /* FP64 FMA issue-rate probe (8 independent DFMA chains per thread, whole GPU).  tflops counts 2 flop
  * per FMA.  A side figure: rooflines are quoted against the nominal FP64 peak. */
 int vb200p_fp64_peak(int device, int iters, double *tflops, double *ms);

@@ -41,7 +41,7 @@ def main():
     print("CCFFit.log_likelihood(dict)            us median/p95:", med(lambda: fit.log_likelihood(prm)))
     st = {}
     print("CCFLikelihood.calculate(**dict)        us median/p95:", med(lambda: like.calculate(st, **prm)))
-    for opt, val in (("tiny", 0), ("graph", 0), ("tiny", 1), ("graph", 1)):
+    for opt, val in (("mapped", 0), ("tiny", 0), ("graph", 0), ("tiny", 1), ("graph", 1), ("mapped", 1)):
         eng.set_option(opt, val)
         print(f"C ABI call after {opt}={val}              us median/p95:", med(lambda: lib.vb200_likelihood(h, rp, 1, None, cp, lp, None)))
     # device-resident buffers: kernel time of the one-launch path by CUDA events

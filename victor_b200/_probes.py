@@ -7,7 +7,7 @@ from ctypes import POINTER, c_char_p, c_double, c_int, c_int64, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvictor_b200_probes.so")
 EXPORTS = ("vb200p_last_error", "vb200p_math_selftest", "vb200p_pipe_probe", "vb200p_seed_probe", "vb200p_mix_probe",
-           "vb200p_fp64_peak", "vb200p_load_probe")
+           "vb200p_fp64_peak", "vb200p_load_probe", "vb200p_quad_probe")
 SELFTEST_OUTPUTS = 10
 
 _lib = None
@@ -31,6 +31,8 @@ def load():
     lib.vb200p_seed_probe.argtypes = [c_int, c_void_p, c_int64, c_void_p]
     lib.vb200p_load_probe.restype = c_int
     lib.vb200p_load_probe.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_double)]
+    lib.vb200p_quad_probe.restype = c_int
+    lib.vb200p_quad_probe.argtypes = [c_int, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, POINTER(c_double)]
     lib.vb200p_fp64_peak.restype = c_int
     lib.vb200p_fp64_peak.argtypes = [c_int, c_int, POINTER(c_double), POINTER(c_double)]
     _lib = lib

@@ -30,6 +30,9 @@ static_assert(kNPar == VB200_NPAR, "kernel row stride and VB200_NPAR differ");
 namespace {
 
 thread_local std::string g_err;
+#ifdef VB200_SMALL_TIMING
+unsigned long long *g_stamps = nullptr;   // diagnostic build only
+#endif
 constexpr int64_t kSmallCall = 256;   // rows: calls up to this size go through pinned staging
 
 int fail(int code, const std::string &msg) {
@@ -116,6 +119,11 @@ struct vb200_ctx {
     int opt_fuse = 1;             // batch mode: chi2 / lnL in the epilogue of K1 instead of a K2 launch
     int opt_tuned = 1;            // 0: force the general kernel (A/B checks of the tuned kernels)
     int opt_tiny = 1;             // calls of <= kSmallRows rows: one launch of k_small instead of K1 + K2 (0: off)
+    int opt_mapped = 1;           // k_small writes (chi2 | lnL) straight into page-locked host memory and raises a flag
+                                  // the host polls: no device-to-host copy node, no stream synchronise.  (Reading the
+                                  // ROWS from host memory as well was 2.4x slower: 210 blocks x tens of uncached
+                                  // PCIe reads, profiles/r02l_small_call_latency.txt -- they still go by a copy node.)
+    double *pin_dev = nullptr;    // device-side address of `pin` (unified addressing), null if not available
     double *tiny_xi = nullptr;    // k_small scratch: xi(s, mu) of kSmallRows rows, and the rows' ticket counters
     unsigned *tiny_tickets = nullptr;
     int family = 0;               // kernel family the tables are eligible for (kTunedIso / kTunedWide / kGeneral)
@@ -440,7 +448,7 @@ bool use_small(const vb200_ctx *c, long long n) {
 
 // theory (optional), chi2 and lnL of n <= kSmallRows rows on the fit's grids in ONE launch (k1_small.cuh)
 int launch_small(vb200_ctx *c, const double *d_params, long long n, double *d_theory, double *d_chi2, double *d_lnl,
-                 cudaStream_t st) {
+                 cudaStream_t st, unsigned *done = nullptr) {
     if (!c->tiny_xi) {
         double *xi = nullptr;
         unsigned *tk = nullptr;
@@ -479,7 +487,12 @@ int launch_small(vb200_ctx *c, const double *d_params, long long n, double *d_th
         a.xw[i] = c->xw[i];
         a.xw[kMaxNx + i] = c->xw[kMaxNx + i] / scale;
     }
-    SmallArgs sm{c->tiny_xi, c->tiny_tickets, d_theory};
+#ifdef VB200_SMALL_TIMING
+    if (!g_stamps) cudaMalloc(&g_stamps, 16 * sizeof(unsigned long long));
+    SmallArgs sm{g_stamps, c->tiny_xi, c->tiny_tickets, d_theory, done};
+#else
+    SmallArgs sm{c->tiny_xi, c->tiny_tickets, d_theory, done};
+#endif
     const int nchunk = (c->fit_nmu + kSmallPairs - 1) / kSmallPairs;
     const long long blocks = n * c->fit_ns * nchunk;
     const size_t smem = small_smem_bytes(c->md.ncell, c->md.nbucket, c->fd.p, rec_doubles(c), big ? kExpTabBig : kExpTab);
@@ -491,10 +504,21 @@ int launch_small(vb200_ctx *c, const double *d_params, long long n, double *d_th
 }
 
 // H2D of the staged rows, K1, K2 (unless fused), D2H of (chi2 | lnL) -- the whole small call on one stream
+// page-locked staging area: rows [kSmallCall][NPAR] | chi2, lnL [2][kSmallCall] | flags [kSmallRows] (unsigned)
+constexpr size_t kPinDoubles = (size_t)kSmallCall * (VB200_NPAR + 2) + 8;
+unsigned *pin_flags(double *pin) { return reinterpret_cast<unsigned *>(pin + (size_t)kSmallCall * (VB200_NPAR + 2)); }
+
+// does this small call run without copy nodes (k_small on the mapped staging area, completion by flag)?
+bool small_is_mapped(const vb200_ctx *c, int64_t n) { return c->opt_mapped && c->pin_dev && use_small(c, n); }
+
 int small_sequence(vb200_ctx *c, int64_t n, cudaStream_t st) {
     int rc;
     double *h_out = c->pin + (size_t)kSmallCall * VB200_NPAR, *d_out = c->d_small + (size_t)kSmallCall * VB200_NPAR;
     CK(cudaMemcpyAsync(c->d_small, c->pin, (size_t)n * VB200_NPAR * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (small_is_mapped(c, n)) {
+        double *m_out = c->pin_dev + (size_t)kSmallCall * VB200_NPAR;
+        return launch_small(c, c->d_small, n, nullptr, m_out, m_out + n, st, pin_flags(c->pin_dev));
+    }
     if (use_small(c, n)) {
         if ((rc = launch_small(c, c->d_small, n, nullptr, d_out, d_out + n, st))) return rc;
     } else {
@@ -509,6 +533,8 @@ int small_sequence(vb200_ctx *c, int64_t n, cudaStream_t st) {
 }
 
 void drop_small_graph(vb200_ctx *c) {
+    // (a flag-completed small call may still be retiring on its stream: let it finish before its graph goes)
+    if (c->small_exec) cudaDeviceSynchronize();
     if (c->small_exec) cudaGraphExecDestroy(c->small_exec);
     c->small_exec = nullptr;
     c->small_n = -1;
@@ -597,6 +623,7 @@ int vb200_device_count(void) {
 void vb200_destroy(vb200_ctx *c) {
     if (!c) return;
     DeviceGuard g(c->device);
+    cudaDeviceSynchronize();
     for (void *p : c->owned) cudaFree(p);
     c->sc_params.release();
     c->sc_theory.release();
@@ -794,6 +821,7 @@ int vb200_set_option(vb200_ctx *c, const char *key, int64_t value) {
     else if (!strcmp(key, "fuse")) c->opt_fuse = (int)std::max<int64_t>(0, std::min<int64_t>(value, 2));
     else if (!strcmp(key, "tuned")) c->opt_tuned = value ? 1 : 0;
     else if (!strcmp(key, "tiny")) c->opt_tiny = value ? 1 : 0;
+    else if (!strcmp(key, "mapped")) c->opt_mapped = value ? 1 : 0;
     else if (!strcmp(key, "newton")) {
         if (value != 0 && value != 2 && value != 3)
             return fail(VB200_EINVAL, "newton must be 0 (default), 2 (one Newton step) or 3 (cubic step)");
@@ -819,6 +847,13 @@ int vb200_synchronize(vb200_ctx *c) {
 }
 
 int64_t vb200_launch_count(const vb200_ctx *c) { return c ? c->launches : 0; }
+
+#ifdef VB200_SMALL_TIMING
+extern "C" int vb200_debug_stamps(unsigned long long *out) {   // diagnostic build only: 16 globaltimer stamps
+    if (!g_stamps) return -1;
+    return cudaMemcpy(out, g_stamps, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 static int theory_impl(vb200_ctx *c, const double *params, int64_t n, const double *s, int32_t ns, const double *mu,
                        int32_t nmu, const double *wmu, int32_t L, double *xi_out, double *mult_out, void *stream,
@@ -945,7 +980,7 @@ int vb200_likelihood(vb200_ctx *c, const double *params, int64_t n, double *theo
         if (!c->pin || !c->d_small || !c->d_small_theory) {
             // all three or none: a failed allocation must not leave a half-initialised staging set behind
             double *pin = nullptr, *d_small = nullptr, *d_theory = nullptr;
-            cudaError_t e = cudaMallocHost(&pin, (size_t)kSmallCall * (VB200_NPAR + 2) * sizeof(double));
+            cudaError_t e = cudaHostAlloc(&pin, kPinDoubles * sizeof(double), cudaHostAllocMapped);
             if (e == cudaSuccess) e = cudaMalloc(&d_small, (size_t)kSmallCall * (VB200_NPAR + 2) * sizeof(double));
             if (e == cudaSuccess) e = cudaMalloc(&d_theory, (size_t)kSmallCall * p * sizeof(double));
             if (e != cudaSuccess) {
@@ -957,9 +992,16 @@ int vb200_likelihood(vb200_ctx *c, const double *params, int64_t n, double *theo
             c->pin = pin;
             c->d_small = d_small;
             c->d_small_theory = d_theory;
+            void *dp = nullptr;
+            if (cudaHostGetDevicePointer(&dp, pin, 0) == cudaSuccess) c->pin_dev = static_cast<double *>(dp);
+            else cudaGetLastError();
         }
         double *h_out = c->pin + (size_t)kSmallCall * VB200_NPAR;
         memcpy(c->pin, params, (size_t)n * VB200_NPAR * sizeof(double));
+        const bool mapped = small_is_mapped(c, n);
+        volatile unsigned *flags = pin_flags(c->pin);
+        if (mapped)
+            for (int64_t i = 0; i < n; ++i) flags[i] = 0u;
         bool replayed = false;
         if (c->opt_graph && c->graphs_ok && (c->small_n == n || build_small_graph(c, n))) {
             if (cudaGraphLaunch(c->small_exec, st) == cudaSuccess) {
@@ -971,7 +1013,17 @@ int vb200_likelihood(vb200_ctx *c, const double *params, int64_t n, double *theo
             }
         }
         if (!replayed && (rc = small_sequence(c, n, st))) return rc;
-        CK(cudaStreamSynchronize(st));
+        bool done = false;
+        if (mapped) {
+            // the last block of every row raises its flag after a system-scope fence behind its results: poll the
+            // flags (a few microseconds) instead of paying the wake-up latency of a stream synchronise; give up after
+            // ~2 ms and synchronise, which also reports a failed launch
+            for (long spin = 0; spin < 4000000 && !done; ++spin) {
+                done = true;
+                for (int64_t i = 0; i < n; ++i) done = done && flags[i] != 0u;
+            }
+        }
+        if (!done) CK(cudaStreamSynchronize(st));
         memcpy(chi2, h_out, (size_t)n * sizeof(double));
         memcpy(lnlike, h_out + n, (size_t)n * sizeof(double));
         return VB200_OK;

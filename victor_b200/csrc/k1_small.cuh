@@ -21,19 +21,231 @@
 
 namespace vb200 {
 
-constexpr int kSmallRows = 4;     // calls of up to this many rows use the kernel below
+constexpr int kSmallRows = 2;     // calls of up to this many rows use the kernel below (measured: faster than K1 + K2
+                                  // for n <= 2, slower from n = 3 on, profiles/r02l_small_call_latency.txt)
 constexpr int kSmallPairs = 16;   // (s_j, mu_k) pairs per block
 constexpr int kSmallLanes = 16;   // lanes per pair
 
+#ifdef VB200_SMALL_TIMING   // diagnostic build: globaltimer stamps of block 0 and of the last block (tools/probe_small_phases.py)
+#define VB_STAMP(slot) do { if (threadIdx.x == 0 && (blockIdx.x == 0 || (slot) >= 5)) { unsigned long long t__; \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__)); sm.stamps[(slot)] = t__; } } while (0)
+#else
+#define VB_STAMP(slot) do { } while (0)
+#endif
+
 struct SmallArgs {
+#ifdef VB200_SMALL_TIMING
+    unsigned long long *stamps;
+#endif
     double *xi_scratch;      // [n][ns][nmu]
     unsigned *tickets;       // [n], zero before the launch; the last block of a row resets its counter
     double *theory;          // [n][p] or null
+    unsigned *done;          // [n] or null: host-mapped flags, set to 1 (after a system-scope fence) once a row's
+                             // chi2 / lnL have been written -- the host may poll them instead of synchronising
 };
+
+// the last block stages both precision matrices of its row's bracket in shared memory (asynchronous copies that
+// run under the projection) when they fit: p <= 64 and even (16-byte rows)
+__host__ __device__ inline bool small_stages_matrices(int p) { return p <= 64 && p % 2 == 0; }
 
 __host__ __device__ inline size_t small_smem_bytes(int ncell, int nbucket, int p, int rec, int tab) {
     size_t d = (size_t)ncell * (rec + 1) + tab + kNScal + fused_fit_doubles(p);
+    d = (d + 1) & ~(size_t)1;
+    if (small_stages_matrices(p)) d += 2 * (size_t)p * p;
     return d * sizeof(double) + (size_t)nbucket * sizeof(int);
+}
+
+// interval k with grid[k] <= b < grid[k+1], clamped (beta_interval of common.cuh) with the grid values spread
+// over the lanes of a warp: one round of loads instead of a serial scan (n <= 33)
+__device__ __forceinline__ int beta_interval_warp(const double *grid, int n, double b, int lane) {
+    const bool ge = (lane >= 1 && lane < n - 1) ? (b >= grid[lane]) : false;
+    return __popc(__ballot_sync(0xffffffffu, ge));
+}
+
+// cov_bracket of k2_chi2.cuh, grid over the lanes (nbeta_cov <= 32); same conventions, same results
+__device__ __forceinline__ void cov_bracket_warp(const FitDev &f, double beta, int lane, int &lo, int &hi, double &w) {
+    lo = hi = 0;
+    w = 0.0;
+    if (f.cov_fixed) return;
+    const int nb = f.nbeta_cov;
+    const double gl = lane < nb ? f.beta_cov[lane] : 0.0;
+    const double g0 = __shfl_sync(0xffffffffu, gl, 0), glast = __shfl_sync(0xffffffffu, gl, nb - 1);
+    const unsigned below_m = __ballot_sync(0xffffffffu, lane < nb && gl < beta);
+    const unsigned exact_m = __ballot_sync(0xffffffffu, lane < nb && gl == beta);
+    if (beta < g0) return;
+    if (beta > glast) {
+        lo = hi = nb - 1;
+        return;
+    }
+    const int below = __popc(below_m);
+    if (exact_m) {
+        lo = hi = 31 - __clz(exact_m);
+    } else if (below == 0) {  // beta is NaN: every comparison false
+        w = beta;
+    } else {
+        lo = below - 1;
+        hi = nb - 1;  // sic: last index with grid >= beta (ccf_fit.py:225-227)
+        const double glo = __shfl_sync(0xffffffffu, gl, lo);
+        w = (beta - glo) / (glast - glo);
+    }
+}
+
+// The last block of a row: projection of xi(s, mu) onto the multipoles, residual, the two quadratic forms,
+// log-det term, likelihood -- block_chi2's arithmetic in block_chi2's order (bit-identical chi-square for the same
+// theory vector), arranged for LATENCY: everything that does not depend on the theory vector is requested first --
+// the bracket from one round of lane-parallel loads, both precision matrices by asynchronous global-to-shared
+// copies (cp.async, no registers held), data-vector table and generalised eigenvalues into a few registers --
+// and arrives while the projection runs.  `mats`: 2 p^2 doubles of shared memory, 16-byte aligned.
+__device__ __forceinline__ void small_epilogue(const K1Args &a, const SmallArgs &sm, const double *xi_row, long long row,
+                                               double beta, double *th, double *mats, int tid, int nthr) {
+    const FitDev &f = a.f;
+    const int p = f.p, ns = a.ns, nmu = a.nmu;
+    const int warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
+    double *red = th + ((p + 1) & ~1);
+    const bool fast = small_stages_matrices(p) && nwarp == kK2Warps && f.nbeta_cov <= 32 && f.nbeta_ccf <= 33;
+    int lo = 0, hi = 0, kd = 0;
+    double w = 0.0, td = 0.0;
+    double dcoef[4] = {0.0, 0.0, 0.0, 0.0}, lam0 = 1.0, lam1 = 1.0;
+    if (fast) {
+        cov_bracket_warp(f, beta, lane, lo, hi, w);
+        {
+            const double *Mlo = f.icov + (size_t)lo * p * p, *Mhi = f.icov + (size_t)hi * p * p;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(mats);
+            const int chunks = p * p / 2;                          // 16-byte pieces per matrix
+            for (int i = tid; i < chunks; i += nthr) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 16), "l"(Mlo + 2 * i) : "memory");
+                if (hi != lo)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (chunks + i) * 16), "l"(Mhi + 2 * i)
+                                 : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        if (f.data_beta_dependent) {
+            kd = beta_interval_warp(f.beta_ccf, f.nbeta_ccf, beta, lane);
+            td = beta - f.beta_ccf[kd];
+        }
+        if (tid < p) {
+            const double *dt = f.data_tab + (size_t)kd * 4 * p;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dcoef[q] = dt[q * p + tid];
+        }
+        if (warp == 0 && f.use_logdet && hi != lo) {
+            const double *lam = f.lam + (size_t)lo * p;
+            lam0 = lane < p ? lam[lane] : 1.0;
+            lam1 = lane + 32 < p ? lam[lane + 32] : 1.0;
+        }
+    }
+    // projection: one warp per s_j, lane-strided FMAs + xor butterfly, exactly as write_outputs does
+    // (ccf_model.py:824-825, utils.py:45-56), then the theory vector l-major (:856-858).  The usual sizes
+    // (ns <= 32, nmu <= 128) take all their loads in one round first (same FMA order; padding adds exact zeros).
+    if (ns <= 4 * kK2Warps && nmu <= 128 && nwarp == kK2Warps) {
+        double wv[kMaxPoles][4], xv[4][4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int kk = lane + 32 * c;
+#pragma unroll
+            for (int l = 0; l < kMaxPoles; ++l) wv[l][c] = (l < a.L && kk < nmu) ? a.wmu[l * nmu + kk] : 0.0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int jl = warp + kK2Warps * r;
+                xv[r][c] = (jl < ns && kk < nmu) ? __ldcg(xi_row + jl * nmu + kk) : 0.0;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int jl = warp + kK2Warps * r;
+            if (jl < ns) {
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (lane + 32 * c < nmu) {
+                        s0 = fma(wv[0][c], xv[r][c], s0);
+                        if (a.L > 1) s1 = fma(wv[1][c], xv[r][c], s1);
+                        if (a.L > 2) s2 = fma(wv[2][c], xv[r][c], s2);
+                    }
+                s0 = warp_sum(s0);
+                if (a.L > 1) s1 = warp_sum(s1);
+                if (a.L > 2) s2 = warp_sum(s2);
+                if (lane == 0) {
+                    th[jl] = s0;
+                    if (a.L > 1) th[ns + jl] = s1;
+                    if (a.L > 2) th[2 * ns + jl] = s2;
+                }
+            }
+        }
+    } else {
+        for (int jl = warp; jl < ns; jl += nwarp) {
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+            for (int kk = lane; kk < nmu; kk += 32) {
+                const double v = __ldcg(xi_row + jl * nmu + kk);
+                s0 = fma(a.wmu[kk], v, s0);
+                if (a.L > 1) s1 = fma(a.wmu[nmu + kk], v, s1);
+                if (a.L > 2) s2 = fma(a.wmu[2 * nmu + kk], v, s2);
+            }
+            s0 = warp_sum(s0);
+            if (a.L > 1) s1 = warp_sum(s1);
+            if (a.L > 2) s2 = warp_sum(s2);
+            if (lane == 0) {
+                th[jl] = s0;
+                if (a.L > 1) th[ns + jl] = s1;
+                if (a.L > 2) th[2 * ns + jl] = s2;
+            }
+        }
+    }
+    __syncthreads();
+    VB_STAMP(6);
+    if (sm.theory)
+        for (int i = tid; i < p; i += nthr) sm.theory[(size_t)row * p + i] = th[i];
+    if (!fast) {
+        __syncthreads();
+        block_chi2(f, beta, th, red, row, a.chi2, a.lnl, tid, nthr);
+        if (sm.done) {   // (block_chi2's lane 0 of warp 0 wrote the results: same thread, fence, then the flag)
+            if (tid == 0) {
+                __threadfence_system();
+                *reinterpret_cast<volatile unsigned *>(sm.done + row) = 1u;
+            }
+        }
+        return;
+    }
+    // residual against the beta-PCHIP data vector (ccf_fit.py:193, 322-323, 350): DataAt's Horner form
+    if (tid < p) th[tid] -= fma(fma(fma(dcoef[3], td, dcoef[2]), td, dcoef[1]), td, dcoef[0]);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    {   // the warps take one partial sum each (part = warp), as in block_chi2
+        const double qlo = quad_partial(mats, th, p, lane, warp);
+        const double qhi = (hi != lo) ? quad_partial(mats + (size_t)p * p, th, p, lane, warp) : 0.0;
+        if (lane == 0) {
+            red[warp] = qlo;
+            red[kK2Warps + warp] = qhi;
+        }
+    }
+    __syncthreads();
+    VB_STAMP(7);
+    if (warp == 0) {
+        double qa = 0.0, qb = 0.0;
+        for (int i = 0; i < kK2Warps; ++i) {   // same order as quad_form
+            qa += red[i];
+            qb += red[kK2Warps + i];
+        }
+        const double chi2 = blend_chi2(qa, qb, lo, hi, w);
+        double norm = 0.0;
+        if (f.use_logdet) {                    // norm_term of k2_chi2.cuh: lanes j and j + 32, then the butterfly
+            double ld = 0.0;
+            if (hi != lo) {
+                if (lane < p) ld += log1p(w * (lam0 - 1.0));
+                if (lane + 32 < p) ld += log1p(w * (lam1 - 1.0));
+                ld = warp_sum(ld);
+            }
+            norm = -0.5 * (f.logdet[lo] + ld);
+        }
+        if (lane == 0) {
+            store_likelihood(f, chi2, norm, row, a.chi2, a.lnl);
+            if (sm.done) {
+                __threadfence_system();
+                *reinterpret_cast<volatile unsigned *>(sm.done + row) = 1u;
+            }
+        }
+    }
 }
 
 template <class C>
@@ -49,7 +261,10 @@ __global__ void __launch_bounds__(kSmallPairs * kSmallLanes) k_small(const __gri
     double *scal = etab + C::kTab;
     double *th = scal + kNScal;
     double *upper = th + fused_fit_doubles(a.f.p);
-    int *bbase = reinterpret_cast<int *>(upper + ncell);
+    // (records, tables, scalars, th, upper) rounded up to a 16-byte boundary, then the matrices, then the bucket table
+    const size_t head = (((size_t)ncell * (kR + 1) + C::kTab + kNScal + fused_fit_doubles(a.f.p)) + 1) & ~(size_t)1;
+    double *mats = reinterpret_cast<double *>(smem_raw) + head;
+    int *bbase = reinterpret_cast<int *>(mats + (small_stages_matrices(a.f.p) ? 2 * (size_t)a.f.p * a.f.p : 0));
 
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int nchunk = (nmu + kSmallPairs - 1) / kSmallPairs;
@@ -62,16 +277,27 @@ __global__ void __launch_bounds__(kSmallPairs * kSmallLanes) k_small(const __gri
     const double beta = m.beta_dependent ? pr[1] : m.beta_fixed;
 
     // ---- prologue: as in k_multipoles (row scalars, then this row's cell records) ----
+    VB_STAMP(0);
+    // warp 0 works out the row scalars (a chain of divisions and a square-root trapezoid, ~2 us) while the other
+    // warps fetch the tables and build the records without the velocity amplitude, which is applied afterwards
+    const bool overlap = !m.vd_beta_dep && !m.v0b && nthr > 32;
     row_scalars_to_shared(m, pr, scal, tid);
-    for (int i = tid; i < ncell; i += nthr) upper[i] = m.upper[i];
-    for (int i = tid; i < m.nbucket; i += nthr) bbase[i] = m.bucket_base[i];
-    {
+    if (tid >= 32 || !overlap) {
+        const int t2 = overlap ? tid - 32 : tid, n2 = overlap ? nthr - 32 : nthr;
+        for (int i = t2; i < ncell; i += n2) upper[i] = m.upper[i];
+        for (int i = t2; i < m.nbucket; i += n2) bbase[i] = m.bucket_base[i];
         const double *src = C::kBigTab ? m.exp_tab_big : m.exp_tab;
-        for (int i = tid; i < C::kTab; i += nthr) etab[i] = src[i];
+        for (int i = t2; i < C::kTab; i += n2) etab[i] = src[i];
+        if (overlap) build_cell_records<C, true>(m, scal, beta, rec, t2, n2);
     }
     __syncthreads();
-    build_cell_records<C>(m, scal, beta, rec, tid, nthr);
+    VB_STAMP(1);
+    if (overlap)
+        scale_cell_records<C>(m, scal, rec, tid, nthr);
+    else
+        build_cell_records<C>(m, scal, beta, rec, tid, nthr);
     __syncthreads();
+    VB_STAMP(2);
 
     // ---- one (s_j, mu_k) pair per half-warp, its velocity nodes over the 16 lanes ----
     const int pair = tid / kSmallLanes, l16 = tid % kSmallLanes;
@@ -110,43 +336,21 @@ __global__ void __launch_bounds__(kSmallPairs * kSmallLanes) k_small(const __gri
 
     // ---- ticket: the last block of this row finishes it ----
     __syncthreads();
+    VB_STAMP(3);
     if (tid == 0) {
         __threadfence();
         const unsigned t = atomicAdd(sm.tickets + row, 1u);
         is_last = (t == (unsigned)(per_row - 1));
     }
     __syncthreads();
+    VB_STAMP(4);
     if (!is_last) return;
+    VB_STAMP(5);
     __threadfence();
     if (tid == 0) sm.tickets[row] = 0;   // ready for the next launch (stream-ordered after this one)
 
-    // projection onto the multipoles: one warp per s_j, lane-strided FMAs + xor butterfly, exactly as
-    // write_outputs does (ccf_model.py:824-825, utils.py:45-56), then the theory vector l-major (:856-858)
-    {
-        const int warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
-        for (int jl = warp; jl < ns; jl += nwarp) {
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-            for (int kk = lane; kk < nmu; kk += 32) {
-                const double v = __ldcg(xi_row + jl * nmu + kk);
-                s0 = fma(a.wmu[kk], v, s0);
-                if (a.L > 1) s1 = fma(a.wmu[nmu + kk], v, s1);
-                if (a.L > 2) s2 = fma(a.wmu[2 * nmu + kk], v, s2);
-            }
-            s0 = warp_sum(s0);
-            if (a.L > 1) s1 = warp_sum(s1);
-            if (a.L > 2) s2 = warp_sum(s2);
-            if (lane == 0) {
-                th[jl] = s0;
-                if (a.L > 1) th[ns + jl] = s1;
-                if (a.L > 2) th[2 * ns + jl] = s2;
-            }
-        }
-    }
-    __syncthreads();
-    if (sm.theory)
-        for (int i = tid; i < a.f.p; i += nthr) sm.theory[(size_t)row * a.f.p + i] = th[i];
-    __syncthreads();
-    block_chi2(a.f, pr[1], th, th + ((a.f.p + 1) & ~1), row, a.chi2, a.lnl, tid, nthr);
+    small_epilogue(a, sm, xi_row, row, pr[1], th, mats, tid, nthr);
+    VB_STAMP(8);
 }
 
 }  // namespace vb200

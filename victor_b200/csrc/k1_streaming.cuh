@@ -299,12 +299,14 @@ __device__ __forceinline__ double nodes(const K1Args &a, const QuadCtx &q, int m
 
 // this row's cell records in shared memory: xi^r(u; beta) from the beta power table (+1 folded into c0),
 // amplitude * V0(u), SV(u), origin (dispersion: G D0 + 1 too); `scal` = row_scalars_to_shared's output
-template <class C>
+// kRaw: V0 (and D0) are stored WITHOUT the row's velocity amplitude, so that the build need not wait for the row
+// scalars (k_small overlaps the two); scale_cell_records() applies the amplitude afterwards -- the same products.
+template <class C, bool kRaw = false>
 __device__ __forceinline__ void build_cell_records(const ModelDev &m, const double *scal, double beta, double *rec,
                                                    int tid, int nthr) {
     constexpr int kR = C::kRecD;
     const int ncell = m.ncell;
-    const double amp = C::kDisp ? scal[5] : scal[4];
+    const double amp = kRaw ? 1.0 : (C::kDisp ? scal[5] : scal[4]);
     int kb = 0;
     double tb = 0.0;
     if (m.beta_dependent) {
@@ -339,8 +341,8 @@ __device__ __forceinline__ void build_cell_records(const ModelDev &m, const doub
             v0 = fma(scal[8], m.v0b[i], v0);
             if (C::kDisp) d0 = fma(scal[8], m.d0b[i], d0);
         }
-        r[4 + c] = amp * v0;
-        if (C::kDisp) r[C::kD1 + c] = (c == 0) ? fma(amp, d0, 1.0) : amp * d0;
+        r[4 + c] = kRaw ? v0 : amp * v0;
+        if (C::kDisp) r[C::kD1 + c] = kRaw ? d0 : ((c == 0) ? fma(amp, d0, 1.0) : amp * d0);
         // kFast: SV / sqrt(16 log2 e) (or sqrt(512 log2 e)), so that its reciprocal carries the scale of the exp argument
         // (the weights a.xw are divided by the same constant on the host)
         r[8 + c] = C::kFast ? m.sv[i] * (1.0 / C::kScale) : m.sv[i];
@@ -348,6 +350,18 @@ __device__ __forceinline__ void build_cell_records(const ModelDev &m, const doub
             r[12] = m.origin[cell];
             r[13] = 0.0;
         }
+    }
+}
+
+template <class C>
+__device__ __forceinline__ void scale_cell_records(const ModelDev &m, const double *scal, double *rec, int tid, int nthr) {
+    constexpr int kR = C::kRecD;
+    const double amp = C::kDisp ? scal[5] : scal[4];
+    for (int i = tid; i < m.ncell * 4; i += nthr) {
+        double *r = rec + (i >> 2) * kR;
+        const int c = i & 3;
+        r[4 + c] = amp * r[4 + c];
+        if (C::kDisp) r[C::kD1 + c] = (c == 0) ? fma(amp, r[C::kD1 + c], 1.0) : amp * r[C::kD1 + c];
     }
 }
 

@@ -199,6 +199,38 @@ int vb200p_load_probe(int device, int path, int distinct, int stride, int blocks
     return kOk;
 }
 
+int vb200p_quad_probe(int device, int kind, const double *R, const double *P, int64_t n, int reps, double *q, double *ms) {
+    if (!R || !P || !q || !ms || n < 1 || reps < 1 || (kind != 0 && kind != 1)) return fail(kEInval, "bad arguments");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(kECuda, "cudaSetDevice failed");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    DevBuf dR, dP, dq;
+    CK(dR.alloc((size_t)n * kQP));
+    CK(dP.alloc((size_t)kQP * kQP));
+    CK(dq.alloc((size_t)n));
+    CK(cudaMemcpy(dR.p, R, (size_t)n * kQP * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dP.p, P, (size_t)kQP * kQP * sizeof(double), cudaMemcpyHostToDevice));
+    const int blocks = prop.multiProcessorCount * 4;
+    EventPair ev;
+    CK(ev.create());
+    auto run = [&]() {
+        if (kind == 0) k_quad_fma<<<blocks, 256>>>(dR.p, dP.p, n, dq.p);
+        else k_quad_dmma<<<blocks, 256>>>(dR.p, dP.p, n, dq.p);
+    };
+    run();
+    CK(cudaEventRecord(ev.a));
+    for (int i = 0; i < reps; ++i) run();
+    CK(cudaEventRecord(ev.b));
+    CK(cudaEventSynchronize(ev.b));
+    CK(cudaGetLastError());
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, ev.a, ev.b));
+    *ms = t / reps;
+    CK(cudaMemcpy(q, dq.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    return kOk;
+}
+
 int vb200p_seed_probe(int device, const double *x, int64_t n, double *out) {
     if (!x || !out || n <= 0) return fail(kEInval, "bad arguments");
     DeviceGuard g(device);

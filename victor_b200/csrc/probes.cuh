@@ -218,6 +218,72 @@ __global__ void __launch_bounds__(256) k_load_probe(const __grid_constant__ Load
     if (s == 12345.678) a.out[0] = s;
 }
 
+// ---------------------------------------------------------------------------------------
+// Quadratic-form probe: q[i] = r_i^T P r_i for n rows r_i [64] (p = 60 zero-padded to 64) against ONE matrix
+// P [64][64] -- the half of K2's work that all rows share (the upper bracket is always the last precision matrix,
+// ccf_fit.py:225-227).  Two arrangements, same inputs:
+//   kind 0  warp-tiled FMA: the production arrangement of k_chi2 (matrix staged in shared memory, one warp per
+//           row, lanes over columns, r_i broadcast from shared memory)
+//   kind 1  FP64 DMMA: mma.sync.aligned.m8n8k4.f64, a warp owns an 8-row strip: Y = R_strip P as 8 column tiles x
+//           16 k-steps, then q = rowsum(Y o R_strip) and a 4-lane butterfly
+// north_star: "FP64 DMMA only if ncu shows it beats warp-tiled FMA".
+// ---------------------------------------------------------------------------------------
+constexpr int kQP = 64;
+
+__global__ void __launch_bounds__(256) k_quad_fma(const double *R, const double *P, long long n, double *q) {
+    __shared__ double sP[kQP * kQP];
+    __shared__ double sr[8][kQP];
+    for (int i = threadIdx.x; i < kQP * kQP; i += blockDim.x) sP[i] = P[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (long long row = (long long)blockIdx.x * 8 + warp; row < n; row += (long long)gridDim.x * 8) {
+        __syncwarp();
+        sr[warp][lane] = R[row * kQP + lane];
+        sr[warp][lane + 32] = R[row * kQP + lane + 32];
+        __syncwarp();
+        double y0 = 0.0, y1 = 0.0;
+#pragma unroll 8
+        for (int i = 0; i < kQP; ++i) {
+            const double ri = sr[warp][i];
+            y0 = fma(sP[i * kQP + lane], ri, y0);
+            y1 = fma(sP[i * kQP + lane + 32], ri, y1);
+        }
+        double acc = fma(y0, sr[warp][lane], y1 * sr[warp][lane + 32]);
+        acc = warp_sum(acc);
+        if (lane == 0) q[row] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_quad_dmma(const double *R, const double *P, long long n, double *q) {
+    __shared__ double sP[kQP * (kQP + 1)];   // [k][n], padded rows: B fragments read a column of 4 k's per group
+    for (int i = threadIdx.x; i < kQP * kQP; i += blockDim.x) sP[(i / kQP) * (kQP + 1) + (i % kQP)] = P[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    for (long long strip = (long long)blockIdx.x * 8 + warp; strip * 8 < n; strip += (long long)gridDim.x * 8) {
+        const long long row = strip * 8 + g;               // this thread's row of the strip (A and C fragments)
+        const double *r = R + (row < n ? row : n - 1) * kQP;
+        double c[8][2];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) c[nt][0] = c[nt][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks) {
+            const double a0 = r[ks * 4 + t];                // A[g][t] of this k-step
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const double b0 = sP[(ks * 4 + t) * (kQP + 1) + nt * 8 + g];   // B[t][g]
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                             : "+d"(c[nt][0]), "+d"(c[nt][1]) : "d"(a0), "d"(b0));
+            }
+        }
+        double acc = 0.0;                                   // C[g][2t], C[g][2t + 1] of every column tile
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) acc = fma(c[nt][0], r[nt * 8 + 2 * t], fma(c[nt][1], r[nt * 8 + 2 * t + 1], acc));
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (t == 0 && row < n) q[row] = acc;
+    }
+}
+
 // raw MUFU seeds (no refinement): out[0..n) = rsqrt.approx(x), out[n..2n) = rcp.approx(x)
 __global__ void k_seed_probe(const double *x, long long n, double *out) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

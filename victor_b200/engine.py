@@ -101,15 +101,31 @@ class Engine:
 
     def likelihood(self, rows, want_theory=False):
         """(theory[n][p] or None, chi2[n], lnl[n]) as host arrays."""
-        rows = np.ascontiguousarray(rows, dtype=np.float64)
+        if type(rows) is not np.ndarray or rows.dtype != np.float64 or not rows.flags.c_contiguous:
+            rows = np.ascontiguousarray(rows, dtype=np.float64)
         n = rows.shape[0]
         theory = np.empty((n, self.p)) if want_theory else None
-        chi2 = np.empty(n)
-        lnl = np.empty(n)
-        self._check(self.lib.vb200_likelihood(
-            self.handle, rows.ctypes.data, n, theory.ctypes.data if want_theory else None,
-            chi2.ctypes.data, lnl.ctypes.data, None))
-        return theory, chi2, lnl
+        out = np.empty((2, n))          # chi2 | lnL: one allocation, two views
+        base = out.ctypes.data
+        rc = self.lib.vb200_likelihood(self.handle, rows.ctypes.data, n, theory.ctypes.data if want_theory else None,
+                                       base, base + 8 * n, None)
+        if rc != 0:
+            self._check(rc)
+        return theory, out[0], out[1]
+
+    def likelihood_point(self, row):
+        """(chi2, lnl) as Python floats for ONE parameter row given as a sequence of NPAR numbers: the MCMC step.
+        Row and results go through two small ctypes arrays owned by the engine (no numpy allocation per call)."""
+        buf = getattr(self, "_point", None)
+        if buf is None:
+            row_c, out_c = (ctypes.c_double * len(row))(), (ctypes.c_double * 2)()
+            buf = self._point = (row_c, out_c, ctypes.addressof(row_c), ctypes.addressof(out_c))
+        row_c, out_c, row_p, out_p = buf
+        row_c[:] = row
+        rc = self.lib.vb200_likelihood(self.handle, row_p, 1, None, out_p, out_p + 8, None)
+        if rc != 0:
+            self._check(rc)
+        return out_c[0], out_c[1]
 
     # ---- raw-pointer path (host or device pointers, caller-owned buffers) ---------------
     def likelihood_ptr(self, params_ptr, n, theory_ptr, chi2_ptr, lnl_ptr, stream=None):

@@ -18,8 +18,22 @@ import os
 import numpy as np
 
 from . import tables as _tables
-from .model import CCFModel, params_to_rows
+from .model import CCFModel, params_to_rows, point_to_row
 from .utils import InputError, load_input_file, log
+
+
+class _WithLikelihood:
+    """Read-only view of a model option dict with the fit's 'likelihood' entry on top (what _engine_key reads)."""
+    __slots__ = ("base", "like")
+
+    def __init__(self, base, like):
+        self.base, self.like = base, like
+
+    def __getitem__(self, key):
+        return self.like if key == "likelihood" else self.base[key]
+
+    def get(self, key, default=None):
+        return self.like if key == "likelihood" else self.base.get(key, default)
 
 
 class CCFFit(CCFModel):
@@ -185,6 +199,11 @@ class CCFFit(CCFModel):
         # same kwargs to the fit options and to the model options (ccf_fit.py:379-381, 444; ccf_model.py:565-567),
         # so a user may change either dict between calls: the engine is looked up by the resolved option key
         # every time (a tuple compare; the tables are only rebuilt for a key not seen before)
+        if not kwargs:   # the MCMC step: resolve the key straight from the two dicts, no copies
+            key = self._engine_key(_WithLikelihood(self.model, self.fit_options["likelihood"]), True)
+            eng = self._engines.get(key)
+            if eng is not None:
+                return eng, self.fit_options
         fit_options = dict(self.fit_options)
         fit_options.update(kwargs)
         opts = self._merged_options(kwargs)
@@ -268,7 +287,13 @@ class CCFFit(CCFModel):
     def log_likelihood(self, params, **kwargs):
         """(lnlike, chisq) at one parameter point (reference: ccf_fit.py:356-483)."""
         self._check_point(params, kwargs)
-        lnl, chi2 = self.log_likelihood_batch(params, **kwargs)
-        if lnl[0] == -np.inf:   # the reference prints here (ccf_fit.py:478-479)
+        row = point_to_row(params) if isinstance(params, dict) else None
+        eng, fit_options = self._fit_engine(kwargs)
+        if row is None or (fit_options["beta_interpolation"] == "likelihood" and not self.fixed_data):
+            lnl, chi2 = self.log_likelihood_batch(params, **kwargs)
+            lnl, chi2 = float(lnl[0]), float(chi2[0])
+        else:
+            chi2, lnl = eng.likelihood_point(row)
+        if lnl == -np.inf:   # the reference prints here (ccf_fit.py:478-479)
             log.warning("Likelihood evaluation failed, returning (-inf, inf). Parameters at fail point: %s", params)
-        return float(lnl[0]), float(chi2[0])
+        return lnl, chi2

@@ -55,6 +55,24 @@ def hubble_ratio(cosmology, z):
     return float(np.sqrt(om * zp1 ** 3 + curv * zp1 ** 2 + ol))
 
 
+def point_to_row(params):
+    """One parameter point given as a dict of plain numbers -> the list of its NPAR row values (the MCMC step's
+    fast path), or None if some value is not a scalar.  Same conventions as ``params_to_rows``."""
+    get = params.get
+    try:
+        fs8, beta, sig = float(get("fsigma8", np.nan)), float(get("beta", np.nan)), float(get("sigma_v", 380.0))
+        if "epsilon" in params:
+            eps = float(params["epsilon"])
+            apar = float(get("alpha", 1.0)) * eps ** (-2 / 3)
+            aperp = eps * apar
+        else:
+            aperp, apar = float(get("aperp", 1.0)), float(get("apar", 1.0))
+        return [fs8, beta, sig, aperp, apar, float(get("astar", 1.0)), float(get("M", 1.0)), float(get("Q", 1.0)),
+                float(get("Av", 0.0)), float(get("bias", np.nan))]
+    except TypeError:      # some value is an array
+        return None
+
+
 def params_to_rows(params, n_hint=None):
     """Normalise a parameter specification to float64[n, NPAR] (tables.PARAM_ORDER).
 
@@ -67,21 +85,9 @@ def params_to_rows(params, n_hint=None):
                 "astar": 1.0, "M": 1.0, "Q": 1.0, "Av": 0.0, "bias": np.nan}   # bias NaN: the model's own (:359)
     if isinstance(params, dict):
         # fast path for one parameter point given as plain numbers (the MCMC step): no array work
-        get = params.get
-        try:
-            fs8, beta, sig = float(get("fsigma8", np.nan)), float(get("beta", np.nan)), float(get("sigma_v", 380.0))
-            if "epsilon" in params:
-                eps = float(params["epsilon"])
-                apar = float(get("alpha", 1.0)) * eps ** (-2 / 3)
-                aperp = eps * apar
-            else:
-                aperp, apar = float(get("aperp", 1.0)), float(get("apar", 1.0))
-            row = [fs8, beta, sig, aperp, apar, float(get("astar", 1.0)), float(get("M", 1.0)), float(get("Q", 1.0)),
-                   float(get("Av", 0.0)), float(get("bias", np.nan))]
-            if not n_hint or n_hint == 1:
-                return np.array([row], dtype=np.float64)
-        except TypeError:      # some value is an array: general path below
-            pass
+        row = point_to_row(params)
+        if row is not None and (not n_hint or n_hint == 1):
+            return np.array([row], dtype=np.float64)
         cols = {}
         lens = [np.size(v) for k, v in params.items()
                 if k in defaults or k in ("epsilon", "alpha")]
@@ -324,15 +330,18 @@ class CCFModel:
         opts.update(kwargs)
         return opts
 
+    def _engine_key(self, opts, need_fit):
+        return (opts["rsd_model"], bool(opts["assume_isotropic"]), bool(opts["velocity_independent_of_AP"]),
+                opts["matter_model"], opts["mean_model"], bool(opts["empirical_corr"]),
+                bool(opts["realspace_ccf_from_data"]), bool(opts.get("kaiser_approximation", False)),
+                bool(opts.get("kaiser_coord_shift", True)), int(opts.get("velocity_nodes", 50)),
+                int(opts.get("mu_nodes", 100)), float(opts.get("bias", 1.9)), int(opts.get("niter", 5)),
+                self._fit_key(opts) if need_fit else None)
+
     def _engine(self, opts, need_fit=False):
         """Context on the GPU for this option set (tables are built and uploaded once per set)."""
         from .engine import Engine
-        key = (opts["rsd_model"], bool(opts["assume_isotropic"]), bool(opts["velocity_independent_of_AP"]),
-               opts["matter_model"], opts["mean_model"], bool(opts["empirical_corr"]),
-               bool(opts["realspace_ccf_from_data"]), bool(opts.get("kaiser_approximation", False)),
-               bool(opts.get("kaiser_coord_shift", True)), int(opts.get("velocity_nodes", 50)),
-               int(opts.get("mu_nodes", 100)), float(opts.get("bias", 1.9)), int(opts.get("niter", 5)),
-               self._fit_key(opts) if need_fit else None)
+        key = self._engine_key(opts, need_fit)
         eng = self._engines.get(key)
         if eng is None:
             mt = _tables.build_model_tables(self, opts, nx=int(opts.get("velocity_nodes", 50)))
@@ -507,9 +516,9 @@ class CCFModel:
 
     def _check_point(self, params, kwargs):
         """Reference behaviour for missing parameters: KeyError on params['beta'] / ['fsigma8']."""
-        opts = self._merged_options(kwargs)
         if isinstance(params, dict):
-            if not (self.fixed_real_input and opts["matter_model"] != "linear_bias"):
+            matter = kwargs["matter_model"] if "matter_model" in kwargs else self.model["matter_model"]
+            if not (self.fixed_real_input and matter != "linear_bias"):
                 params["beta"]
             params["fsigma8"]
 
