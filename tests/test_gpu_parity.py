@@ -981,3 +981,47 @@ def test_device_resident_likelihood(fit, golden):
     from victor_b200.batch import likelihood_sharded
     l2, c2, (lo, hi) = likelihood_sharded(fit, params_to_rows(g["params"]))      # no process group: one slice
     assert (lo, hi) == (0, len(lnl_h)) and np.array_equal(l2, lnl_h) and np.array_equal(c2, chi2_h)
+
+
+def test_small_row_kernel_general_epilogue(boss_blocks, tmp_path):
+    """k_small with a data vector longer than 64 (three multipoles, p = 90): the last block falls back from the
+    staged-matrix epilogue to block_chi2.  Builder-made inputs (the BOSS data with the quadrupole repeated as a
+    hexadecapole and a block covariance); checked against the batch kernels and the C table walk."""
+    from oracle.table_walk import TableWalk
+    from victor_b200 import CCFFit
+    from victor_b200.model import params_to_rows
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    src = np.load(f"{data['dir']}/{data['redshift_space_ccf']['data_file']}")
+    keys = data["redshift_space_ccf"]["ccf_keys"]
+    arrays = {k: src[k] for k in src.files}
+    arrays["hexadecapole_copy"] = 0.5 * src[keys[2]]
+    np.savez(tmp_path / "data3.npz", **arrays)
+    cov = np.load(f"{data['dir']}/{data['covariance_matrix']['data_file']}")
+    ckey = data["covariance_matrix"]["cov_key"]
+    c60 = cov[ckey]
+    c90 = np.zeros((c60.shape[0], 90, 90))
+    c90[:, :60, :60] = c60
+    c90[:, 60:, 60:] = c60[:, 30:, 30:] * 0.5
+    carr = {k: cov[k] for k in cov.files}
+    carr[ckey] = c90
+    np.savez(tmp_path / "cov3.npz", **carr)
+    data["dir"] = str(tmp_path)
+    data["redshift_space_ccf"]["data_file"] = "data3.npz"
+    data["redshift_space_ccf"]["ccf_keys"] = list(keys) + ["hexadecapole_copy"]
+    data["covariance_matrix"]["data_file"] = "cov3.npz"
+    fit3 = CCFFit(model, data)
+    assert len(fit3.poles_s) == 3
+    P = np.array([[0.47, 0.37, 380.0, 1.0, 1.0], [0.9, 0.52, 210.0, 1.05, 0.95], [0.2, 0.25, 450.0, 0.93, 1.08]])
+    eng, _ = fit3._fit_engine({})
+    eng.set_option("tiny", 0)
+    bl, bc = fit3.log_likelihood_batch(P)
+    eng.set_option("tiny", 1)
+    wt, wc, wl = TableWalk(fit3).likelihood(params_to_rows(P), want_theory=True)
+    for i in range(len(P)):
+        before = eng.launch_count()
+        l, c, t = fit3.log_likelihood_batch(P[i:i + 1], return_theory=True)
+        assert eng.launch_count() - before == 1
+        assert abs(c[0] - bc[i]) < 1e-9 and abs(l[0] - bl[i]) < 1e-9
+        assert abs(c[0] - wc[i]) < CHI2_ATOL and abs(l[0] - wl[i]) < CHI2_ATOL
+        assert_theory(t, wt[i:i + 1], ns=len(fit3.s))
+    fit3.close()

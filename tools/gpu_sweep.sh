@@ -11,4 +11,4 @@ for N in 2 4 8; do
 done
 for f in gpurun_out/sweep_n*.json; do grep "^{" $f | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print(d['n_gpus'], 'value=%.4g' % d['value'], 'e2e=%.4g' % d['e2e']['value'], 'ms/step=%.1f' % d['ms_per_step'], d['scaling'], d['config'].get('sweep_rows_total'))"; done | tee gpurun_out/sweep_summary.txt
+d=json.loads(sys.stdin.read()); print(d['n_gpus'], 'value=%.4g' % d['value'], 'e2e=%.4g' % d['e2e']['value'], 'ms/step=%.1f' % d['ms_per_step'], d['scaling'], d["config"].get("rows_total"))"; done | tee gpurun_out/sweep_summary.txt
