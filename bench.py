@@ -253,7 +253,10 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------ GPU side
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """`nvidia-smi` sampled every 100 ms.  The process takes a few hundred ms to come up, so it is started before
+    the warm-up; `mark()` is called where the timed region begins and `stop()` reports the samples taken from then
+    on (all samples, flagged, if the region was shorter than one sampling period)."""
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -262,6 +265,7 @@ class ClockSampler:
         self.index = vis.split(",")[index] if vis else index
         self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.proc = None
+        self.t_mark = None
 
     def start(self):
         try:
@@ -272,7 +276,12 @@ class ClockSampler:
             self.proc = None
         return self
 
+    def mark(self):
+        self.t_mark = time.time()
+        return self
+
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
@@ -283,25 +292,27 @@ class ClockSampler:
             self.proc.kill()
         self.tmp.flush()
         self.tmp.seek(0)
-        sm, smax, power, reasons = [], [], [], set()
+        rows = []
         for ln in self.tmp.read().splitlines():
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
-                power.append(float(f[3]))
+                stamp = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((stamp, float(f[1]), float(f[2]), float(f[3]),
+                             [name for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                                         "sw_power_cap"), f[5:9]) if val.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
-                                 f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
         os.unlink(self.tmp.name)
-        if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(smax), reasons=sorted(reasons),
-                       samples=len(sm), power_w_max=max(power), sm_mhz_min=min(sm))
+        window = [r for r in rows if self.t_mark is None or r[0] >= self.t_mark - 0.05]
+        if rows and not window:
+            window, out["window"] = rows, "timed region shorter than one sampling period: samples include the warm-up"
+        if window:
+            sm = [r[1] for r in window]
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(r[2] for r in window),
+                       reasons=sorted({x for r in window for x in r[4]}), samples=len(window),
+                       power_w_max=max(r[3] for r in window), sm_mhz_min=min(sm))
         return out
 
 
@@ -380,7 +391,7 @@ def extra_dispersion(job, fit, n, steps):
                                                     d_lnl.data_ptr(), None), steps, 1)
     k1 = job.timed_steps(lambda: eng.likelihood_ptr(d_params.data_ptr(), n, d_theory.data_ptr(), None, None, None),
                          steps, 0)
-    nonfinite = int((~torch.isfinite(d_lnl)).sum())
+    nonfinite = int(np.count_nonzero(~np.isfinite(d_lnl.cpu().numpy())))
 
     def finish(step_ms, k1_ms):
         fl = flop_k1(NS, NMU, NX, L, rsd="dispersion")
@@ -516,7 +527,7 @@ def extra_sustained(job, step, n, seconds):
     the clock?  The sampler of rank 0 runs over exactly this region."""
     torch = job.torch
     job.barrier()
-    sampler = ClockSampler(job.local).start() if job.rank == 0 else None
+    sampler = ClockSampler(job.local).start().mark() if job.rank == 0 else None
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     count = 0
     t0 = time.perf_counter()
@@ -563,10 +574,12 @@ def run_gpu(args):
                            stream_ptr)
 
     # --- device-resident throughput (`value`) ---
+    sampler = ClockSampler(job.local).start() if rank == 0 else None
     for _ in range(args.warmup):
         step_device()
     job.barrier()
-    sampler = ClockSampler(job.local).start() if rank == 0 else None
+    if sampler:
+        sampler.mark()
     launches0 = eng.launch_count()
     step_ms = job.timed_steps(step_device, args.steps, 0)
     launches = eng.launch_count() - launches0
