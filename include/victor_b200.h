@@ -141,14 +141,19 @@ int vb200_device_count(void);
 int vb200_create(const vb200_model_tables *model, const vb200_fit_tables *fit, int device, vb200_ctx **out);
 void vb200_destroy(vb200_ctx *ctx);
 
-/* Kernel variant switches (integers): "fast_math" (1 = hand-rolled rsqrt / rcp / exp, default;
- * 0 = CUDA libm), "nsplit" (blocks per parameter row; 0 = automatic), "threads" (block size),
- * "ilp" (velocity nodes per loop trip: 1, 2, 4), "exp_degree" (5, default, or 6), "newton" (3 = cubic
- * refinement of the MUFU seeds, default; 2 = one Newton step).  They select among the tuned streaming
- * kernels; the general kernel (dispersion, kaiser, anisotropic or from-data real-space input) has one
- * variant per rsd_model.  "fuse": chi2 / lnL in the epilogue of the theory kernel when one block owns a
- * row (0 never, 1 where measured faster = default, 2 always).  "graph": replay calls of up to 256 host
- * rows (MCMC steps) as one CUDA graph (1 = default, 0 = plain stream submissions). */
+/* Kernel variant switches (integers; 0 selects the default where a default exists):
+ *   "fast_math"  1 = hand-rolled rsqrt / rcp / exp (default), 0 = CUDA libm (the parity-test variant)
+ *   "tuned"      1 = tuned kernels where they apply (default), 0 = always the general kernel
+ *   "newton"     refinement of the MUFU seeds in the tuned streaming kernel: 2 = one Newton step (default), 3 = cubic step
+ *   "exp_degree" 5 = degree-5 remainder polynomial on a 32-entry table (default), 3 = degree 3 on a 1024-entry table
+ *   "ilp"        velocity nodes per loop trip, 4 (default) or 1
+ *   "threads"    block size of the batch kernels (32..256), "nsplit" blocks per parameter row (0 = automatic)
+ *   "fuse"       chi2 / lnL in the epilogue of the theory kernel when one block owns a row: 0 never, 1 where measured
+ *                faster (default), 2 always
+ *   "tiny"       calls of one or two rows through the one-launch kernel k_small (1 = default)
+ *   "mapped"     k_small writes its results into mapped page-locked host memory and the host polls a flag (1 = default)
+ *   "graph"      replay calls of up to 256 host rows as one CUDA graph (1 = default)
+ *   "chunks"     row chunks of host-bound bulk outputs (0 = automatic) */
 int vb200_set_option(vb200_ctx *ctx, const char *key, int64_t value);
 
 /* xi(s, mu) and / or its projections for n parameter rows.

@@ -102,10 +102,8 @@ def test_boss_streaming_golden(fit, golden, fast):
     np.testing.assert_allclose(lnl, g["lnl"], rtol=0, atol=CHI2_ATOL)
 
 
-@pytest.mark.parametrize("opts", [{"ilp": 1}, {"exp_degree": 6, "newton": 3}, {"exp_degree": 5, "newton": 3},
-                                  {"exp_degree": 5, "newton": 2}, {"exp_degree": 53, "newton": 2},
-                                  {"exp_degree": 3, "newton": 3}, {"exp_degree": 3, "newton": 2},
-                                  {"exp_degree": 30, "newton": 2}, {"threads": 128}, {"threads": 64}])
+@pytest.mark.parametrize("opts", [{"ilp": 1}, {"exp_degree": 5, "newton": 3}, {"exp_degree": 5, "newton": 2},
+                                  {"exp_degree": 3, "newton": 2}, {"threads": 128}, {"threads": 64}])
 def test_kernel_variants_hold_parity(fit, golden, opts):
     """Every tuning variant of K1 must meet the same bar as the default."""
     g = golden("boss_streaming_points")
@@ -551,14 +549,11 @@ def test_tuned_wide_kernels_agree_with_general(fit, kw):
             eng.set_option("tuned", tuned)
             out[tuned] = eng.likelihood(rows, want_theory=True)
         eng.set_option("tuned", 1)
-        for ilp in (2, 4):
-            eng.set_option("ilp", ilp)
-            th, c2, _ = eng.likelihood(rows[:300], want_theory=True)   # 300 rows: the s range is split over blocks
-            np.testing.assert_array_equal(th, out[1][0][:300])
-            np.testing.assert_array_equal(c2, out[1][1][:300])
+        th, c2, _ = eng.likelihood(rows[:300], want_theory=True)   # 300 rows: the s range is split over blocks
+        np.testing.assert_array_equal(th, out[1][0][:300])
+        np.testing.assert_array_equal(c2, out[1][1][:300])
     finally:
         eng.set_option("tuned", 1)
-        eng.set_option("ilp", 4)
     th1, c1, l1 = out[1]
     th0, c0, l0 = out[0]
     scale = np.abs(th0).reshape(len(rows), 2, -1).max(axis=2, keepdims=True)

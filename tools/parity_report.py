@@ -37,9 +37,9 @@ for kw in ({}, {"rsd_model": "dispersion"}, {"assume_isotropic": False}):
     wth, wc2, wll = TableWalk(fit, options=kw).likelihood(rows, want_theory=True)
     variants = [{"fast_math": 0}, {"newton": 3, "exp_degree": 5}, {"newton": 2, "exp_degree": 5}]
     if not kw:
-        variants += [{"newton": 2, "exp_degree": 53}, {"newton": 2, "exp_degree": 3}, {"newton": 3, "exp_degree": 3}]
+        variants += [{"newton": 2, "exp_degree": 3}]
     else:
-        variants = [{"fast_math": 0}, {"tuned": 0}, {"tuned": 1}, {"tuned": 1, "newton": 2}]
+        variants = [{"fast_math": 0}, {"tuned": 0}, {"tuned": 1}]
     for opts in variants:
         for k, v in {"fast_math": 1, "ilp": 4, "tuned": 1, "newton": 0, "exp_degree": 0, **opts}.items():
             eng.set_option(k, v)

@@ -205,7 +205,7 @@ K1Pick k1_iso_variant(bool fast, int ilp, int expdeg, int newton) {
     if (kFlags) return {k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, kDefNewton>>, kDefExp};
     if (ilp < 4) return {k_multipoles<K1Cfg<true, kFlags, 1, kDefExp, kDefNewton>>, kDefExp};
 #define VB_V(E, N) if (expdeg == E && newton == N) return {k_multipoles<K1Cfg<true, kFlags, 4, E, N>>, E};
-    VB_V(5, 3) VB_V(5, 2) VB_V(53, 2) VB_V(6, 3) VB_V(3, 3) VB_V(3, 2) VB_V(30, 2)
+    VB_V(5, 3) VB_V(5, 2) VB_V(3, 2)
 #undef VB_V
     return {k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, kDefNewton>>, kDefExp};
 }
@@ -228,28 +228,22 @@ k1_fn pick_k1_fused(bool fast, bool flags, int ilp, int expdeg, int newton) {
 
 // Tuned kernel, the other velocity-integral setups on model coordinates: anisotropic streaming
 // (xi_0 + xi_2 L_2 [+ xi_4 L_4]) and the dispersion model.  Fast math only (the libm test variant of these
-// models is the general kernel); `ilp` 2 selects two nodes in flight for measurement.
+// models is the general kernel).
 // (the dispersion model keeps the cubic refinement whatever the streaming default is: its coordinate iteration
-// amplifies seed errors, see k1_streaming.cuh: disp_nodes; `newton` 2 selects the one-step variant for measurement)
+// amplifies seed errors, see k1_streaming.cuh: disp_nodes)
 template <bool kFlags>
-k1_fn k1_wide_variant(int rsd_model, int n_ell, int ilp, int newton) {
+k1_fn k1_wide_variant(int rsd_model, int n_ell) {
     if (rsd_model == kRsdDispersion) {
-        if (n_ell == 1) {
-            if (newton == 2 && !kFlags) return k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, 2, kRsdDispersion, 1>>;
-            return ilp < 4 ? k_multipoles<K1Cfg<true, kFlags, 2, kDefExp, 3, kRsdDispersion, 1>>
-                           : k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, 3, kRsdDispersion, 1>>;
-        }
+        if (n_ell == 1) return k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, 3, kRsdDispersion, 1>>;
         if (n_ell == 2) return k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, 3, kRsdDispersion, 2>>;
         return k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, 3, kRsdDispersion, 3>>;
     }
-    if (n_ell == 2)
-        return ilp < 4 ? k_multipoles<K1Cfg<true, kFlags, 2, kDefExp, kDefNewton, kRsdStreaming, 2>>
-                       : k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, kDefNewton, kRsdStreaming, 2>>;
+    if (n_ell == 2) return k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, kDefNewton, kRsdStreaming, 2>>;
     return k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, kDefNewton, kRsdStreaming, 3>>;
 }
 
-k1_fn pick_k1_wide(int rsd_model, int n_ell, bool flags, int ilp, int newton) {
-    return flags ? k1_wide_variant<true>(rsd_model, n_ell, ilp, newton) : k1_wide_variant<false>(rsd_model, n_ell, ilp, newton);
+k1_fn pick_k1_wide(int rsd_model, int n_ell, bool flags) {
+    return flags ? k1_wide_variant<true>(rsd_model, n_ell) : k1_wide_variant<false>(rsd_model, n_ell);
 }
 
 // k_small: the few-rows kernel, default math of the tuned families (fast only)
@@ -405,7 +399,7 @@ int launch_k1(vb200_ctx *c, const double *d_params, long long n, const double *d
         for (int i = 0; i < c->md.nx; ++i) a.xw[kMaxNx + i] = c->xw[kMaxNx + i] / scale;
     }
     k1_fn fn = fam == kTunedIso    ? pick_k1(c->opt_fast != 0, c->has_flags, c->opt_ilp, c->opt_expdeg, c->opt_newton).fn
-               : fam == kTunedWide ? pick_k1_wide(c->md.rsd_model, c->md.n_ell, c->has_flags, c->opt_ilp, c->opt_newton)
+               : fam == kTunedWide ? pick_k1_wide(c->md.rsd_model, c->md.n_ell, c->has_flags)
                                    : pick_general(c->md.rsd_model, c->opt_fast != 0);
     if (a.fuse) fn = fused_fn;
     void *kargs[] = {(void *)&a};
@@ -783,7 +777,7 @@ int vb200_create(const vb200_model_tables *m, const vb200_fit_tables *f, int dev
     // allow the large dynamic shared memory carve-out (dense mu grids stage up to ~200 KB)
     c->k1_smem_limit = std::min<size_t>((size_t)prop.sharedMemPerBlockOptin, (size_t)200 * 1024);
     std::vector<const void *> fns;
-    const int exps[] = {5, 53, 6, 3, 30};
+    const int exps[] = {5, 3};
     for (int fl = 0; fl < 2; ++fl) {
         fns.push_back((const void *)pick_k1(false, fl, 1, 6, 3).fn);
         fns.push_back((const void *)pick_k1(true, fl, 1, kDefExp, kDefNewton).fn);
@@ -792,9 +786,7 @@ int vb200_create(const vb200_model_tables *m, const vb200_fit_tables *f, int dev
         fns.push_back((const void *)pick_k1_fused(true, fl, 4, kDefExp, kDefNewton));
         for (int r = 0; r < 2; ++r)
             for (int l = 1; l <= 3; ++l)
-                for (int ilp = 2; ilp <= 4; ilp += 2)
-                    for (int nw = 2; nw <= 3; ++nw)
-                        if (r || l > 1) fns.push_back((const void *)pick_k1_wide(r, l, fl, ilp, nw));
+                if (r || l > 1) fns.push_back((const void *)pick_k1_wide(r, l, fl));
     }
     for (int r = 0; r < 6; ++r) fns.push_back((const void *)pick_general(r >> 1, r & 1));
     for (int r = 0; r < 3; ++r) fns.push_back((const void *)pick_general_fused(r, true));
@@ -828,8 +820,8 @@ int vb200_set_option(vb200_ctx *c, const char *key, int64_t value) {
         c->opt_newton = (int)value;
     } else if (!strcmp(key, "ilp")) c->opt_ilp = value >= 4 ? 4 : (value >= 2 ? 2 : 1);
     else if (!strcmp(key, "exp_degree")) {
-        if (value != 0 && value != 5 && value != 6 && value != 53 && value != 3 && value != 30)
-            return fail(VB200_EINVAL, "exp_degree must be 0 (default), 3, 30, 5, 53 or 6");
+        if (value != 0 && value != 5 && value != 3)
+            return fail(VB200_EINVAL, "exp_degree must be 0 (default), 5 or 3 (1024-entry table, degree-3 remainder)");
         c->opt_expdeg = (int)value;
     } else if (!strcmp(key, "threads")) {
         if (value < 32 || value > 256 || value % 32) return fail(VB200_EINVAL, "threads must be 32..256, multiple of 32");

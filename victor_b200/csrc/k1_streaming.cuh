@@ -56,9 +56,10 @@ __host__ __device__ inline size_t k1_smem_bytes(int ncell, int jper, int nmu, in
 //            comparison path (non-lattice knot sets).
 //   kU     : velocity nodes processed together per loop trip (instruction-level parallelism; a warp
 //            must keep >= 4 independent DFMAs in flight to reach the FP64 issue rate).
-//   kExp   : exp remainder polynomial: 6 = Taylor, 5 = economised, 52 / 53 = economised with its two /
-//            three highest Horner steps in FP32 (common.cuh: gauss_tab_scaled); 3 / 30 = degree 3 on a
-//            1024-entry table, range reduction through the conversion unit / the magic-number FMA (gauss_big).
+//   kExp   : exp remainder polynomial: 5 = economised degree 5 on the 32-entry table (default), 6 = Taylor (libm-free
+//            reference form), 3 = degree 3 on a 1024-entry table with the range reduction through the conversion unit
+//            (gauss_big; measured no faster, kept as the second form).  The FP32-tail forms (52 / 53) and the
+//            magic-number big-table form (30) measured in round 2 remain as device functions for the probes library.
 //   kModel : kRsdStreaming or kRsdDispersion.
 //   kNEll  : real-space multipoles in xi(r, mu_r): 1 (isotropic), 2 (0, 2) or 3 (0, 2, 4).
 //   kMinBlocks : 4 -> 64 registers per thread, 3 -> 80.
