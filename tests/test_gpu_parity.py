@@ -1020,3 +1020,31 @@ def test_small_row_kernel_general_epilogue(boss_blocks, tmp_path):
         assert abs(c[0] - wc[i]) < CHI2_ATOL and abs(l[0] - wl[i]) < CHI2_ATOL
         assert_theory(t, wt[i:i + 1], ns=len(fit3.s))
     fit3.close()
+
+
+def test_hostile_single_rows_through_k_small(fit, golden):
+    """The one-launch kernel with rows far outside any prior, one call each: every block must still draw its ticket
+    (a hang here would mean a block left before the counter), results follow the NaN convention, and the context
+    keeps working -- the golden check at the end would show a corrupted ticket counter or scratch row."""
+    base = np.array([0.47, 0.37, 380.0, 1.0, 1.0])
+    rows = []
+    for col in range(5):
+        for val in (0.0, -1.0, 1e-300, 1e8, 1e300, np.inf, -np.inf, np.nan):
+            r = base.copy()
+            r[col] = val
+            rows.append(r)
+    for kw in ({}, {"rsd_model": "dispersion"}, {"assume_isotropic": False}):
+        eng, _ = fit._fit_engine(kw)
+        for r in rows:
+            before = eng.launch_count()
+            lnl, chi2 = fit.log_likelihood_batch(r[None, :], **kw)
+            assert eng.launch_count() - before == 1
+            if not np.isfinite(lnl[0]):
+                assert lnl[0] == -np.inf and chi2[0] == np.inf                   # ccf_fit.py:477-481
+        two = fit.log_likelihood_batch(np.array([rows[5], base]), **kw)          # a failing and a good row together
+        good = fit.log_likelihood_batch(base[None, :], **kw)
+        assert two[0][1] == good[0][0] and two[1][1] == good[1][0]
+    g = golden("boss_streaming_points")
+    for i in (0, 17, 63):
+        lnl, chi2 = fit.log_likelihood_batch(g["params"][i:i + 1])
+        assert abs(chi2[0] - g["chi2"][i]) < CHI2_ATOL and abs(lnl[0] - g["lnl"][i]) < CHI2_ATOL
