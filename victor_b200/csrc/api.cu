@@ -242,7 +242,22 @@ k1_fn k1_wide_variant(int rsd_model, int n_ell) {
     return k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, kDefNewton, kRsdStreaming, 3>>;
 }
 
-k1_fn pick_k1_wide(int rsd_model, int n_ell, bool flags) {
+// real-space ccf measured from data (ccf_model.py:675-679) on the tuned kernel: knots on the bucket lattice only
+// (the shipped measured-model files).  Streaming four nodes in flight, dispersion two (four spill at 64 registers
+// and are no faster: profiles/r02t_general_kernel_configs.txt)
+k1_fn k1_fromdata_variant(int rsd_model, int n_ell) {
+    if (rsd_model == kRsdDispersion) {
+        if (n_ell == 1) return k_multipoles<K1Cfg<true, false, 2, kDefExp, 3, kRsdDispersion, 1, 4, true>>;
+        if (n_ell == 2) return k_multipoles<K1Cfg<true, false, 2, kDefExp, 3, kRsdDispersion, 2, 4, true>>;
+        return k_multipoles<K1Cfg<true, false, 2, kDefExp, 3, kRsdDispersion, 3, 4, true>>;
+    }
+    if (n_ell == 1) return k_multipoles<K1Cfg<true, false, 4, kDefExp, kDefNewton, kRsdStreaming, 1, 4, true>>;
+    if (n_ell == 2) return k_multipoles<K1Cfg<true, false, 4, kDefExp, kDefNewton, kRsdStreaming, 2, 4, true>>;
+    return k_multipoles<K1Cfg<true, false, 4, kDefExp, kDefNewton, kRsdStreaming, 3, 4, true>>;
+}
+
+k1_fn pick_k1_wide(int rsd_model, int n_ell, bool flags, bool from_data = false) {
+    if (from_data) return k1_fromdata_variant(rsd_model, n_ell);
     return flags ? k1_wide_variant<true>(rsd_model, n_ell) : k1_wide_variant<false>(rsd_model, n_ell);
 }
 
@@ -399,7 +414,7 @@ int launch_k1(vb200_ctx *c, const double *d_params, long long n, const double *d
         for (int i = 0; i < c->md.nx; ++i) a.xw[kMaxNx + i] = c->xw[kMaxNx + i] / scale;
     }
     k1_fn fn = fam == kTunedIso    ? pick_k1(c->opt_fast != 0, c->has_flags, c->opt_ilp, c->opt_expdeg, c->opt_newton).fn
-               : fam == kTunedWide ? pick_k1_wide(c->md.rsd_model, c->md.n_ell, c->has_flags)
+               : fam == kTunedWide ? pick_k1_wide(c->md.rsd_model, c->md.n_ell, c->has_flags, c->md.from_data != 0)
                                    : pick_general(c->md.rsd_model, c->opt_fast != 0);
     if (a.fuse) fn = fused_fn;
     void *kargs[] = {(void *)&a};
@@ -435,6 +450,7 @@ int launch_k2(vb200_ctx *c, const double *d_params, const double *d_theory, long
 // does a likelihood call of n rows go through k_small?  (tuned kernel families with their default math only)
 bool use_small(const vb200_ctx *c, long long n) {
     return c->opt_tiny && c->has_fit && n >= 1 && n <= kSmallRows && c->opt_fast && kernel_family(c) != kGeneral &&
+           !c->md.from_data &&
            c->opt_ilp >= 4 && !c->opt_expdeg && !c->opt_newton && c->opt_nsplit <= 0 &&
            small_smem_bytes(c->md.ncell, c->md.nbucket, c->fd.p, rec_doubles(c), big_table(kDefExp) ? kExpTabBig : kExpTab) <=
                c->k1_smem_limit;
@@ -688,8 +704,12 @@ int vb200_create(const vb200_model_tables *m, const vb200_fit_tables *f, int dev
         bool ells_ok = m->ells[0] == 0;
         for (int i = 1; i < m->n_ell; ++i) ells_ok = ells_ok && m->ells[i] == 2 * i;
         c->family = kGeneral;
-        if (vel_integral && ells_ok && !m->realspace_from_data && m->sv_ny == 0)
-            c->family = (m->rsd_model == VB200_RSD_STREAMING && m->n_ell == 1) ? kTunedIso : kTunedWide;
+        if (vel_integral && ells_ok && m->sv_ny == 0) {
+            if (!m->realspace_from_data)
+                c->family = (m->rsd_model == VB200_RSD_STREAMING && m->n_ell == 1) ? kTunedIso : kTunedWide;
+            else
+                c->family = kTunedWide;   // (demoted to the general kernel below if some bucket holds an interior knot)
+        }
     }
     const size_t nc4 = (size_t)m->ncell * 4;
     if ((rc = upload(c, m->origin, (size_t)m->ncell, &d.origin))) return bail(rc);
@@ -730,6 +750,7 @@ int vb200_create(const vb200_model_tables *m, const vb200_fit_tables *f, int dev
         if ((rc = upload(c, big.data(), big.size(), &d.exp_tab_big))) return bail(rc);
     }
     for (int i = 0; i < m->nbucket; ++i) c->has_flags = c->has_flags || (m->bucket_base[i] < 0);
+    if (m->realspace_from_data && c->has_flags) c->family = kGeneral;   // from-data tuned variants exist without flags only
     for (int i = 0; i < m->nx; ++i) {
         c->xw[i] = m->x[i];
         c->xw[kMaxNx + i] = m->wx[i];
@@ -785,8 +806,10 @@ int vb200_create(const vb200_model_tables *m, const vb200_fit_tables *f, int dev
             for (int nw = 2; nw <= 3; ++nw) fns.push_back((const void *)pick_k1(true, fl, 4, e, nw).fn);
         fns.push_back((const void *)pick_k1_fused(true, fl, 4, kDefExp, kDefNewton));
         for (int r = 0; r < 2; ++r)
-            for (int l = 1; l <= 3; ++l)
+            for (int l = 1; l <= 3; ++l) {
                 if (r || l > 1) fns.push_back((const void *)pick_k1_wide(r, l, fl));
+                if (!fl) fns.push_back((const void *)pick_k1_wide(r, l, false, true));
+            }
     }
     for (int r = 0; r < 6; ++r) fns.push_back((const void *)pick_general(r >> 1, r & 1));
     for (int r = 0; r < 3; ++r) fns.push_back((const void *)pick_general_fused(r, true));

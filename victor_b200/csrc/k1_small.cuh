@@ -319,6 +319,11 @@ __global__ void __launch_bounds__(kSmallPairs * kSmallLanes) k_small(const __gri
         const double Sperp = sj * a.sqmu[k] * scal[1];
         q.Spar = sj * a.mu[k] * scal[2];
         q.Sperp2 = Sperp * Sperp;
+        q.f_over_apar = scal[0] / scal[6];
+        {
+            const double rt = sj * a.sqmu[k];
+            q.rt2 = rt * rt;
+        }
         first_guess<C>(q);
         int mi = l16 * npl;
         const int mend = min(mi + npl, nx);

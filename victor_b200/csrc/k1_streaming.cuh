@@ -63,9 +63,12 @@ __host__ __device__ inline size_t k1_smem_bytes(int ncell, int jper, int nmu, in
 //   kModel : kRsdStreaming or kRsdDispersion.
 //   kNEll  : real-space multipoles in xi(r, mu_r): 1 (isotropic), 2 (0, 2) or 3 (0, 2, 4).
 //   kMinBlocks : 4 -> 64 registers per thread, 3 -> 80.
+//   kFromData : model['realspace_ccf']['from_data'] (ccf_model.py:675-679): the real-space ccf was measured in the
+//            fiducial cosmology, so xi is looked up at (r_par / apar, s_perp / aperp) -- a second radius and cell per node.
 template <bool kFast_, bool kFlags_, int kU_, int kExp_, int kNewton_ = 3, int kModel_ = kRsdStreaming, int kNEll_ = 1,
-          int kMinBlocks_ = 4>
+          int kMinBlocks_ = 4, bool kFromData_ = false>
 struct K1Cfg {
+    static constexpr bool kFromData = kFromData_;    // real-space ccf measured from data: xi at fiducial coordinates
     static constexpr int kMinBlocks = kMinBlocks_;   // resident blocks per SM the register budget is set for
     static constexpr bool kFast = kFast_, kFlags = kFlags_;
     static constexpr int kU = kU_, kExp = kExp_;
@@ -93,6 +96,7 @@ struct QuadCtx {
     int maxscan;
     double first, ifirst;   // dispersion: 1 + G V0(S) / S at the redshift-space point itself, and its reciprocal
     int niter;
+    double f_over_apar, rt2;   // kFromData: u-units -> fiducial Mpc/h along the line of sight; (s_perp / aperp)^2
 };
 
 // shared address of the cell record that holds coordinate u
@@ -139,11 +143,25 @@ __device__ __forceinline__ double xi_plus_one(unsigned ra, double t, double mur)
     return xi1;
 }
 
+// 1 + xi^r for a node at line-of-sight separation rp (u-units): at its own record / coordinate / mu_r, or, for a real-space
+// ccf measured from data, at the fiducial-cosmology point (r_par / apar, s_perp / aperp)            ccf_model.py:675-687
+template <class C>
+__device__ __forceinline__ double xi_node(const QuadCtx &q, unsigned ra, double t, double mur, double rp) {
+    if (!C::kFromData) return xi_plus_one<C>(ra, t, mur);
+    const double rpd = rp * q.f_over_apar;                 // :675
+    const double rd2 = fma(rpd, rpd, q.rt2);               // :677
+    double rd, mud;
+    radius<C::kMath>(rd2, rpd, rd, mud);                   // :678
+    const unsigned rc = cell_record<C>(q, rd);
+    return xi_plus_one<C>(rc, cell_coord(rc, rd), mud);
+}
+
 // U consecutive velocity nodes of one (s_j, mu_k) pair, written stage by stage so that the U
 // dependency chains are interleaved in program order (DFMA latency 8.5 cycles, issue every 2.2).
 template <class C, int U>
 __device__ __forceinline__ double quad_nodes(const K1Args &a, const QuadCtx &q, int mi, double acc) {
     double xm[U], u[U], mur[U], t[U], rq[U], z2[U], g[U];   // kFast: z2 holds zs = z sqrt(16 log2 e), not z^2
+    double rpk[C::kFromData ? U : 1];
     unsigned ra[U];
 #pragma unroll
     for (int i = 0; i < U; ++i) {
@@ -151,6 +169,7 @@ __device__ __forceinline__ double quad_nodes(const K1Args &a, const QuadCtx &q, 
         const double rp = fma(-xm[i], q.kappa, q.Spar);       // ccf_model.py:648-650
         const double u2 = fma(rp, rp, q.Sperp2);              // :651
         radius<C::kMath>(u2, rp, u[i], mur[i]);               // :651-652
+        if (C::kFromData) rpk[i] = rp;
     }
 #pragma unroll
     for (int i = 0; i < U; ++i) ra[i] = cell_record<C>(q, u[i]);
@@ -171,7 +190,7 @@ __device__ __forceinline__ double quad_nodes(const K1Args &a, const QuadCtx &q, 
     for (int i = 0; i < U; ++i) g[i] = C::kFast ? C::gauss(z2[i], q.etab_s) : exp(-0.5 * z2[i]);
 #pragma unroll
     for (int i = 0; i < U; ++i) {
-        const double xi1 = xi_plus_one<C>(ra[i], t[i], mur[i]);                           // :621, :683-687
+        const double xi1 = xi_node<C>(q, ra[i], t[i], mur[i], C::kFromData ? rpk[i] : 0.0);   // :621, :675-687
         acc = fma(a.xw[kMaxNx + mi + i] * (xi1 * rq[i]), g[i], acc);                      // :690
     }
     return acc;
@@ -287,7 +306,7 @@ __device__ __forceinline__ double disp_nodes(const K1Args &a, const QuadCtx &q, 
     }
 #pragma unroll
     for (int i = 0; i < U; ++i) {
-        const double xi1 = xi_plus_one<C>(ra[i], t[i], mur[i]);
+        const double xi1 = xi_node<C>(q, ra[i], t[i], mur[i], rp[i]);
         acc = fma(a.xw[kMaxNx + mi + i] * (xi1 * rq[i]) * rj[i], g[i], acc);   // :671, :690
     }
     return acc;
@@ -440,6 +459,8 @@ __global__ void __launch_bounds__(256, C::kMinBlocks) k_multipoles(const __grid_
     q.upper = upper;
     q.maxscan = m.maxscan;
     q.niter = m.niter;
+    q.f_over_apar = scal[0] / scal[6];
+    q.rt2 = 0.0;
     q.first = q.ifirst = 0.0;
     for (int pidx = tid; pidx < npairs; pidx += nthr) {
         const int jl = pidx / nmu, k = pidx - jl * nmu;
@@ -448,6 +469,10 @@ __global__ void __launch_bounds__(256, C::kMinBlocks) k_multipoles(const __grid_
         const double Sperp = sj * a.sqmu[km] * sperp_f;
         q.Spar = sj * a.mu[km] * spar_f;
         q.Sperp2 = Sperp * Sperp;
+        if (C::kFromData) {
+            const double rt = sj * a.sqmu[km];               // s_perp / aperp in fiducial units (:676)
+            q.rt2 = rt * rt;
+        }
         first_guess<C>(q);
         double acc = 0.0;
         int mi = 0;
