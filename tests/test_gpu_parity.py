@@ -555,6 +555,11 @@ def test_tuned_from_data_kernels_agree_with_general(boss_blocks, kw):
         out[tuned] = eng.likelihood(rows, want_theory=True)
     eng.set_option("tuned", 1)
     (th1, c1, l1), (th0, c0, l0) = out[1], out[0]
+    for i in (3, 700):                                        # single rows: the one-launch kernel, same model
+        before = eng.launch_count()
+        ls, cs, ts = fm.log_likelihood_batch(rows[i:i + 1], return_theory=True, **kw)
+        assert eng.launch_count() - before == 1
+        assert abs(cs[0] - c1[i]) < 1e-8 and np.abs(ts[0] - th1[i]).max() < 1e-12
     ok = np.isfinite(l0) & np.isfinite(l1)
     assert ok.sum() >= len(rows) - 2
     scale = np.abs(th0[ok]).reshape(ok.sum(), 2, -1).max(axis=2, keepdims=True)

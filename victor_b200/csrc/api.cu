@@ -274,7 +274,18 @@ small_fn small_variant(int rsd_model, int n_ell) {
     if (n_ell == 2) return k_small<K1Cfg<true, kFlags, 4, kDefExp, kDefNewton, kRsdStreaming, 2>>;
     return k_small<K1Cfg<true, kFlags, 4, kDefExp, kDefNewton, kRsdStreaming, 3>>;
 }
-small_fn pick_small(int rsd_model, int n_ell, bool flags) {
+small_fn small_fromdata_variant(int rsd_model, int n_ell) {
+    if (rsd_model == kRsdDispersion) {
+        if (n_ell == 1) return k_small<K1Cfg<true, false, 4, kDefExp, 3, kRsdDispersion, 1, 4, true>>;
+        if (n_ell == 2) return k_small<K1Cfg<true, false, 4, kDefExp, 3, kRsdDispersion, 2, 4, true>>;
+        return k_small<K1Cfg<true, false, 4, kDefExp, 3, kRsdDispersion, 3, 4, true>>;
+    }
+    if (n_ell == 1) return k_small<K1Cfg<true, false, 4, kDefExp, kDefNewton, kRsdStreaming, 1, 4, true>>;
+    if (n_ell == 2) return k_small<K1Cfg<true, false, 4, kDefExp, kDefNewton, kRsdStreaming, 2, 4, true>>;
+    return k_small<K1Cfg<true, false, 4, kDefExp, kDefNewton, kRsdStreaming, 3, 4, true>>;
+}
+small_fn pick_small(int rsd_model, int n_ell, bool flags, bool from_data = false) {
+    if (from_data) return small_fromdata_variant(rsd_model, n_ell);   // (lattice knot sets only: see kernel_family)
     return flags ? small_variant<true>(rsd_model, n_ell) : small_variant<false>(rsd_model, n_ell);
 }
 
@@ -450,7 +461,7 @@ int launch_k2(vb200_ctx *c, const double *d_params, const double *d_theory, long
 // does a likelihood call of n rows go through k_small?  (tuned kernel families with their default math only)
 bool use_small(const vb200_ctx *c, long long n) {
     return c->opt_tiny && c->has_fit && n >= 1 && n <= kSmallRows && c->opt_fast && kernel_family(c) != kGeneral &&
-           !c->md.from_data &&
+
            c->opt_ilp >= 4 && !c->opt_expdeg && !c->opt_newton && c->opt_nsplit <= 0 &&
            small_smem_bytes(c->md.ncell, c->md.nbucket, c->fd.p, rec_doubles(c), big_table(kDefExp) ? kExpTabBig : kExpTab) <=
                c->k1_smem_limit;
@@ -507,7 +518,7 @@ int launch_small(vb200_ctx *c, const double *d_params, long long n, double *d_th
     const long long blocks = n * c->fit_ns * nchunk;
     const size_t smem = small_smem_bytes(c->md.ncell, c->md.nbucket, c->fd.p, rec_doubles(c), big ? kExpTabBig : kExpTab);
     void *kargs[] = {(void *)&a, (void *)&sm};
-    CK(cudaLaunchKernel((const void *)pick_small(c->md.rsd_model, c->md.n_ell, c->has_flags), dim3((unsigned)blocks),
+    CK(cudaLaunchKernel((const void *)pick_small(c->md.rsd_model, c->md.n_ell, c->has_flags, c->md.from_data != 0), dim3((unsigned)blocks),
                         dim3(kSmallPairs * kSmallLanes), kargs, smem, st));
     c->launches++;
     return VB200_OK;
@@ -815,7 +826,10 @@ int vb200_create(const vb200_model_tables *m, const vb200_fit_tables *f, int dev
     for (int r = 0; r < 3; ++r) fns.push_back((const void *)pick_general_fused(r, true));
     for (int fl = 0; fl < 2; ++fl)
         for (int r = 0; r < 2; ++r)
-            for (int l = 1; l <= 3; ++l) fns.push_back((const void *)pick_small(r, l, fl));
+            for (int l = 1; l <= 3; ++l) {
+                fns.push_back((const void *)pick_small(r, l, fl));
+                if (!fl) fns.push_back((const void *)pick_small(r, l, false, true));
+            }
     for (const void *fn : fns) {
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->k1_smem_limit);
         if (e != cudaSuccess)
