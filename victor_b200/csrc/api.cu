@@ -11,17 +11,11 @@
 
 #include "../../include/victor_b200.h"
 
-// defaults of the tuned kernel's math (vb200_set_option "exp_degree", "newton" select the others)
-#ifndef VB200_DEFAULT_EXP
-#define VB200_DEFAULT_EXP 5
-#endif
-#ifndef VB200_DEFAULT_NEWTON
-#define VB200_DEFAULT_NEWTON 2   // one Newton step on the MUFU seeds: +3.9 % and 5.5e-12 / 7.5e-10 measured margins
-#endif
 #include "k1_general.cuh"
 #include "k1_small.cuh"
 #include "k1_streaming.cuh"
 #include "k2_chi2.cuh"
+#include "kernels.h"
 
 using namespace vb200;
 
@@ -183,127 +177,6 @@ int check_model(const vb200_model_tables *m) {
     return VB200_OK;
 }
 
-typedef void (*k1_fn)(const K1Args);
-
-// ---- kernel variants in this build --------------------------------------------------------------------
-// Tuned kernel, streaming model + isotropic xi (the BOSS likelihood).  Default <fast, U = 4, exp kDefExp,
-// refinement kDefNewton>; the others exist for parity tests (libm math) and for measurement (ILP, exp
-// polynomial, refinement order).  Tables with knots off the bucket lattice (kFlags) get the default and the
-// libm variant only.
-constexpr int kDefExp = VB200_DEFAULT_EXP, kDefNewton = VB200_DEFAULT_NEWTON;
-
-// a kernel and the exp variant it was built with (the host folds that variant's argument scale into the weights
-// and sizes the exp table in shared memory accordingly)
-struct K1Pick {
-    k1_fn fn;
-    int exp;
-};
-
-template <bool kFlags>
-K1Pick k1_iso_variant(bool fast, int ilp, int expdeg, int newton) {
-    if (!fast) return {k_multipoles<K1Cfg<false, kFlags, 1, 6>>, 6};
-    if (kFlags) return {k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, kDefNewton>>, kDefExp};
-    if (ilp < 4) return {k_multipoles<K1Cfg<true, kFlags, 1, kDefExp, kDefNewton>>, kDefExp};
-#define VB_V(E, N) if (expdeg == E && newton == N) return {k_multipoles<K1Cfg<true, kFlags, 4, E, N>>, E};
-    VB_V(5, 3) VB_V(5, 2) VB_V(3, 2)
-#undef VB_V
-    return {k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, kDefNewton>>, kDefExp};
-}
-
-K1Pick pick_k1(bool fast, bool flags, int ilp, int expdeg, int newton) {
-    if (!expdeg) expdeg = kDefExp;
-    if (!newton) newton = kDefNewton;
-    return flags ? k1_iso_variant<true>(fast, ilp, expdeg, newton) : k1_iso_variant<false>(fast, ilp, expdeg, newton);
-}
-
-// fused likelihood epilogue: for the default tuned configuration only (nullptr otherwise: the caller then
-// launches K2 after the plain kernel)
-k1_fn pick_k1_fused(bool fast, bool flags, int ilp, int expdeg, int newton) {
-    if (!expdeg) expdeg = kDefExp;
-    if (!newton) newton = kDefNewton;
-    if (!fast || ilp < 4 || expdeg != kDefExp || newton != kDefNewton) return nullptr;
-    return flags ? k_multipoles<K1Cfg<true, true, 4, kDefExp, kDefNewton>, true>
-                 : k_multipoles<K1Cfg<true, false, 4, kDefExp, kDefNewton>, true>;
-}
-
-// Tuned kernel, the other velocity-integral setups on model coordinates: anisotropic streaming
-// (xi_0 + xi_2 L_2 [+ xi_4 L_4]) and the dispersion model.  Fast math only (the libm test variant of these
-// models is the general kernel).
-// (the dispersion model keeps the cubic refinement whatever the streaming default is: its coordinate iteration
-// amplifies seed errors, see k1_streaming.cuh: disp_nodes)
-template <bool kFlags>
-k1_fn k1_wide_variant(int rsd_model, int n_ell) {
-    if (rsd_model == kRsdDispersion) {
-        if (n_ell == 1) return k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, 3, kRsdDispersion, 1>>;
-        if (n_ell == 2) return k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, 3, kRsdDispersion, 2>>;
-        return k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, 3, kRsdDispersion, 3>>;
-    }
-    if (n_ell == 2) return k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, kDefNewton, kRsdStreaming, 2>>;
-    return k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, kDefNewton, kRsdStreaming, 3>>;
-}
-
-// real-space ccf measured from data (ccf_model.py:675-679) on the tuned kernel: knots on the bucket lattice only
-// (the shipped measured-model files).  Streaming four nodes in flight, dispersion two (four spill at 64 registers
-// and are no faster: profiles/r02t_general_kernel_configs.txt)
-k1_fn k1_fromdata_variant(int rsd_model, int n_ell) {
-    if (rsd_model == kRsdDispersion) {
-        if (n_ell == 1) return k_multipoles<K1Cfg<true, false, 2, kDefExp, 3, kRsdDispersion, 1, 4, true>>;
-        if (n_ell == 2) return k_multipoles<K1Cfg<true, false, 2, kDefExp, 3, kRsdDispersion, 2, 4, true>>;
-        return k_multipoles<K1Cfg<true, false, 2, kDefExp, 3, kRsdDispersion, 3, 4, true>>;
-    }
-    if (n_ell == 1) return k_multipoles<K1Cfg<true, false, 4, kDefExp, kDefNewton, kRsdStreaming, 1, 4, true>>;
-    if (n_ell == 2) return k_multipoles<K1Cfg<true, false, 4, kDefExp, kDefNewton, kRsdStreaming, 2, 4, true>>;
-    return k_multipoles<K1Cfg<true, false, 4, kDefExp, kDefNewton, kRsdStreaming, 3, 4, true>>;
-}
-
-k1_fn pick_k1_wide(int rsd_model, int n_ell, bool flags, bool from_data = false) {
-    if (from_data) return k1_fromdata_variant(rsd_model, n_ell);
-    return flags ? k1_wide_variant<true>(rsd_model, n_ell) : k1_wide_variant<false>(rsd_model, n_ell);
-}
-
-// k_small: the few-rows kernel, default math of the tuned families (fast only)
-typedef void (*small_fn)(const K1Args, const SmallArgs);
-template <bool kFlags>
-small_fn small_variant(int rsd_model, int n_ell) {
-    if (rsd_model == kRsdDispersion) {
-        if (n_ell == 1) return k_small<K1Cfg<true, kFlags, 4, kDefExp, 3, kRsdDispersion, 1>>;
-        if (n_ell == 2) return k_small<K1Cfg<true, kFlags, 4, kDefExp, 3, kRsdDispersion, 2>>;
-        return k_small<K1Cfg<true, kFlags, 4, kDefExp, 3, kRsdDispersion, 3>>;
-    }
-    if (n_ell == 1) return k_small<K1Cfg<true, kFlags, 4, kDefExp, kDefNewton>>;
-    if (n_ell == 2) return k_small<K1Cfg<true, kFlags, 4, kDefExp, kDefNewton, kRsdStreaming, 2>>;
-    return k_small<K1Cfg<true, kFlags, 4, kDefExp, kDefNewton, kRsdStreaming, 3>>;
-}
-small_fn small_fromdata_variant(int rsd_model, int n_ell) {
-    if (rsd_model == kRsdDispersion) {
-        if (n_ell == 1) return k_small<K1Cfg<true, false, 4, kDefExp, 3, kRsdDispersion, 1, 4, true>>;
-        if (n_ell == 2) return k_small<K1Cfg<true, false, 4, kDefExp, 3, kRsdDispersion, 2, 4, true>>;
-        return k_small<K1Cfg<true, false, 4, kDefExp, 3, kRsdDispersion, 3, 4, true>>;
-    }
-    if (n_ell == 1) return k_small<K1Cfg<true, false, 4, kDefExp, kDefNewton, kRsdStreaming, 1, 4, true>>;
-    if (n_ell == 2) return k_small<K1Cfg<true, false, 4, kDefExp, kDefNewton, kRsdStreaming, 2, 4, true>>;
-    return k_small<K1Cfg<true, false, 4, kDefExp, kDefNewton, kRsdStreaming, 3, 4, true>>;
-}
-small_fn pick_small(int rsd_model, int n_ell, bool flags, bool from_data = false) {
-    if (from_data) return small_fromdata_variant(rsd_model, n_ell);   // (lattice knot sets only: see kernel_family)
-    return flags ? small_variant<true>(rsd_model, n_ell) : small_variant<false>(rsd_model, n_ell);
-}
-
-k1_fn pick_general_fused(int rsd_model, bool fast) {
-    if (!fast) return nullptr;
-    if (rsd_model == kRsdStreaming) return k_multipoles_general<kRsdStreaming, true, true>;
-    if (rsd_model == kRsdDispersion) return k_multipoles_general<kRsdDispersion, true, true>;
-    return k_multipoles_kaiser<true, true>;
-}
-
-k1_fn pick_general(int rsd_model, bool fast) {
-    if (rsd_model == kRsdStreaming)
-        return fast ? k_multipoles_general<kRsdStreaming, true> : k_multipoles_general<kRsdStreaming, false>;
-    if (rsd_model == kRsdDispersion)
-        return fast ? k_multipoles_general<kRsdDispersion, true> : k_multipoles_general<kRsdDispersion, false>;
-    return fast ? k_multipoles_kaiser<true> : k_multipoles_kaiser<false>;
-}
-
 // which kernel family serves this context with the current options
 //   kTunedIso : streaming + isotropic xi + model coordinates + sigma_v(r): every variant of pick_k1
 //   kTunedWide: anisotropic streaming or dispersion on model coordinates + sigma_v(r), fast math, "tuned" option on
@@ -445,14 +318,7 @@ int launch_k2(vb200_ctx *c, const double *d_params, const double *d_theory, long
     a.n = n;
     a.chi2 = d_chi2;
     a.lnl = d_lnl;
-    if (n <= (long long)c->sm_count * 4) {
-        // few rows: a block per row, so that one row's matrix reads are spread over eight warps
-        k_chi2_block<<<(unsigned)n, kK2Warps * 32, (size_t)fused_fit_doubles(c->fd.p) * sizeof(double), st>>>(a);
-    } else {
-        const long long rows_per_block = (long long)kK2Warps * kK2RowsPerWarp;
-        const long long blocks = (n + rows_per_block - 1) / rows_per_block;
-        k_chi2<<<(unsigned)blocks, kK2Warps * 32, k2_smem_bytes(c->fd.p), st>>>(a);
-    }
+    CK(launch_k2_kernels(a, n, c->sm_count, st));
     CK(cudaGetLastError());
     c->launches++;
     return VB200_OK;
@@ -617,6 +483,8 @@ void fill_exp_table(double *t, int n = kExpTab) {
 
 }  // namespace
 
+// everything else in the library is compiled with hidden visibility: the C ABI below is all it exports
+#pragma GCC visibility push(default)
 extern "C" {
 
 const char *vb200_version(void) { return "victor_b200 0.1.0 (sm_100a)"; }
@@ -1140,3 +1008,4 @@ int vb200_likelihood(vb200_ctx *c, const double *params, int64_t n, double *theo
 }
 
 }  // extern "C"
+#pragma GCC visibility pop

@@ -170,9 +170,9 @@ __device__ __forceinline__ int lds_s32(unsigned addr) {
 //   kExpPoly  : degree-6 Taylor (truncation 3e-18)
 //   kExpPoly5 : degree-5 economised fit at Chebyshev nodes (max relative error 1.4e-16; from a
 //               60-digit mpmath solve), one FMA less
-__constant__ double kExpPoly[6] = {2.166084939249829e-02, 2.3459619820224677e-04, 1.6938509724371819e-06,
+static __constant__ double kExpPoly[6] = {2.166084939249829e-02, 2.3459619820224677e-04, 1.6938509724371819e-06,
                                    9.172562701824643e-09, 3.9737099845494154e-11, 1.4345655584131932e-13};
-__constant__ double kExpPoly5[5] = {2.166084939249829e-02, 2.345961981994449e-04, 1.6938509724285119e-06,
+static __constant__ double kExpPoly5[5] = {2.166084939249829e-02, 2.345961981994449e-04, 1.6938509724285119e-06,
                                     9.172607532092245e-09, 3.9737238568525983e-11};
 
 // exp(-z2/2) from the 2^(j/32) table at 32-bit shared address `etab_s`
@@ -208,7 +208,7 @@ __device__ __forceinline__ double gauss_tab(double z2, unsigned etab_s) {
 // zs^2 only ever appears inside an FMA (exact product, one instruction and four register reads
 // fewer than forming z^2 first).  kGaussScale is folded into the sigma_v table by the caller.
 constexpr double kGaussScale = 4.804489635145799;   // sqrt(16 log2(e))
-__constant__ float kExpPoly5f[5] = {2.166084939249829e-02f, 2.345961981994449e-04f, 1.6938509724285119e-06f,
+static __constant__ float kExpPoly5f[5] = {2.166084939249829e-02f, 2.345961981994449e-04f, 1.6938509724285119e-06f,
                                     9.172607532092245e-09f, 3.9737238568525983e-11f};
 
 // kDeg: 6 Taylor, 5 economised, 52 / 53 economised with the two / three highest Horner steps in FP32:
@@ -260,7 +260,7 @@ __device__ __forceinline__ double gauss_tab_scaled(double zs, unsigned etab_s) {
 //   then rounded once (relative 1.1e-16, i.e. z^2/2 * 1.1e-16 relative in the result -- the conditioning of
 //   exp(-z^2/2) itself, and what libm's exp(-0.5 * z * z) carries too).
 constexpr double kGaussScaleBig = 27.178297609216609367;   // sqrt(512 log2(e))
-__constant__ double kExpPoly3[3] = {0.0006769015435155716, 2.2909785144706367e-07, 5.169222960550727e-11};
+static __constant__ double kExpPoly3[3] = {0.0006769015435155716, 2.2909785144706367e-07, 5.169222960550727e-11};
 
 template <bool kCvt>
 __device__ __forceinline__ double gauss_big(double zs, unsigned etab_s) {

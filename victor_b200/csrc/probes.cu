@@ -66,6 +66,7 @@ void fill_exp_tables(double *t) {   // 2^(j/32) then 2^(j/1024)
 
 }  // namespace
 
+#pragma GCC visibility push(default)
 extern "C" {
 
 const char *vb200p_last_error(void) { return g_err.c_str(); }
@@ -272,3 +273,4 @@ int vb200p_fp64_peak(int device, int iters, double *tflops, double *ms) {
 }
 
 }  // extern "C"
+#pragma GCC visibility pop
