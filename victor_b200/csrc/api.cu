@@ -334,8 +334,8 @@ bool use_small(const vb200_ctx *c, long long n) {
 }
 
 // theory (optional), chi2 and lnL of n <= kSmallRows rows on the fit's grids in ONE launch (k1_small.cuh)
-int launch_small(vb200_ctx *c, const double *d_params, long long n, double *d_theory, double *d_chi2, double *d_lnl,
-                 cudaStream_t st, unsigned *done = nullptr) {
+// scratch of k_small: allocated outside any stream capture (cudaMalloc is not allowed inside one)
+int ensure_small_scratch(vb200_ctx *c) {
     if (!c->tiny_xi) {
         double *xi = nullptr;
         unsigned *tk = nullptr;
@@ -350,6 +350,12 @@ int launch_small(vb200_ctx *c, const double *d_params, long long n, double *d_th
         c->tiny_xi = xi;
         c->tiny_tickets = tk;
     }
+    return VB200_OK;
+}
+
+int launch_small(vb200_ctx *c, const double *d_params, long long n, double *d_theory, double *d_chi2, double *d_lnl,
+                 cudaStream_t st, unsigned *done = nullptr) {
+    if (!c->tiny_xi) return fail(VB200_ECUDA, "internal: k_small scratch not allocated");
     K1Args a{};
     a.m = c->md;
     a.params = d_params;
@@ -893,6 +899,7 @@ int vb200_likelihood(vb200_ctx *c, const double *params, int64_t n, double *theo
             if (cudaHostGetDevicePointer(&dp, pin, 0) == cudaSuccess) c->pin_dev = static_cast<double *>(dp);
             else cudaGetLastError();
         }
+        if (use_small(c, n) && (rc = ensure_small_scratch(c))) return rc;
         double *h_out = c->pin + (size_t)kSmallCall * VB200_NPAR;
         memcpy(c->pin, params, (size_t)n * VB200_NPAR * sizeof(double));
         const bool mapped = small_is_mapped(c, n);
@@ -960,6 +967,7 @@ int vb200_likelihood(vb200_ctx *c, const double *params, int64_t n, double *theo
     const bool theory_to_host = theory && d_theory != theory;
     if ((chi2 || lnlike) && use_small(c, n)) {
         // a handful of rows (device buffers, or the theory vectors wanted too): still one launch
+        if ((rc = ensure_small_scratch(c))) return rc;
         if ((rc = launch_small(c, d_params, n, theory ? d_theory : nullptr, d_chi2, d_lnl, st))) return rc;
         if (theory_to_host) CK(cudaMemcpyAsync(theory, d_theory, (size_t)n * p * sizeof(double), cudaMemcpyDeviceToHost, st));
         if (chi2 && d_chi2 != chi2) CK(cudaMemcpyAsync(chi2, d_chi2, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
