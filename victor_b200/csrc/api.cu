@@ -1,6 +1,7 @@
 // C-ABI host side of libvictor_b200.so: context (device copies of the host-built tables),
 // staging of host buffers, kernel launches.  See include/victor_b200.h for the contract.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -928,6 +929,7 @@ int vb200_likelihood(vb200_ctx *c, const double *params, int64_t n, double *theo
             }
         }
         if (!done) CK(cudaStreamSynchronize(st));
+        std::atomic_thread_fence(std::memory_order_acquire);   // results are read after the flags, not before
         memcpy(chi2, h_out, (size_t)n * sizeof(double));
         memcpy(lnlike, h_out + n, (size_t)n * sizeof(double));
         return VB200_OK;
