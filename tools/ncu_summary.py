@@ -41,7 +41,7 @@ hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
 data = rows[2:]
 mx = max(float(r[ix['Instructions Executed']] or 0) for r in data)
-hot = [r for r in data if float(r[ix['Instructions Executed']] or 0) > 0.2 * mx]
+hot = [r for r in data if float(r[ix['Instructions Executed']] or 0) > 0.05 * mx]
 cls = collections.Counter()
 wf = 0.0
 for r in hot:
