@@ -649,6 +649,26 @@ def run_gpu(args):
         if os.path.isfile(prof):
             with open(prof) as fh:
                 roofline["traffic"] = json.load(fh).get("dram_bytes_per_launch")
+        # what the committed `ncu --set full` capture of this kernel says limits it (static figures from profiles/,
+        # not measured in this run): the FP64 pipe and the shared-memory crossbar together
+        prof = os.path.join(ROOT, "profiles", "r02p_k_multipoles_streaming_ncu.json")
+        if os.path.isfile(prof):
+            with open(prof) as fh:
+                cap = json.load(fh)
+            met = cap.get("metrics", {})
+
+            def pct(key):
+                try:
+                    return float(str(met.get(key, "")).split()[0])
+                except (ValueError, IndexError):
+                    return None
+            roofline["ncu_capture"] = {
+                "source": "profiles/r02p_k_multipoles_streaming_ncu.json",
+                "fp64_pipe_pct_of_peak": pct("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed"),
+                "smem_wavefronts_pct_of_peak": pct("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
+                "issue_slots_pct": pct("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                "fp64_instructions_per_point": cap.get("fp64_per_point"),
+                "smem_wavefronts_per_point": cap.get("smem_wavefronts_per_point")}
         cpu = None
         if world == 1 and not args.no_cpu:
             cpu = cpu_baseline_leg()
