@@ -55,6 +55,10 @@ def hubble_ratio(cosmology, z):
     return float(np.sqrt(om * zp1 ** 3 + curv * zp1 ** 2 + ol))
 
 
+# defaults of the columns a parameter table may leave out, in tables.PARAM_ORDER (bias NaN: the model's own, :359)
+_DEFAULT_ROW = np.array([np.nan, np.nan, 380.0, 1.0, 1.0, 1.0, 1.0, 1.0, 0.0, np.nan])
+
+
 def point_to_row(params):
     """One parameter point given as a dict of plain numbers -> the list of its NPAR row values (the MCMC step's
     fast path), or None if some value is not a scalar.  Same conventions as ``params_to_rows``."""
@@ -117,8 +121,9 @@ def params_to_rows(params, n_hint=None):
         raise InputError(f"parameter table must have between 3 and {_tables.NPAR} columns "
                          f"{_tables.PARAM_ORDER}")
     rows = np.empty((arr.shape[0], _tables.NPAR))
-    for i, name in enumerate(_tables.PARAM_ORDER):
-        rows[:, i] = arr[:, i] if i < arr.shape[1] else defaults[name]
+    k = arr.shape[1]
+    rows[:, :k] = arr
+    rows[:, k:] = _DEFAULT_ROW[k:]
     return rows
 
 
