@@ -115,9 +115,10 @@ struct vb200_ctx {
     int opt_tuned = 1;            // 0: force the general kernel (A/B checks of the tuned kernels)
     int opt_tiny = 1;             // calls of <= kSmallRows rows: one launch of k_small instead of K1 + K2 (0: off)
     int opt_mapped = 1;           // k_small writes (chi2 | lnL) straight into page-locked host memory and raises a flag
-                                  // the host polls: no device-to-host copy node, no stream synchronise.  (Reading the
-                                  // ROWS from host memory as well was 2.4x slower: 210 blocks x tens of uncached
-                                  // PCIe reads, profiles/r02l_small_call_latency.txt -- they still go by a copy node.)
+                                  // the host polls, and takes its one or two rows from the kernel parameters: one
+                                  // bare launch, no copy nodes, no stream synchronise.  (Reading the rows from mapped
+                                  // host memory was 2.4x slower: 210 blocks x tens of uncached PCIe reads,
+                                  // profiles/r02l_small_call_latency.txt.)
     double *pin_dev = nullptr;    // device-side address of `pin` (unified addressing), null if not available
     double *tiny_xi = nullptr;    // k_small scratch: xi(s, mu) of kSmallRows rows, and the rows' ticket counters
     unsigned *tiny_tickets = nullptr;
@@ -355,7 +356,7 @@ int ensure_small_scratch(vb200_ctx *c) {
 }
 
 int launch_small(vb200_ctx *c, const double *d_params, long long n, double *d_theory, double *d_chi2, double *d_lnl,
-                 cudaStream_t st, unsigned *done = nullptr) {
+                 cudaStream_t st, unsigned *done = nullptr, const double *inline_rows = nullptr) {
     if (!c->tiny_xi) return fail(VB200_ECUDA, "internal: k_small scratch not allocated");
     K1Args a{};
     a.m = c->md;
@@ -387,6 +388,8 @@ int launch_small(vb200_ctx *c, const double *d_params, long long n, double *d_th
 #else
     SmallArgs sm{c->tiny_xi, c->tiny_tickets, d_theory, done};
 #endif
+    sm.inline_rows = inline_rows ? 1 : 0;
+    if (inline_rows) memcpy(sm.rows, inline_rows, (size_t)n * VB200_NPAR * sizeof(double));
     const int nchunk = (c->fit_nmu + kSmallPairs - 1) / kSmallPairs;
     const long long blocks = n * c->fit_ns * nchunk;
     const size_t smem = small_smem_bytes(c->md.ncell, c->md.nbucket, c->fd.p, rec_doubles(c), big ? kExpTabBig : kExpTab);
@@ -402,17 +405,14 @@ int launch_small(vb200_ctx *c, const double *d_params, long long n, double *d_th
 constexpr size_t kPinDoubles = (size_t)kSmallCall * (VB200_NPAR + 2) + 8;
 unsigned *pin_flags(double *pin) { return reinterpret_cast<unsigned *>(pin + (size_t)kSmallCall * (VB200_NPAR + 2)); }
 
-// does this small call run without copy nodes (k_small on the mapped staging area, completion by flag)?
+// does this small call run as one bare launch (k_small with the rows in its parameters, results through the mapped
+// staging area, completion by flag)?
 bool small_is_mapped(const vb200_ctx *c, int64_t n) { return c->opt_mapped && c->pin_dev && use_small(c, n); }
 
 int small_sequence(vb200_ctx *c, int64_t n, cudaStream_t st) {
     int rc;
     double *h_out = c->pin + (size_t)kSmallCall * VB200_NPAR, *d_out = c->d_small + (size_t)kSmallCall * VB200_NPAR;
     CK(cudaMemcpyAsync(c->d_small, c->pin, (size_t)n * VB200_NPAR * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (small_is_mapped(c, n)) {
-        double *m_out = c->pin_dev + (size_t)kSmallCall * VB200_NPAR;
-        return launch_small(c, c->d_small, n, nullptr, m_out, m_out + n, st, pin_flags(c->pin_dev));
-    }
     if (use_small(c, n)) {
         if ((rc = launch_small(c, c->d_small, n, nullptr, d_out, d_out + n, st))) return rc;
     } else {
@@ -908,7 +908,13 @@ int vb200_likelihood(vb200_ctx *c, const double *params, int64_t n, double *theo
         if (mapped)
             for (int64_t i = 0; i < n; ++i) flags[i] = 0u;
         bool replayed = false;
-        if (c->opt_graph && c->graphs_ok && (c->small_n == n || build_small_graph(c, n))) {
+        if (mapped) {
+            // one launch and nothing else on the stream: the rows ride in the kernel parameters, the results come back
+            // through mapped memory (a graph would only wrap this single node)
+            double *m_out = c->pin_dev + (size_t)kSmallCall * VB200_NPAR;
+            if ((rc = launch_small(c, nullptr, n, nullptr, m_out, m_out + n, st, pin_flags(c->pin_dev), params))) return rc;
+            replayed = true;
+        } else if (c->opt_graph && c->graphs_ok && (c->small_n == n || build_small_graph(c, n))) {
             if (cudaGraphLaunch(c->small_exec, st) == cudaSuccess) {
                 c->launches += c->small_launches;
                 replayed = true;

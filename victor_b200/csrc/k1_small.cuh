@@ -42,6 +42,8 @@ struct SmallArgs {
     double *theory;          // [n][p] or null
     unsigned *done;          // [n] or null: host-mapped flags, set to 1 (after a system-scope fence) once a row's
                              // chi2 / lnL have been written -- the host may poll them instead of synchronising
+    int inline_rows;         // 1: the parameter rows travel in `rows` below (kernel-parameter constant bank) instead of
+    double rows[kSmallRows][kNPar];   // a device buffer: no copy node in front of the kernel, no global load in its prologue
 };
 
 // the last block stages both precision matrices of its row's bracket in shared memory (asynchronous copies that
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(kSmallPairs * kSmallLanes) k_small(const __gri
     const int rem = blockIdx.x - (int)(row * per_row);
     const int j = rem / nchunk, kc = rem - j * nchunk;
 
-    const double *pr = a.params + row * kNPar;
+    const double *pr = sm.inline_rows ? sm.rows[row] : a.params + row * kNPar;
     const double beta = m.beta_dependent ? pr[1] : m.beta_fixed;
 
     // ---- prologue: as in k_multipoles (row scalars, then this row's cell records) ----
