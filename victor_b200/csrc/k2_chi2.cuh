@@ -22,26 +22,39 @@ constexpr int kK2MaxChunks = 8;  // p <= 256
 // arithmetic, and res^T M res does not depend on which index is contracted first).  The partition is
 // the same whether one warp walks through all the partials (k_chi2) or the warps of a block take one
 // each (block_chi2), so both give bit-identical chi-squares.
-__device__ __forceinline__ double quad_partial(const double *M, const double *res, int p, int lane, int part) {
-    double y[kK2MaxChunks];
+// kC = number of 32-column chunks actually present (p <= 32 kC): the loops below run over kC chunks only -- with the
+// data vector's p = 60 that is 2 of the kK2MaxChunks = 8 the general form walks through with predicates
+template <int kC>
+__device__ __forceinline__ double quad_partial_t(const double *M, const double *res, int p, int lane, int part) {
+    double y[kC];
 #pragma unroll
-    for (int c = 0; c < kK2MaxChunks; ++c) y[c] = 0.0;
+    for (int c = 0; c < kC; ++c) y[c] = 0.0;
     for (int i = part; i < p; i += kK2Warps) {
         const double ri = res[i];
         const double *rowp = M + (size_t)i * p;
 #pragma unroll
-        for (int c = 0; c < kK2MaxChunks; ++c) {
+        for (int c = 0; c < kC; ++c) {
             const int j = lane + 32 * c;
             if (j < p) y[c] = fma(rowp[j], ri, y[c]);
         }
     }
     double q = 0.0;
 #pragma unroll
-    for (int c = 0; c < kK2MaxChunks; ++c) {
+    for (int c = 0; c < kC; ++c) {
         const int j = lane + 32 * c;
         if (j < p) q = fma(y[c], res[j], q);
     }
     return warp_sum(q);
+}
+
+__device__ __forceinline__ double quad_partial(const double *M, const double *res, int p, int lane, int part) {
+    switch ((p + 31) >> 5) {   // same sums in the same order whichever instantiation runs
+        case 1: return quad_partial_t<1>(M, res, p, lane, part);
+        case 2: return quad_partial_t<2>(M, res, p, lane, part);
+        case 3: return quad_partial_t<3>(M, res, p, lane, part);
+        case 4: return quad_partial_t<4>(M, res, p, lane, part);
+        default: return quad_partial_t<kK2MaxChunks>(M, res, p, lane, part);
+    }
 }
 
 __device__ __forceinline__ double quad_form(const double *M, const double *res, int p, int lane) {
