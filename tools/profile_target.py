@@ -71,7 +71,8 @@ def main():
         times.append(a.elapsed_time(b))
     print(f"batch={n} fast={args.fast} threads={args.threads} nsplit={args.nsplit} ilp={args.ilp} expdeg={args.expdeg} newton={args.newton} fuse={args.fuse} theory={args.theory} sigma_v={args.sigma_v} rsd={args.rsd} aniso={args.aniso} tuned={args.tuned} lib={os.path.basename(os.environ.get('VICTOR_B200_LIB', 'default'))} "
           f"ms={['%.3f' % t for t in times]} evals/s={n / (min(times) * 1e-3):.4g} "
-          f"chi2[0]={float(d_chi2[0]):.10f}")
+          f"chi2[0]={float(d_chi2[0]):.10f} "
+          f"digest={__import__('hashlib').sha1(d_theory.cpu().numpy().tobytes() + d_chi2.cpu().numpy().tobytes()).hexdigest()[:12]}")
     fit.close()
 
 
