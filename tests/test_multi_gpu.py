@@ -31,6 +31,10 @@ lnl, chi2, (lo, hi) = evaluate_sharded(fit.log_likelihood_batch, rows, gather=Tr
 # the device-to-device form: slices evaluated into device buffers, all-gather over NCCL, one D2H
 lnl_d, chi2_d, (lo_d, hi_d) = likelihood_sharded(fit, rows, gather=True)
 assert (lo_d, hi_d) == (lo, hi) and np.array_equal(lnl_d, lnl) and np.array_equal(chi2_d, chi2)
+for m in (1000, 1001, 37, 1001):          # the gather buffers are kept between calls: other sizes, then the first again
+    l_e, c_e, _ = evaluate_sharded(fit.log_likelihood_batch, rows[:m], gather=True)
+    l_d, c_d, _ = likelihood_sharded(fit, rows[:m], gather=True)
+    assert np.array_equal(l_d, l_e) and np.array_equal(c_d, c_e), m
 lnl_s, chi2_s, _ = likelihood_sharded(fit, rows, gather=False)
 assert np.array_equal(lnl_s, lnl[lo:hi]) and np.array_equal(chi2_s, chi2[lo:hi])
 np.savez(os.path.join(os.environ["VB200_OUT"], f"rank{rank}.npz"), lnl=lnl, chi2=chi2, lo=lo, hi=hi)

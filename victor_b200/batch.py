@@ -95,18 +95,38 @@ def likelihood_sharded(fit, rows, gather=True, group=None, **kwargs):
     per = bounds[0][1] - bounds[0][0]
     eng, _ = fit._fit_engine(kwargs)
     dev = torch.device("cuda", eng.device)
-    table = torch.full((world, 2, per), float("nan"), dtype=torch.float64, device=dev) if gather else None
-    mine = table[rank] if gather else torch.empty((2, per), dtype=torch.float64, device=dev)
-    if hi > lo:
-        fit.log_likelihood_device(rows[lo:hi], out=mine, **kwargs)
     if not gather:
+        mine = torch.empty((2, per), dtype=torch.float64, device=dev)
+        if hi > lo:
+            fit.log_likelihood_device(rows[lo:hi], out=mine, **kwargs)
         host = mine[:, :hi - lo].cpu().numpy()
         return host[0], host[1], (lo, hi)
+    table, mirror = _gather_buffers(fit, world, per, dev)
+    mine = table[rank]
+    if hi > lo:
+        fit.log_likelihood_device(rows[lo:hi], out=mine, **kwargs)
     dist.all_gather_into_tensor(table.view(-1), mine.reshape(-1), group=group)   # in place: rank r's slot is table[r]
-    host = table.cpu().numpy()
+    mirror.copy_(table, non_blocking=True)                                       # one DMA into page-locked memory
+    torch.cuda.current_stream(dev).synchronize()
+    host = mirror.numpy()
     lnl_all = np.concatenate([host[r, 0, :b - a] for r, (a, b) in enumerate(bounds)])
     chi2_all = np.concatenate([host[r, 1, :b - a] for r, (a, b) in enumerate(bounds)])
     return lnl_all, chi2_all, (lo, hi)
+
+
+def _gather_buffers(fit, world, per, dev):
+    """The gather table [world][lnL | chi2][per] on the device and its page-locked host mirror, kept on the fit
+    between calls of the same shape.  Slots start NaN-filled; a rank only writes the rows it owns and the padding
+    behind a short last slice is never read."""
+    import torch
+    key = (world, per, dev.index)
+    cache = fit.__dict__.setdefault("_gather_cache", {})
+    if key not in cache:
+        cache.clear()                                                            # one shape at a time
+        table = torch.full((world, 2, per), float("nan"), dtype=torch.float64, device=dev)
+        mirror = torch.empty((world, 2, per), dtype=torch.float64).pin_memory()
+        cache[key] = (table, mirror)
+    return cache[key]
 
 
 class MultiDeviceFit:

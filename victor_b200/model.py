@@ -531,3 +531,4 @@ class CCFModel:
         for eng in self._engines.values():
             eng.close()
         self._engines = {}
+        self.__dict__.pop("_gather_cache", None)      # batch.likelihood_sharded's device / pinned buffers
