@@ -24,4 +24,5 @@ capture k1 k_multipoles 1 profile_target.py --passes 3
 capture disp k_multipoles 1 profile_target.py --passes 3 --batch 16384 --rsd dispersion --theory 0
 capture aniso k_multipoles 1 profile_target.py --passes 3 --batch 16384 --aniso 1 --theory 0
 capture small k_small 3 small_call_target.py
+capture k2 k_chi2 1 profile_target.py --passes 3
 cut -c1-400 gpurun_out/bench.json
