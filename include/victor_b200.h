@@ -29,6 +29,9 @@
  *     the host buffers.  With device pointers only, the call is asynchronous on `stream`
  *     (a cudaStream_t, or NULL for the legacy default stream) and the caller synchronises.
  *   - A context belongs to one GPU and is not re-entrant; distinct contexts are independent.
+ *     Its scratch buffers (staging, theory vectors, the one-launch kernel's tickets) are shared by
+ *     all of its calls: asynchronous calls on ONE context must go to one stream at a time (or be
+ *     ordered by events); use one context per stream / host thread for concurrent work.
  *   - Per-row numerical failure (NaN anywhere in the row) gives lnlike = -inf, chi2 = +inf,
  *     as the reference does (victor/ccf_fit.py:477-481).
  */
