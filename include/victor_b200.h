@@ -153,6 +153,8 @@ void vb200_destroy(vb200_ctx *ctx);
  *   "threads"    block size of the batch kernels (32..256), "nsplit" blocks per parameter row (0 = automatic)
  *   "fuse"       chi2 / lnL in the epilogue of the theory kernel when one block owns a row: 0 never, 1 where measured
  *                faster (default), 2 always
+ *   "bucket"     chi2 kernel of batches of 4096 rows and more: rows grouped by covariance bracket first, both precision
+ *                matrices of a group served from shared memory (1 = default; 0 = every row streams its own matrix)
  *   "tiny"       calls of one or two rows through the one-launch kernel k_small (1 = default)
  *   "mapped"     k_small writes its results into mapped page-locked host memory and the host polls a flag (1 = default)
  *   "graph"      replay calls of up to 256 host rows as one CUDA graph (1 = default)

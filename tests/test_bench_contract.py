@@ -70,7 +70,7 @@ def test_gpu_arm_line():
     assert d["unit"] == "evals/s" and d["n_gpus"] == 1 and d["steps"] == 2 and d["scaling"] == "weak"
     assert d["dtype"] == "f64" and d["data"] == "synthetic" and d["vs_baseline"] is None
     assert "BOSS DR12 CMASS" in d["config"]["workload"] and "l2" in d["config"]
-    assert d["value"] > 1e6 and d["gpu_launches"] == 4                    # K1 + K2 per step
+    assert d["value"] > 1e6 and d["gpu_launches"] == 8                    # K1 + K2 (bracket count, scatter, chi2) per step
     x = d["extra"]
     for name in ("dispersion", "dense_sweep", "mcmc", "strong_64k"):
         assert x[name]["value"] > 0, name

@@ -260,6 +260,61 @@ def test_fused_likelihood_epilogue_is_bit_identical(fit):
         eng.set_option("tuned", 1)
 
 
+def test_bucketed_chi2_is_bit_identical(fit, boss_blocks):
+    """K2 of large batches groups the rows by covariance bracket (count, scatter, k_chi2_bucketed: both precision
+    matrices of a group in shared memory, two rows per fetched element).  chi2 and lnL equal those of the row-by-row
+    kernel ("bucket" 0) bit for bit -- on rows of every kind (beta on a grid value, outside the grid at both ends,
+    NaN), for sizes around the tile and threshold edges, for every likelihood form, and with ONE fixed covariance."""
+    from victor_b200 import CCFFit
+    rng = np.random.default_rng(23)
+
+    def table(n, grid):
+        P = np.column_stack([rng.uniform(0.05, 1.5, n), rng.uniform(0.1, 0.7, n), rng.uniform(100, 500, n),
+                             rng.uniform(0.9, 1.1, n), rng.uniform(0.9, 1.1, n)])
+        P[3, 1] = np.nan
+        P[4:36, 1] = grid[:32] if len(grid) >= 32 else grid[0]            # exactly on grid values
+        P[40, 1], P[41, 1] = grid[0] - 0.01, grid[-1] + 0.01              # beyond both ends
+        P[50:80, 1] = 0.3011                                              # one crowded bracket next to empty ones
+        return P
+
+    grid = np.asarray(fit.beta_covmat if hasattr(fit, "beta_covmat") else fit.beta_ccf, dtype=float)
+    eng, _ = fit._fit_engine({})
+    for n in (4096, 4097, 4127, 20000):
+        P = table(n, grid)
+        out = {}
+        for bucket in (0, 1):
+            eng.set_option("bucket", bucket)
+            before = eng.launch_count()
+            out[bucket] = fit.log_likelihood_batch(P)
+            assert eng.launch_count() - before == (4 if bucket else 2)         # K1 + (count, scatter,) chi2
+        eng.set_option("bucket", 1)
+        assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]), n
+        assert out[1][0][3] == -np.inf and out[1][1][3] == np.inf
+        again = fit.log_likelihood_batch(P)                                    # whatever order the scatter produced
+        assert np.array_equal(again[0], out[1][0]) and np.array_equal(again[1], out[1][1])
+    P = table(6000, grid)
+    for form in ("gaussian", "hartlap", "percival", "sellentin"):
+        like = {"form": form, "nmocks": 1000, "nparams": 4}
+        e2, _ = fit._fit_engine({"likelihood": like})
+        res = {}
+        for bucket in (0, 1):
+            e2.set_option("bucket", bucket)
+            res[bucket] = fit.log_likelihood_batch(P, likelihood=like)
+        e2.set_option("bucket", 1)
+        assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1]), form
+    model, data = copy.deepcopy(boss_blocks[0]), copy.deepcopy(boss_blocks[1])
+    data["covariance_matrix"] = {"data_file": "data/boss_dr12_cmass/cmass_fixed_D_covariance.npz",
+                                 "cov_key": "covmat", "fixed_beta": True}
+    ffix = CCFFit(model, data)
+    e3, _ = ffix._fit_engine({})
+    res = {}
+    for bucket in (0, 1):
+        e3.set_option("bucket", bucket)
+        res[bucket] = ffix.log_likelihood_batch(P)
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    ffix.close()
+
+
 def test_small_calls_replayed_as_graph(fit, golden):
     """MCMC-sized calls (host rows, n <= 256) go through a captured CUDA graph; changing n or an option
     rebuilds it; results equal the plain submissions bit for bit and the golden values.  (Calls of up to two

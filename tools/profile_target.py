@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--rsd", default="streaming", help="rsd_model (general kernel for anything but streaming)")
     ap.add_argument("--aniso", type=int, default=0, help="1: assume_isotropic False")
     ap.add_argument("--tuned", type=int, default=1, help="0: force the general kernel")
+    ap.add_argument("--bucket", type=int, default=1, help="0: K2 row by row (k_chi2) instead of grouped by covariance bracket")
     args = ap.parse_args()
     model, data = boss_blocks()
     fit = CCFFit(model, data, device=0)
@@ -51,6 +52,7 @@ def main():
         eng.set_option("newton", args.newton)
     eng.set_option("fuse", args.fuse)
     eng.set_option("tuned", args.tuned)
+    eng.set_option("bucket", args.bucket)
     n = args.batch
     dev = torch.device("cuda", 0)
     rows = params_to_rows(synthetic_batch(n))
@@ -69,7 +71,7 @@ def main():
         b.record()
         torch.cuda.synchronize()
         times.append(a.elapsed_time(b))
-    print(f"batch={n} fast={args.fast} threads={args.threads} nsplit={args.nsplit} ilp={args.ilp} expdeg={args.expdeg} newton={args.newton} fuse={args.fuse} theory={args.theory} sigma_v={args.sigma_v} rsd={args.rsd} aniso={args.aniso} tuned={args.tuned} lib={os.path.basename(os.environ.get('VICTOR_B200_LIB', 'default'))} "
+    print(f"batch={n} fast={args.fast} threads={args.threads} nsplit={args.nsplit} ilp={args.ilp} expdeg={args.expdeg} newton={args.newton} fuse={args.fuse} theory={args.theory} sigma_v={args.sigma_v} rsd={args.rsd} aniso={args.aniso} tuned={args.tuned} bucket={args.bucket} lib={os.path.basename(os.environ.get('VICTOR_B200_LIB', 'default'))} "
           f"ms={['%.3f' % t for t in times]} evals/s={n / (min(times) * 1e-3):.4g} "
           f"chi2[0]={float(d_chi2[0]):.10f} "
           f"digest={__import__('hashlib').sha1(d_theory.cpu().numpy().tobytes() + d_chi2.cpu().numpy().tobytes()).hexdigest()[:12]}")

@@ -28,6 +28,7 @@ thread_local std::string g_err;
 #ifdef VB200_SMALL_TIMING
 unsigned long long *g_stamps = nullptr;   // diagnostic build only
 #endif
+constexpr int64_t kBucketMinRows = 4096;   // K2: from this many rows on, group the rows by covariance bracket first
 constexpr int64_t kSmallCall = 256;   // rows: calls up to this size go through pinned staging
 
 int fail(int code, const std::string &msg) {
@@ -107,12 +108,13 @@ struct vb200_ctx {
     int fit_ns = 0, fit_nmu = 0, fit_L = 0;
     double *fit_s = nullptr, *fit_mu = nullptr, *fit_sqmu = nullptr, *fit_wmu = nullptr;
     std::vector<void *> owned;
-    Scratch sc_params, sc_theory, sc_chi2, sc_lnl, sc_xi, sc_mult, sc_grid;
+    Scratch sc_params, sc_theory, sc_chi2, sc_lnl, sc_xi, sc_mult, sc_grid, sc_bucket;
     // options
     int opt_fast = 1, opt_nsplit = 0, opt_threads = 256, opt_ilp = 4;
     int opt_expdeg = 0, opt_newton = 0;   // 0 = the kernel family's default (kDefExp / kDefNewton; dispersion: cubic)
     int opt_fuse = 1;             // batch mode: chi2 / lnL in the epilogue of K1 instead of a K2 launch
     int opt_tuned = 1;            // 0: force the general kernel (A/B checks of the tuned kernels)
+    int opt_bucket = 1;           // K2 of large batches: rows grouped by covariance bracket, matrices served from shared memory
     int opt_tiny = 1;             // calls of <= kSmallRows rows: one launch of k_small instead of K1 + K2 (0: off)
     int opt_mapped = 1;           // k_small writes (chi2 | lnL) straight into page-locked host memory and raises a flag
                                   // the host polls, and takes its one or two rows from the kernel parameters: one
@@ -320,6 +322,17 @@ int launch_k2(vb200_ctx *c, const double *d_params, const double *d_theory, long
     a.n = n;
     a.chi2 = d_chi2;
     a.lnl = d_lnl;
+    // large batches: rows grouped by covariance bracket first (k_chi2_bucketed); "bucket" 0 keeps k_chi2
+    const int nb = c->fd.cov_fixed ? 1 : c->fd.nbeta_cov;
+    if (c->opt_bucket && n >= kBucketMinRows && n <= 2147483647LL && k2_stages(c->fd.p) && nb <= kK2MaxBins) {
+        const size_t words = (size_t)n + ((size_t)n + 3) / 4 + 2 * kK2MaxBins;   // order | lo8 | bins, in 4-byte words
+        int rc = c->sc_bucket.ensure((words + 1) / 2);
+        if (rc) return rc;
+        a.order = reinterpret_cast<int *>(c->sc_bucket.ptr);
+        a.bins = reinterpret_cast<unsigned *>(a.order + n);
+        a.lo8 = reinterpret_cast<unsigned char *>(a.bins + 2 * kK2MaxBins);
+        c->launches += 2;   // count + scatter in front of the chi-square kernel
+    }
     CK(launch_k2_kernels(a, n, c->sm_count, st));
     CK(cudaGetLastError());
     c->launches++;
@@ -527,6 +540,7 @@ void vb200_destroy(vb200_ctx *c) {
     c->sc_xi.release();
     c->sc_mult.release();
     c->sc_grid.release();
+    c->sc_bucket.release();
     if (c->small_exec) cudaGraphExecDestroy(c->small_exec);
     if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -724,6 +738,7 @@ int vb200_set_option(vb200_ctx *c, const char *key, int64_t value) {
     else if (!strcmp(key, "fuse")) c->opt_fuse = (int)std::max<int64_t>(0, std::min<int64_t>(value, 2));
     else if (!strcmp(key, "tuned")) c->opt_tuned = value ? 1 : 0;
     else if (!strcmp(key, "tiny")) c->opt_tiny = value ? 1 : 0;
+    else if (!strcmp(key, "bucket")) c->opt_bucket = value ? 1 : 0;
     else if (!strcmp(key, "mapped")) c->opt_mapped = value ? 1 : 0;
     else if (!strcmp(key, "newton")) {
         if (value != 0 && value != 2 && value != 3)

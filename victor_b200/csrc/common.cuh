@@ -64,12 +64,18 @@ struct K1Args {
     double *chi2, *lnl;   // [n] each, either may be null
 };
 
+constexpr int kK2MaxBins = 64;   // brackets the bucketed K2 can tell apart (nbeta_cov <= 64)
+
 struct K2Args {
     FitDev f;
     const double *params;
     const double *theory;  // [n][p]
     long long n;
     double *chi2, *lnl;    // either may be null
+    // bucketed form (k2_chi2.cuh: k_chi2_bucketed): rows grouped by their lower covariance bracket
+    int *order;            // [n] row indices, bucket after bucket; null = not bucketed
+    unsigned char *lo8;    // [n] lower bracket of every row
+    unsigned *bins;        // [2 * kK2MaxBins]: rows per bracket | scatter cursors (zero before the launch sequence)
 };
 
 // ---------------------------------------------------------------------------------------

@@ -57,13 +57,6 @@ __host__ __device__ inline size_t small_smem_bytes(int ncell, int nbucket, int p
     return d * sizeof(double) + (size_t)nbucket * sizeof(int);
 }
 
-// interval k with grid[k] <= b < grid[k+1], clamped (beta_interval of common.cuh) with the grid values spread
-// over the lanes of a warp: one round of loads instead of a serial scan (n <= 33)
-__device__ __forceinline__ int beta_interval_warp(const double *grid, int n, double b, int lane) {
-    const bool ge = (lane >= 1 && lane < n - 1) ? (b >= grid[lane]) : false;
-    return __popc(__ballot_sync(0xffffffffu, ge));
-}
-
 // cov_bracket of k2_chi2.cuh, grid over the lanes (nbeta_cov <= 32); same conventions, same results
 __device__ __forceinline__ void cov_bracket_warp(const FitDev &f, double beta, int lane, int &lo, int &hi, double &w) {
     lo = hi = 0;

@@ -57,10 +57,84 @@ __device__ __forceinline__ double quad_partial(const double *M, const double *re
     }
 }
 
+// The same partial sums for FOUR residual vectors against one matrix (k_chi2_bucketed): every matrix element is fetched
+// once and used four times.  `res4` holds the four vectors interleaved ([i][4]: two 16-byte broadcast loads per matrix
+// row), `own[r][c]` is res_r[lane + 32 c] in registers.  Each row's operations and their order are those of
+// quad_partial_t / quad_form: bit-identical results.
+// shared-memory loads of data written earlier in the same kernel (ordered after the barrier by the memory clobber;
+// the plain lds_f64 of common.cuh is for tables that never change once the kernel's main loop runs)
+__device__ __forceinline__ double2 lds_f64x2_ordered(unsigned addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ double lds_f64_ordered(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+template <int kC>
+__device__ __forceinline__ void quad_form4_t(unsigned m_s, unsigned res_s, const double (&own)[4][kC], int p, int lane,
+                                             double (&q)[4]) {
+    // m_s / res_s: shared-window addresses of the matrix and of the interleaved residuals: the loop below advances two
+    // 32-bit addresses and nothing else
+    bool has[kC];
+#pragma unroll
+    for (int c = 0; c < kC; ++c) has[c] = lane + 32 * c < p;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) q[r] = 0.0;
+    const unsigned rowstep = 8u * (unsigned)p * kK2Warps;
+    for (int part = 0; part < kK2Warps; ++part) {
+        double y[4][kC];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < kC; ++c) y[r][c] = 0.0;
+        unsigned ma = m_s + 8u * ((unsigned)part * p + lane), ra = res_s + 32u * part;
+#pragma unroll 4
+        for (int i = part; i < p; i += kK2Warps, ma += rowstep, ra += 32u * kK2Warps) {
+            const double2 r01 = lds_f64x2_ordered(ra), r23 = lds_f64x2_ordered(ra + 16);
+#pragma unroll
+            for (int c = 0; c < kC; ++c) {
+                if (has[c]) {
+                    const double m = lds_f64_ordered(ma + 256u * c);
+                    y[0][c] = fma(m, r01.x, y[0][c]);
+                    y[1][c] = fma(m, r01.y, y[1][c]);
+                    y[2][c] = fma(m, r23.x, y[2][c]);
+                    y[3][c] = fma(m, r23.y, y[3][c]);
+                }
+            }
+        }
+        double t[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            t[r] = 0.0;
+#pragma unroll
+            for (int c = 0; c < kC; ++c)
+                if (has[c]) t[r] = fma(y[r][c], own[r][c], t[r]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {   // four butterflies side by side (each one is warp_sum's)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) t[r] += __shfl_xor_sync(0xffffffffu, t[r], o);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) q[r] += t[r];
+    }
+}
+
 __device__ __forceinline__ double quad_form(const double *M, const double *res, int p, int lane) {
     double q = 0.0;
     for (int part = 0; part < kK2Warps; ++part) q += quad_partial(M, res, p, lane, part);
     return q;
+}
+
+// interval k with grid[k] <= b < grid[k+1], clamped (beta_interval of common.cuh) with the grid values spread
+// over the lanes of a warp: one round of loads instead of a serial scan (n <= 33)
+__device__ __forceinline__ int beta_interval_warp(const double *grid, int n, double b, int lane) {
+    const bool ge = (lane >= 1 && lane < n - 1) ? (b >= grid[lane]) : false;
+    return __popc(__ballot_sync(0xffffffffu, ge));
 }
 
 // data vector at beta: PCHIP power table (ccf_fit.py:193, 322-323, 350)
@@ -73,6 +147,17 @@ struct DataAt {
         td = 0.0;
         if (f.data_beta_dependent) {
             kd = beta_interval(f.beta_ccf, f.nbeta_ccf, beta);
+            td = beta - f.beta_ccf[kd];
+        }
+        dt = f.data_tab + (size_t)kd * 4 * p;
+    }
+    // the same with the interval found by the whole warp (beta_interval_warp: same interval, one round of loads)
+    __device__ __forceinline__ DataAt(const FitDev &f, double beta, int lane) : p(f.p) {
+        int kd = 0;
+        td = 0.0;
+        if (f.data_beta_dependent) {
+            kd = f.nbeta_ccf <= 33 ? beta_interval_warp(f.beta_ccf, f.nbeta_ccf, beta, lane)
+                                   : beta_interval(f.beta_ccf, f.nbeta_ccf, beta);
             td = beta - f.beta_ccf[kd];
         }
         dt = f.data_tab + (size_t)kd * 4 * p;
@@ -112,8 +197,24 @@ __device__ __forceinline__ void cov_bracket(const FitDev &f, double beta, int &l
     }
 }
 
+// cov_bracket for a row whose lower bracket `lo` is already known (the bucketed kernel: lo is the tile's bracket):
+// the remaining case analysis of cov_bracket on three grid values -- same hi, same w
+__device__ __forceinline__ void bracket_from_lo(const FitDev &f, double beta, int lo, double g0, double glo, double glast,
+                                                int &hi, double &w) {
+    hi = lo;
+    w = 0.0;
+    if (f.cov_fixed) return;
+    if (beta != beta) {   // NaN: cov_bracket leaves lo = hi = 0 and hands the NaN on
+        w = beta;
+        return;
+    }
+    if (beta < g0 || beta > glast || glo == beta) return;   // outside the grid: the end matrix; on a grid value: that matrix
+    hi = f.nbeta_cov - 1;
+    w = (beta - glo) / (glast - glo);
+}
+
 __device__ __forceinline__ double blend_chi2(double qlo, double qhi, int lo, int hi, double w) {
-    if (hi != lo) return (1.0 - w) * qlo + w * qhi;
+    if (hi != lo) return fma(1.0 - w, qlo, w * qhi);   // written out: every kernel form must round this the same way
     return (w != w) ? w : qlo;
 }
 
@@ -153,6 +254,14 @@ constexpr int kK2StageMaxP = 64;   // p x p doubles must fit beside the residual
 __host__ __device__ inline bool k2_stages(int p) { return p <= kK2StageMaxP; }
 __host__ __device__ inline size_t k2_smem_bytes(int p) {
     return ((size_t)kK2Warps * p + (k2_stages(p) ? (size_t)p * p : 0)) * sizeof(double);
+}
+
+// Bucketed form: rows sorted by lower bracket (k_bracket_count / k_bracket_scatter), then a block takes kK2TileRows
+// rows of ONE bracket and keeps both of their precision matrices (and the bracket's eigenvalue row) in shared memory.
+constexpr int kK2TileRows = 32;    // rows per block: 4 per warp, taken together
+__host__ __device__ inline size_t k2_bucket_smem_bytes(int p) {
+    const size_t pe = (size_t)((p + 1) & ~1), pp = ((size_t)p * p + 1) & ~(size_t)1;
+    return (2 * pp + pe + (size_t)kK2Warps * 4 * pe) * sizeof(double);
 }
 
 // doubles of shared memory the fused epilogue needs: the theory / residual vector and the per-warp
