@@ -651,7 +651,7 @@ def run_gpu(args):
                 roofline["traffic"] = json.load(fh).get("dram_bytes_per_launch")
         # what the committed `ncu --set full` capture of this kernel says limits it (static figures from profiles/,
         # not measured in this run): the FP64 pipe and the shared-memory crossbar together
-        prof = os.path.join(ROOT, "profiles", "r02y_k_multipoles_streaming_ncu.json")
+        prof = os.path.join(ROOT, "profiles", "r02zb_k_multipoles_streaming_ncu.json")
         if os.path.isfile(prof):
             with open(prof) as fh:
                 cap = json.load(fh)
@@ -663,7 +663,7 @@ def run_gpu(args):
                 except (ValueError, IndexError):
                     return None
             roofline["ncu_capture"] = {
-                "source": "profiles/r02y_k_multipoles_streaming_ncu.json",
+                "source": "profiles/r02zb_k_multipoles_streaming_ncu.json",
                 "fp64_pipe_pct_of_peak": pct("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed"),
                 "smem_wavefronts_pct_of_peak": pct("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
                 "issue_slots_pct": pct("smsp__issue_active.avg.pct_of_peak_sustained_active"),

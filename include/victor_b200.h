@@ -149,8 +149,10 @@ void vb200_destroy(vb200_ctx *ctx);
  *   "tuned"      1 = tuned kernels where they apply (default), 0 = always the general kernel
  *   "newton"     refinement of the MUFU seeds in the tuned streaming kernel: 2 = one Newton step (default), 3 = cubic step
  *   "exp_degree" 5 = degree-5 remainder polynomial on a 32-entry table (default), 3 = degree 3 on a 1024-entry table
- *   "ilp"        velocity nodes per loop trip, 4 (default) or 1
- *   "threads"    block size of the batch kernels (32..256), "nsplit" blocks per parameter row (0 = automatic)
+ *   "ilp"        velocity nodes per loop trip: 0 = the kernel's default (10 streaming, 8 dispersion), 4 or 1 = the older
+ *                variants (measurement)
+ *   "threads"    block size of the batch kernels: 0 = automatic (128 tuned kernels, 256 general kernel) or 32..256;
+ *                "nsplit" blocks per parameter row (0 = automatic)
  *   "fuse"       chi2 / lnL in the epilogue of the theory kernel when one block owns a row: 0 never, 1 where measured
  *                faster (default), 2 always
  *   "bucket"     chi2 kernel of batches of 4096 rows and more: rows grouped by covariance bracket first, both precision

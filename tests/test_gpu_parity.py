@@ -102,13 +102,13 @@ def test_boss_streaming_golden(fit, golden, fast):
     np.testing.assert_allclose(lnl, g["lnl"], rtol=0, atol=CHI2_ATOL)
 
 
-@pytest.mark.parametrize("opts", [{"ilp": 1}, {"exp_degree": 5, "newton": 3}, {"exp_degree": 5, "newton": 2},
-                                  {"exp_degree": 3, "newton": 2}, {"threads": 128}, {"threads": 64}])
+@pytest.mark.parametrize("opts", [{"ilp": 1}, {"ilp": 4}, {"exp_degree": 5, "newton": 3}, {"exp_degree": 5, "newton": 2},
+                                  {"exp_degree": 3, "newton": 2}, {"threads": 256}, {"threads": 64}])
 def test_kernel_variants_hold_parity(fit, golden, opts):
     """Every tuning variant of K1 must meet the same bar as the default."""
     g = golden("boss_streaming_points")
     eng, _ = fit._fit_engine({})
-    defaults = {"ilp": 4, "exp_degree": 0, "threads": 256, "newton": 0}      # 0 = the library's default
+    defaults = {"ilp": 0, "exp_degree": 0, "threads": 0, "newton": 0}        # 0 = the library's default
     try:
         for k, v in opts.items():
             eng.set_option(k, v)

@@ -41,7 +41,7 @@ for kw in ({}, {"rsd_model": "dispersion"}, {"assume_isotropic": False}):
     else:
         variants = [{"fast_math": 0}, {"tuned": 0}, {"tuned": 1}]
     for opts in variants:
-        for k, v in {"fast_math": 1, "ilp": 4, "tuned": 1, "newton": 0, "exp_degree": 0, **opts}.items():
+        for k, v in {"fast_math": 1, "ilp": 0, "tuned": 1, "newton": 0, "exp_degree": 0, **opts}.items():
             eng.set_option(k, v)
         out = {"model": kw or "streaming", "variant": opts}
         if not kw:

@@ -21,9 +21,9 @@ def main():
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--passes", type=int, default=3)
     ap.add_argument("--fast", type=int, default=1)
-    ap.add_argument("--threads", type=int, default=256)
+    ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--nsplit", type=int, default=0)
-    ap.add_argument("--ilp", type=int, default=4)
+    ap.add_argument("--ilp", type=int, default=0)
     ap.add_argument("--expdeg", type=int, default=None)
     ap.add_argument("--newton", type=int, default=None)
     ap.add_argument("--fuse", type=int, default=1, help="1: chi2 / lnL in the K1 epilogue; 0: separate K2 launch")

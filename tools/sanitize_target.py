@@ -26,7 +26,7 @@ for opt in ({"fast_math": 0}, {"ilp": 1}, {"newton": 2}, {"nsplit": 7}):
     for k, v in opt.items():
         eng.set_option(k, v)
     print(opt, fit.log_likelihood_batch(P)[1])
-for k, v in (("fast_math", 1), ("ilp", 4), ("newton", 3), ("nsplit", 0)):
+for k, v in (("fast_math", 1), ("ilp", 0), ("newton", 3), ("nsplit", 0)):
     eng.set_option(k, v)
 # batch mode (one block per row): separate K2, then the fused epilogue in the tuned and the general kernels
 rng = np.random.default_rng(4)

@@ -110,7 +110,9 @@ struct vb200_ctx {
     std::vector<void *> owned;
     Scratch sc_params, sc_theory, sc_chi2, sc_lnl, sc_xi, sc_mult, sc_grid, sc_bucket;
     // options
-    int opt_fast = 1, opt_nsplit = 0, opt_threads = 256, opt_ilp = 4;
+    int opt_fast = 1, opt_nsplit = 0;
+    int opt_threads = 0;          // 0 = automatic: 128-thread blocks for the tuned kernels, 256 for the general one
+    int opt_ilp = 0;              // 0 = the kernel family's default number of nodes per trip; 4 and 1 select the older variants
     int opt_expdeg = 0, opt_newton = 0;   // 0 = the kernel family's default (kDefExp / kDefNewton; dispersion: cubic)
     int opt_fuse = 1;             // batch mode: chi2 / lnL in the epilogue of K1 instead of a K2 launch
     int opt_tuned = 1;            // 0: force the general kernel (A/B checks of the tuned kernels)
@@ -264,7 +266,8 @@ int launch_k1(vb200_ctx *c, const double *d_params, long long n, const double *d
     while (jper > 1 && smem_for(jper) > want) jper = (jper + 1) / 2;
     nsplit = (ns + jper - 1) / jper;
     const int npairs = jper * nmu;
-    int threads = std::min(c->opt_threads, ((npairs + 31) / 32) * 32);
+    const int threads_opt = c->opt_threads > 0 ? c->opt_threads : (fam != kGeneral ? 128 : 256);
+    int threads = std::min(threads_opt, ((npairs + 31) / 32) * 32);
     threads = std::max(32, std::min(threads, 256));
     const size_t smem = smem_for(jper);
     if (smem > c->k1_smem_limit)
@@ -342,7 +345,7 @@ int launch_k2(vb200_ctx *c, const double *d_params, const double *d_theory, long
 // does a likelihood call of n rows go through k_small?  (tuned kernel families with their default math only)
 bool use_small(const vb200_ctx *c, long long n) {
     return c->opt_tiny && c->has_fit && n >= 1 && n <= kSmallRows && c->opt_fast && kernel_family(c) != kGeneral &&
-           c->opt_ilp >= 4 && !c->opt_expdeg && !c->opt_newton && c->opt_nsplit <= 0 &&
+           (c->opt_ilp == 0 || c->opt_ilp >= 4) && !c->opt_expdeg && !c->opt_newton && c->opt_nsplit <= 0 &&
            small_smem_bytes(c->md.ncell, c->md.nbucket, c->fd.p, rec_doubles(c), big_table(kDefExp) ? kExpTabBig : kExpTab) <=
                c->k1_smem_limit;
 }
@@ -744,13 +747,14 @@ int vb200_set_option(vb200_ctx *c, const char *key, int64_t value) {
         if (value != 0 && value != 2 && value != 3)
             return fail(VB200_EINVAL, "newton must be 0 (default), 2 (one Newton step) or 3 (cubic step)");
         c->opt_newton = (int)value;
-    } else if (!strcmp(key, "ilp")) c->opt_ilp = value >= 4 ? 4 : (value >= 2 ? 2 : 1);
+    } else if (!strcmp(key, "ilp")) c->opt_ilp = value <= 0 ? 0 : (value >= 10 ? 10 : (value >= 4 ? 4 : 1));
     else if (!strcmp(key, "exp_degree")) {
         if (value != 0 && value != 5 && value != 3)
             return fail(VB200_EINVAL, "exp_degree must be 0 (default), 5 or 3 (1024-entry table, degree-3 remainder)");
         c->opt_expdeg = (int)value;
     } else if (!strcmp(key, "threads")) {
-        if (value < 32 || value > 256 || value % 32) return fail(VB200_EINVAL, "threads must be 32..256, multiple of 32");
+        if (value != 0 && (value < 32 || value > 256 || value % 32))
+            return fail(VB200_EINVAL, "threads must be 0 (automatic) or 32..256, multiple of 32");
         c->opt_threads = (int)value;
     } else
         return fail(VB200_EINVAL, std::string("unknown option ") + key);

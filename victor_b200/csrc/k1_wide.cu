@@ -9,14 +9,16 @@ namespace vb200 {
 // models is the general kernel).
 // (the dispersion model keeps the cubic refinement whatever the streaming default is: its coordinate iteration
 // amplifies seed errors, see k1_streaming.cuh: disp_nodes)
+// Nodes per trip / register budget of the two BOSS-shaped instantiations as measured (profiles/r02za_variants_ilp_blocks.txt);
+// the rarer ones (three multipoles, tables with bucket flags) keep four nodes at 64 registers.
 template <bool kFlags>
 k1_fn k1_wide_variant(int rsd_model, int n_ell) {
     if (rsd_model == kRsdDispersion) {
-        if (n_ell == 1) return k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, 3, kRsdDispersion, 1>>;
+        if (n_ell == 1) return k_multipoles<K1Cfg<true, kFlags, 8, kDefExp, 3, kRsdDispersion, 1, 2>>;   // 128 registers: 25.47 vs 25.90 ms
         if (n_ell == 2) return k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, 3, kRsdDispersion, 2>>;
         return k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, 3, kRsdDispersion, 3>>;
     }
-    if (n_ell == 2) return k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, kDefNewton, kRsdStreaming, 2>>;
+    if (n_ell == 2) return k_multipoles<K1Cfg<true, kFlags, 10, kDefExp, kDefNewton, kRsdStreaming, 2, 3>>;   // 80 registers: 8.47 vs 8.59 ms
     return k_multipoles<K1Cfg<true, kFlags, 4, kDefExp, kDefNewton, kRsdStreaming, 3>>;
 }
 
