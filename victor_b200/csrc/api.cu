@@ -345,6 +345,7 @@ int launch_k2(vb200_ctx *c, const double *d_params, const double *d_theory, long
 // does a likelihood call of n rows go through k_small?  (tuned kernel families with their default math only)
 bool use_small(const vb200_ctx *c, long long n) {
     return c->opt_tiny && c->has_fit && n >= 1 && n <= kSmallRows && c->opt_fast && kernel_family(c) != kGeneral &&
+           c->fit_L * ((c->fit_nmu + kSmallPairs - 1) / kSmallPairs) <= c->fit_nmu &&   // the shares fit the scratch row
            (c->opt_ilp == 0 || c->opt_ilp >= 4) && !c->opt_expdeg && !c->opt_newton && c->opt_nsplit <= 0 &&
            small_smem_bytes(c->md.ncell, c->md.nbucket, c->fd.p, rec_doubles(c), big_table(kDefExp) ? kExpTabBig : kExpTab) <=
                c->k1_smem_limit;

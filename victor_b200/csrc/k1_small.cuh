@@ -37,7 +37,7 @@ struct SmallArgs {
 #ifdef VB200_SMALL_TIMING
     unsigned long long *stamps;
 #endif
-    double *xi_scratch;      // [n][ns][nmu]
+    double *xi_scratch;      // [n][ns * nmu] doubles per row; holds the blocks' projection shares [L][ns][nchunk]
     unsigned *tickets;       // [n], zero before the launch; the last block of a row resets its counter
     double *theory;          // [n][p] or null
     unsigned *done;          // [n] or null: host-mapped flags, set to 1 (after a system-scope fence) once a row's
@@ -91,8 +91,8 @@ __device__ __forceinline__ void cov_bracket_warp(const FitDev &f, double beta, i
 // the bracket from one round of lane-parallel loads, both precision matrices by asynchronous global-to-shared
 // copies (cp.async, no registers held), data-vector table and generalised eigenvalues into a few registers --
 // and arrives while the projection runs.  `mats`: 2 p^2 doubles of shared memory, 16-byte aligned.
-__device__ __forceinline__ void small_epilogue(const K1Args &a, const SmallArgs &sm, const double *xi_row, long long row,
-                                               double beta, double *th, double *mats, int tid, int nthr) {
+__device__ __forceinline__ void small_epilogue(const K1Args &a, const SmallArgs &sm, const double *part_row, int nchunk,
+                                               long long row, double beta, double *th, double *mats, int tid, int nthr) {
     const FitDev &f = a.f;
     const int p = f.p, ns = a.ns, nmu = a.nmu;
     const int warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
@@ -130,62 +130,14 @@ __device__ __forceinline__ void small_epilogue(const K1Args &a, const SmallArgs 
             lam1 = lane + 32 < p ? lam[lane + 32] : 1.0;
         }
     }
-    // projection: one warp per s_j, lane-strided FMAs + xor butterfly, exactly as write_outputs does
-    // (ccf_model.py:824-825, utils.py:45-56), then the theory vector l-major (:856-858).  The usual sizes
-    // (ns <= 32, nmu <= 128) take all their loads in one round first (same FMA order; padding adds exact zeros).
-    if (ns <= 4 * kK2Warps && nmu <= 128 && nwarp == kK2Warps) {
-        double wv[kMaxPoles][4], xv[4][4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int kk = lane + 32 * c;
-#pragma unroll
-            for (int l = 0; l < kMaxPoles; ++l) wv[l][c] = (l < a.L && kk < nmu) ? a.wmu[l * nmu + kk] : 0.0;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int jl = warp + kK2Warps * r;
-                xv[r][c] = (jl < ns && kk < nmu) ? __ldcg(xi_row + jl * nmu + kk) : 0.0;
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int jl = warp + kK2Warps * r;
-            if (jl < ns) {
-                double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    if (lane + 32 * c < nmu) {
-                        s0 = fma(wv[0][c], xv[r][c], s0);
-                        if (a.L > 1) s1 = fma(wv[1][c], xv[r][c], s1);
-                        if (a.L > 2) s2 = fma(wv[2][c], xv[r][c], s2);
-                    }
-                s0 = warp_sum(s0);
-                if (a.L > 1) s1 = warp_sum(s1);
-                if (a.L > 2) s2 = warp_sum(s2);
-                if (lane == 0) {
-                    th[jl] = s0;
-                    if (a.L > 1) th[ns + jl] = s1;
-                    if (a.L > 2) th[2 * ns + jl] = s2;
-                }
-            }
-        }
-    } else {
-        for (int jl = warp; jl < ns; jl += nwarp) {
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-            for (int kk = lane; kk < nmu; kk += 32) {
-                const double v = __ldcg(xi_row + jl * nmu + kk);
-                s0 = fma(a.wmu[kk], v, s0);
-                if (a.L > 1) s1 = fma(a.wmu[nmu + kk], v, s1);
-                if (a.L > 2) s2 = fma(a.wmu[2 * nmu + kk], v, s2);
-            }
-            s0 = warp_sum(s0);
-            if (a.L > 1) s1 = warp_sum(s1);
-            if (a.L > 2) s2 = warp_sum(s2);
-            if (lane == 0) {
-                th[jl] = s0;
-                if (a.L > 1) th[ns + jl] = s1;
-                if (a.L > 2) th[2 * ns + jl] = s2;
-            }
-        }
+    // projection: the blocks of the row left their shares w_l xi of every s_j (see k_small); add them in block order
+    // and lay the theory vector out l-major (ccf_model.py:856-858).  One round of loads.
+    for (int i = tid; i < a.L * ns; i += nthr) {
+        const double *pp = part_row + (size_t)i * nchunk;
+        double sum = 0.0;
+#pragma unroll 8
+        for (int c = 0; c < nchunk; ++c) sum += __ldcg(pp + c);
+        th[i] = sum;
     }
     __syncthreads();
     VB_STAMP(6);
@@ -299,6 +251,9 @@ __global__ void __launch_bounds__(kSmallPairs * kSmallLanes) k_small(const __gri
     const int k = kc * kSmallPairs + pair;
     const int npl = (nx + kSmallLanes - 1) / kSmallLanes;
     double acc = 0.0;
+    double wk[kMaxPoles];   // projection weights of this pair's mu_k: fetched now, used after the quadrature
+#pragma unroll
+    for (int l = 0; l < kMaxPoles; ++l) wk[l] = (l < a.L && k < nmu) ? a.wmu[l * nmu + k] : 0.0;
     if (k < nmu) {
         QuadCtx q;
         q.kappa = scal[3];
@@ -331,8 +286,25 @@ __global__ void __launch_bounds__(kSmallPairs * kSmallLanes) k_small(const __gri
     }
 #pragma unroll
     for (int o = kSmallLanes / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    double *xi_row = sm.xi_scratch + (size_t)row * ns * nmu;
-    if (l16 == 0 && k < nmu) xi_row[j * nmu + k] = acc - 1.0;   // ccf_model.py:690
+    // This block's share of the mu projection (ccf_model.py:690, :824-825, utils.py:45-56): w_l(mu_k) xi(s_j, mu_k) of
+    // its 16 pairs, added in pair order by one thread per multipole; the row's last block adds the shares of the
+    // nchunk blocks of every s_j in block order.  (The batch kernels add the same products lane-strided + butterfly:
+    // a few ulp of difference, like the node sums above.)
+    __shared__ double wxi[kMaxPoles][kSmallPairs];
+    if (l16 == 0) {
+        const double xi = acc - 1.0;
+#pragma unroll
+        for (int l = 0; l < kMaxPoles; ++l)
+            if (l < a.L) wxi[l][pair] = k < nmu ? wk[l] * xi : 0.0;
+    }
+    __syncthreads();
+    double *part_row = sm.xi_scratch + (size_t)row * ns * nmu;   // [L][ns][nchunk] shares (L nchunk <= nmu)
+    if (tid < a.L) {
+        double sum = 0.0;
+#pragma unroll
+        for (int q = 0; q < kSmallPairs; ++q) sum += wxi[tid][q];
+        part_row[((size_t)tid * ns + j) * nchunk + kc] = sum;
+    }
 
     // ---- ticket: the last block of this row finishes it ----
     __syncthreads();
@@ -349,7 +321,7 @@ __global__ void __launch_bounds__(kSmallPairs * kSmallLanes) k_small(const __gri
     __threadfence();
     if (tid == 0) sm.tickets[row] = 0;   // ready for the next launch (stream-ordered after this one)
 
-    small_epilogue(a, sm, xi_row, row, pr[1], th, mats, tid, nthr);
+    small_epilogue(a, sm, part_row, nchunk, row, pr[1], th, mats, tid, nthr);
     VB_STAMP(8);
 }
 
