@@ -116,3 +116,15 @@ def test_package_surface_mirrors_the_reference():
     cosmo = victor_b200.BackgroundCosmology({"Omega_m": 0.31})
     assert abs((1 + 0.57) / (100 * cosmo.Ez(0.57)) - iaH) < 1e-16       # ccf_model.py:44-45
     assert abs(cosmo.Om(0.0) - 0.31) < 1e-15 and np.allclose(cosmo.H([0.0, 0.57]), [67.5, 67.5 * cosmo.Ez(0.57)])
+
+
+def test_every_runtime_option_is_documented_in_the_header(repo_root):
+    """vb200_set_option's keys (api.cu) and the option list of include/victor_b200.h name the same set."""
+    import re
+    with open(os.path.join(repo_root, "victor_b200", "csrc", "api.cu")) as fh:
+        keys = set(re.findall(r'!strcmp\(key, "(\w+)"\)', fh.read()))
+    with open(os.path.join(repo_root, "include", "victor_b200.h")) as fh:
+        header = fh.read()
+    assert len(keys) >= 10
+    missing = sorted(k for k in keys if f'"{k}"' not in header)
+    assert not missing, f"options without a line in the header: {missing}"
